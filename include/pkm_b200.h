@@ -1,0 +1,169 @@
+/*
+ * pkm_b200.h - C ABI of the B200-native popkinmocks datacube hot path.
+ *
+ * Shared library: popkinmocks_b200/csrc/libpkm_b200.so  (built by `make -C popkinmocks_b200/csrc`
+ * or `__graft_entry__.build()`; nvcc -gencode arch=compute_100a,code=sm_100a).
+ *
+ * Every entry point replaces one piece of the reference's pure-Python hot path
+ * (reference = prashjet/popkinmocks v1.0.1; file:line relative to /root/reference):
+ *
+ *   pkm_ybar_density   <- Component.evaluate_ybar            popkinmocks/components/base.py:789-882
+ *   pkm_ybar_gaussian  <- ParametricComponent.evaluate_ybar  popkinmocks/components/parametric.py:335-407
+ *   pkm_axpy_cubes     <- Mixture.evaluate_ybar              popkinmocks/components/mixture.py:35-48
+ *   pkm_reduce_logp    <- Component._get_log_p_* marginals   popkinmocks/components/base.py:884-1174
+ *   pkm_moments        <- get_mean/get_noncentral_moment ... popkinmocks/components/base.py:179-452
+ *   pkm_noise          <- ShotNoise/ConstantSNR + Diagonal.sample  popkinmocks/noise.py:16-71
+ *   pkm_plan_create    <- the constant operands read from IFUCube / milesSSPs
+ *                         (ssps.FXw, par_dims, n_fft, dv, delta_t, delta_z; cube.dx, dy, v_edg)
+ *                         popkinmocks/ifu_cube.py:20-50, popkinmocks/model_grids.py:240-293
+ *
+ * Conventions
+ *   - plain C types only; all arrays are C-order float64 unless stated; complex = interleaved (re, im).
+ *   - bulk array arguments documented "host or device" are classified with
+ *     cudaPointerGetAttributes; host buffers are staged by the library (pinned
+ *     or pageable both work, pinned is faster).
+ *   - every function returns PKM_OK (0) or a negative pkm_status; pkm_last_error()
+ *     returns a thread-local message for the last failure.  No C++ exception crosses the ABI.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls with device buffers are asynchronous on `stream`; calls with any host
+ *     buffer return after the result is in the host buffer.
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points
+ *     return PKM_ERR_CUDA.
+ */
+#ifndef PKM_B200_H
+#define PKM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PKM_ABI_VERSION 1
+
+typedef enum pkm_status {
+  PKM_OK = 0,
+  PKM_ERR_INVALID = -1,   /* bad argument / shape / unsupported size */
+  PKM_ERR_CUDA = -2,      /* CUDA runtime error (message holds cudaGetErrorString) */
+  PKM_ERR_OOM = -3,       /* device or host allocation failed */
+  PKM_ERR_NO_ZERO_BIN = -4 /* density path needs a velocity bin centred on 0 (reference raises IndexError, base.py:822-823) */
+} pkm_status;
+
+/* Output layouts of the ybar entry points. */
+#define PKM_LAYOUT_CUBE 0      /* [n_fft][rows][nx2]  - the reference layout (omega slowest)      */
+#define PKM_LAYOUT_PIXEL_MAJOR 1 /* [rows*nx2][n_fft] - spaxel-major, used for the multi-GPU gather */
+
+/* Constant description of one (cube, ssps) pair.  Pixels are a batch dimension and
+ * are given per call, so one plan serves any nx1 x nx2 with the same grids. */
+typedef struct pkm_cube_desc {
+  int32_t nt;      /* number of SSP ages            (ssps.par_dims[1]) */
+  int32_t nz;      /* number of SSP metallicities   (ssps.par_dims[0]) */
+  int32_t nv;      /* number of velocity bins       (cube.nv)          */
+  int32_t n_fft;   /* ssps.n_fft (= len(ssps.w) with pad=False); any length, primes included */
+  int32_t v0_idx;  /* index of the velocity bin centred on 0 (base.py:842); -1 if there is none */
+  int32_t device;  /* CUDA device ordinal */
+  int32_t precision; /* 0 = float64 arithmetic (default); 1 = float32 arithmetic (inputs/outputs stay float64) */
+  int32_t reserved;
+  double dv;       /* ssps.dv  */
+  double dx, dy;   /* cube.dx, cube.dy */
+} pkm_cube_desc;
+
+typedef struct pkm_plan pkm_plan;
+
+const char* pkm_last_error(void);
+int32_t pkm_abi_version(void);
+/* Number of visible CUDA devices (0 without a GPU/driver; never fails). */
+int32_t pkm_device_count(void);
+
+/* Build the device-resident constant operands.
+ *   FXw      host, complex128 [n_fft/2+1][nz][nt]  (ssps.FXw reshaped, model_grids.py:277-281)
+ *   delta_t  host [nt], delta_z host [nz]
+ * Uploads S-hat' = FXw*dz*dt (density path) and FXw (Gaussian path) in kernel-friendly
+ * layouts, builds the not-a-knot spline tables, the folded DFT matrices, chirp-z tables. */
+int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw, const double* delta_t,
+                        const double* delta_z, pkm_plan** plan_out);
+int32_t pkm_plan_destroy(pkm_plan* plan);
+/* Cap the device workspace (bytes) used for intermediate spline coefficients; the
+ * pixel batch is tiled to fit.  0 restores the default (4 GiB). */
+int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes);
+/* Number of kernels launched by this plan since creation (for bench accounting). */
+int64_t pkm_plan_launch_count(const pkm_plan* plan);
+
+/* Density path.  dens: [nt][nv][nx1][nx2][nz] float64, host or device; is_log != 0 means
+ * it holds log p (exp is fused into the first kernel; -inf -> 0).  Rows [row_begin,row_end)
+ * of the x1 axis are evaluated (spatial sharding); ybar_out (host or device) receives
+ * (row_end-row_begin)*nx2*n_fft float64 in `out_layout`. */
+int32_t pkm_ybar_density(pkm_plan* plan, const double* dens, int32_t is_log, int32_t nx1,
+                         int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
+                         int32_t out_layout, void* stream);
+
+/* Gaussian-LOSVD path.  P_txz [nt][nx1][nx2][nz] (volume-weighted probabilities),
+ * mu_v / sig_v addressed as base[t*s[0] + x1*s[1] + x2*s[2]] with ELEMENT strides
+ * (0 strides allow numpy broadcast views, stream.py:126); omega [n_fft/2+1] is the
+ * reference's linspace(0, pi, nfo)/dv (parametric.py:360-362), host.  All of P_txz,
+ * mu_v, sig_v must be on the same side (all host or all device). */
+int32_t pkm_ybar_gaussian(pkm_plan* plan, const double* P_txz, const double* mu_v,
+                          const int64_t mu_strides[3], const double* sig_v,
+                          const int64_t sig_strides[3], const double* omega, int32_t nx1,
+                          int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
+                          int32_t out_layout, void* stream);
+
+/* out[i] = sum_c weights[c] * ybars[c][i], i < n.  ybars: host array of n_cmps pointers
+ * (all host or all device, same side as out); weights host. */
+int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
+                       int64_t n, double* out, int32_t device, void* stream);
+
+/* Spaxel-major [npix][n] -> cube layout [n][npix] (device pointers only). */
+int32_t pkm_transpose_to_cube(const double* pixel_major, int64_t npix, int64_t n, double* cube,
+                              int32_t device, void* stream);
+
+/* Batched inverse real FFT of arbitrary length (numpy.fft.irfft semantics, base.py:858):
+ * Yhat complex128 [npix][n_fft/2+1] device -> out float64 [npix][n_fft] device, times `scale`.
+ * Exposed for tests; pkm_ybar_* call the same kernels. */
+int32_t pkm_irfft_batch(pkm_plan* plan, const double* Yhat, int64_t npix, double scale,
+                        double* out, void* stream);
+/* O(n^2) inverse real DFT with exact integer phase reduction - independent cross-check. */
+int32_t pkm_irfft_naive(pkm_plan* plan, const double* Yhat, int64_t npix, double scale,
+                        double* out, void* stream);
+
+/* log-marginals of the pixelated density (base.py:884-1174, 1017-1041).
+ *   log_p_tvxz [nt][nv][npix][nz] host or device; log_dv host [nv] = log(velocity bin widths);
+ *   light_weights host [nt][nz] or NULL (mass-weighted);
+ *   keep_mask bit0=t bit1=v bit2=x bit3=z: axes kept in the output (others are
+ *   log-sum-exp'ed); out (same side as input) has the kept axes in t,v,x,z order.
+ *   Returns log P (volume weighted) if density == 0, else log density. */
+int32_t pkm_reduce_logp(pkm_plan* plan, const double* log_p_tvxz, int64_t npix,
+                        const double* log_dv, const double* light_weights, uint32_t keep_mask,
+                        int32_t density, double* out, void* stream);
+
+/* Moments of a conditional 1-D distribution held as probabilities P[nvar][ncond]
+ * (axis 0 = variable, base.py:208-260): out[0][c]=mean, out[1..3][c]= central moments 2,3,4.
+ * P, values[nvar], out[4][ncond]: host or device (same side). */
+int32_t pkm_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,
+                    double* out, int32_t device, void* stream);
+
+/* Observation noise (noise.py:16-71).  mode 0 = ShotNoise (sigma = sqrt(max ybar)/snr * sqrt(ybar)),
+ * mode 1 = ConstantSNR (sigma = ybar/snr).  yobs = ybar + N(0, sigma) (Philox counter RNG,
+ * seeded); sigma_out may be NULL.  ybar_max < 0 => the library reduces max(ybar) itself;
+ * otherwise it is used as given (multi-GPU: pass the all-reduced maximum).
+ * ybar, yobs, sigma_out: host or device (same side). */
+int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t mode, uint64_t seed,
+                  uint64_t offset, double ybar_max, double* yobs, double* sigma_out,
+                  int32_t device, void* stream);
+/* max over a device/host float64 buffer (NaN-propagating like numpy.max). */
+int32_t pkm_max(const double* x, int64_t n, double* result_host, int32_t device, void* stream);
+
+/* Host-only helpers (no GPU needed), exposed so the tables can be checked on CPU.
+ * Not-a-knot cubic spline nfi -> nfo on linspace(0,1,.) (base.py:846-853):
+ *   A_inv [nfi][nfi]; tap_idx [nfo] first coefficient of the 4-tap window; tap_w [nfo][4]. */
+int32_t pkm_spline_tables(int32_t nfi, int32_t nfo, double* A_inv, int32_t* tap_idx,
+                          double* tap_w);
+/* The folded matrices of the first density kernel: CR [nfi][nv/2+1], CI [nfi][(nv-1)/2] with
+ * c = CR * e + i * CI * o, e/o = even/odd parts of the rolled velocity profile. */
+int32_t pkm_fold_tables(int32_t nv, int32_t v0_idx, double dv, double* CR, double* CI,
+                        int32_t* idx_plus, int32_t* idx_minus);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PKM_B200_H */

@@ -1,0 +1,265 @@
+// Arbitrary-length batched inverse real FFT (numpy.fft.irfft semantics) for sm_100a.
+//
+// The reference calls np.fft.irfft(F_y, n_fft, axis=1) per (t,z) (base.py:858) or once per
+// pixel (parametric.py:373); n_fft = len(ssps.w) is whatever np.arange yields - 1992, 4907 =
+// 7*701, 1021 and 11069 (primes), ... - so a fixed-radix transform is not enough.
+//
+//   y[m] = (1/n) Re sum_{k<nfo} alpha_k Y'[k] e^{+2 pi i k m / n},     nfo = n/2+1
+//
+// (alpha = 1 for DC / Nyquist whose imaginary parts are ignored, 2 otherwise) is evaluated as
+// a chirp-z transform: k m = (k^2 + m^2 - (m-k)^2)/2, i.e. a length nfo+n-1 linear convolution
+// with the chirp chi[j] = e^{i pi j^2/n}, done with power-of-two FFTs of size M >= nfo+n-1.
+// One CTA per pixel; the M-point transforms run in place in shared memory (M <= 8192) or in a
+// CTA-private, L2-resident global scratch (larger n).  Forward = decimation in frequency,
+// inverse = its exact stage-by-stage inverse, so no bit-reversal pass is needed: the filter
+// spectrum is prepared once with the same forward routine (same permuted order).
+// Chirp phases are reduced exactly (j^2 mod 2n in integers) on the host.
+#include "pkm_internal.h"
+
+namespace {
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+  return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// forward DIF: natural order in, digit-permuted order out
+__device__ void fft_forward(double2* s, int M, int logM, const double2* __restrict__ tw) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  int Nb = M;
+  for (; Nb >= 4; Nb >>= 2) {
+    const int q = Nb >> 2, stride = M / Nb;
+    for (int i = tid; i < (M >> 2); i += nthr) {
+      const int j = i & (q - 1);
+      const int base = (i - j) * 4 + j;
+      double2 a = s[base], b = s[base + q], c = s[base + 2 * q], d = s[base + 3 * q];
+      double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
+      double2 t3 = make_double2(bd.y, -bd.x);  // -i (b - d)
+      double2 y0 = cadd(t0, t2), y1 = cadd(t1, t3), y2 = csub(t0, t2), y3 = csub(t1, t3);
+      s[base] = y0;
+      s[base + q] = cmul(y1, __ldg(tw + j * stride));
+      s[base + 2 * q] = cmul(y2, __ldg(tw + 2 * j * stride));
+      s[base + 3 * q] = cmul(y3, __ldg(tw + 3 * j * stride));
+    }
+    __syncthreads();
+  }
+  if (Nb == 2) {
+    for (int i = tid; i < (M >> 1); i += nthr) {
+      double2 a = s[2 * i], b = s[2 * i + 1];
+      s[2 * i] = cadd(a, b);
+      s[2 * i + 1] = csub(a, b);
+    }
+    __syncthreads();
+  }
+}
+
+// exact inverse of fft_forward up to the factor M: permuted order in, natural order out
+__device__ void fft_inverse(double2* s, int M, int logM, const double2* __restrict__ tw) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  int Nb = 4;
+  if (logM & 1) {
+    for (int i = tid; i < (M >> 1); i += nthr) {
+      double2 a = s[2 * i], b = s[2 * i + 1];
+      s[2 * i] = cadd(a, b);
+      s[2 * i + 1] = csub(a, b);
+    }
+    __syncthreads();
+    Nb = 8;
+  }
+  for (; Nb <= M; Nb <<= 2) {
+    const int q = Nb >> 2, stride = M / Nb;
+    for (int i = tid; i < (M >> 2); i += nthr) {
+      const int j = i & (q - 1);
+      const int base = (i - j) * 4 + j;
+      double2 y0 = s[base];
+      double2 y1 = cmulc(s[base + q], __ldg(tw + j * stride));
+      double2 y2 = cmulc(s[base + 2 * q], __ldg(tw + 2 * j * stride));
+      double2 y3 = cmulc(s[base + 3 * q], __ldg(tw + 3 * j * stride));
+      double2 u0 = cadd(y0, y2), u1 = csub(y0, y2), u2 = cadd(y1, y3), yd = csub(y1, y3);
+      double2 u3 = make_double2(-yd.y, yd.x);  // +i (y1 - y3)
+      s[base] = cadd(u0, u2);
+      s[base + q] = cadd(u1, u3);
+      s[base + 2 * q] = csub(u0, u2);
+      s[base + 3 * q] = csub(u1, u3);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_filter_spectrum(const double2* __restrict__ bfilt, double2* __restrict__ Bhat, int M, int logM,
+                  const double2* __restrict__ tw, double2* scratch) {
+  extern __shared__ double2 sbuf[];
+  double2* s = scratch ? scratch : sbuf;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s[i] = bfilt[i];
+  __syncthreads();
+  fft_forward(s, M, logM, tw);
+  for (int i = threadIdx.x; i < M; i += blockDim.x) Bhat[i] = s[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_irfft_czt(const double2* __restrict__ yhat, long long npix, int n, int nfo, int M, int logM,
+            double scale, const double2* __restrict__ chi, const double* __restrict__ alpha,
+            const double2* __restrict__ tw, const double2* __restrict__ Bhat,
+            double* __restrict__ out, double2* scratch) {
+  extern __shared__ double2 sbuf[];
+  double2* s = scratch ? scratch + (size_t)blockIdx.x * M : sbuf;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (long long x = blockIdx.x; x < npix; x += gridDim.x) {
+    const double2* yin = yhat + (size_t)x * nfo;
+    for (int k = tid; k < M; k += nthr) {
+      double2 v = make_double2(0.0, 0.0);
+      if (k < nfo) {
+        double2 a = yin[k];
+        const double al = alpha[k];
+        if (al == 1.0) a.y = 0.0;  // DC / Nyquist: imaginary part ignored (numpy c2r)
+        a.x *= al;
+        a.y *= al;
+        v = cmul(a, __ldg(chi + k));
+      }
+      s[k] = v;
+    }
+    __syncthreads();
+    fft_forward(s, M, logM, tw);
+    for (int i = tid; i < M; i += nthr) s[i] = cmul(s[i], __ldg(Bhat + i));
+    __syncthreads();
+    fft_inverse(s, M, logM, tw);
+    double* yo = out + (size_t)x * n;
+    for (int m = tid; m < n; m += nthr) {
+      double2 v = cmul(__ldg(chi + m), s[m]);
+      yo[m] = v.x * scale;
+    }
+    __syncthreads();
+  }
+}
+
+// O(n * nfo) reference transform with exact integer phase reduction (tests only)
+__global__ void __launch_bounds__(256)
+k_irfft_naive(const double2* __restrict__ yhat, int n, int nfo, double scale,
+              const double* __restrict__ alpha, const double2* __restrict__ wn,
+              double* __restrict__ out) {
+  const long long x = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const double2* yin = yhat + (size_t)x * nfo;
+  double acc = 0.0;
+  int r = 0;  // (k*m) mod n
+  for (int k = 0; k < nfo; ++k) {
+    double2 a = yin[k];
+    const double al = alpha[k];
+    if (al == 1.0) a.y = 0.0;
+    double2 w = __ldg(wn + r);  // e^{+2 pi i r / n}
+    acc += al * (a.x * w.x - a.y * w.y);
+    r += m;
+    if (r >= n) r -= n;
+  }
+  out[(size_t)x * n + m] = acc * scale;
+}
+
+__global__ void k_transpose(const double* __restrict__ src, long long npix, long long n,
+                            double* __restrict__ dst, long long row_stride, long long col0) {
+  __shared__ double tile[32][33];
+  const long long m0 = (long long)blockIdx.x * 32, x0 = (long long)blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    long long x = x0 + r, m = m0 + threadIdx.x;
+    if (x < npix && m < n) tile[r][threadIdx.x] = src[x * n + m];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    long long m = m0 + r, x = x0 + threadIdx.x;
+    if (x < npix && m < n) dst[m * row_stride + col0 + x] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void k_axpy(int n_cmps, const double* const* __restrict__ ptrs,
+                       const double* __restrict__ w, long long n, double* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int c = 0; c < n_cmps; ++c) acc += w[c] * ptrs[c][i];  // same order as mixture.py:45-47
+    out[i] = acc;
+  }
+}
+
+}  // namespace
+
+static constexpr int CZT_SMEM_MAX_M = 8192;
+
+void czt_prepare_filter(pkm_plan* pl) {
+  const CztTables& c = pl->czt;
+  double2* d_b = nullptr;
+  PKM_CUDA(cudaMalloc(&d_b, sizeof(double2) * c.M));
+  PKM_CUDA(cudaMemcpy(d_b, c.bfilt.data(), sizeof(double2) * c.M, cudaMemcpyHostToDevice));
+  size_t smem = 0;
+  double2* scratch = nullptr;
+  if (c.M <= CZT_SMEM_MAX_M) {
+    smem = sizeof(double2) * c.M;
+    PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    PKM_CUDA(cudaMalloc(&scratch, sizeof(double2) * c.M));
+  }
+  k_filter_spectrum<<<1, 256, smem>>>(d_b, pl->d_Bhat, c.M, c.logM, pl->d_twiddle, scratch);
+  PKM_CUDA(cudaGetLastError());
+  PKM_CUDA(cudaDeviceSynchronize());
+  cudaFree(d_b);
+  if (scratch) cudaFree(scratch);
+}
+
+void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double scale, double* out,
+                      cudaStream_t st) {
+  if (npix <= 0) return;
+  const CztTables& c = pl->czt;
+  const double s = scale / ((double)c.M * (double)c.n);
+  size_t smem = 0;
+  double2* scratch = nullptr;
+  int grid;
+  if (c.M <= CZT_SMEM_MAX_M) {
+    smem = sizeof(double2) * c.M;
+    PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+    grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
+  } else {
+    grid = (int)std::min<int64_t>(npix, pl->num_sms);
+    pl->misc.reserve(sizeof(double2) * (size_t)c.M * grid);
+    scratch = pl->misc.as<double2>();
+  }
+  k_irfft_czt<<<grid, 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_chi, pl->d_alpha,
+                                       pl->d_twiddle, pl->d_Bhat, out, scratch);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches++;
+}
+
+void launch_irfft_naive(pkm_plan* pl, const double2* yhat, int64_t npix, double scale, double* out,
+                        cudaStream_t st) {
+  if (npix <= 0) return;
+  const CztTables& c = pl->czt;
+  dim3 grid((c.n + 255) / 256, (unsigned)npix);
+  k_irfft_naive<<<grid, 256, 0, st>>>(yhat, c.n, c.nfo, scale / (double)c.n, pl->d_alpha, pl->d_wn, out);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches++;
+}
+
+void launch_transpose(const double* src, int64_t npix, int64_t n, double* dst, int64_t row_stride,
+                      int64_t col0, cudaStream_t st) {
+  if (npix <= 0 || n <= 0) return;
+  dim3 block(32, 8);
+  // grid.y is limited to 65535 blocks of 32 pixels (2M pixels) - split if ever needed
+  for (int64_t x0 = 0; x0 < npix; x0 += 65535LL * 32) {
+    int64_t np = std::min<int64_t>(npix - x0, 65535LL * 32);
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((np + 31) / 32));
+    k_transpose<<<grid, block, 0, st>>>(src + x0 * n, np, n, dst, row_stride, col0 + x0);
+    PKM_CUDA(cudaGetLastError());
+  }
+}
+
+void launch_axpy(int n_cmps, const double* const* d_ptrs_dev, const double* d_w, int64_t n,
+                 double* out, cudaStream_t st) {
+  if (n <= 0) return;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  k_axpy<<<grid, 256, 0, st>>>(n_cmps, d_ptrs_dev, d_w, n, out);
+  PKM_CUDA(cudaGetLastError());
+}

@@ -1,0 +1,182 @@
+// Internal declarations shared by the translation units of libpkm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "pkm_b200.h"
+
+// ----------------------------------------------------------------------------
+// error plumbing: every C-ABI function catches everything and returns a status
+// ----------------------------------------------------------------------------
+struct pkm_error {
+  int code;
+  std::string msg;
+};
+void pkm_set_error(const std::string& msg);
+
+#define PKM_THROW(code_, ...)                                  \
+  do {                                                         \
+    char _b[512];                                              \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                     \
+    throw pkm_error{(code_), std::string(_b)};                 \
+  } while (0)
+
+#define PKM_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      int _c = (_e == cudaErrorMemoryAllocation) ? PKM_ERR_OOM : PKM_ERR_CUDA;          \
+      PKM_THROW(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                __LINE__);                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define PKM_REQUIRE(cond, ...)                        \
+  do {                                                \
+    if (!(cond)) PKM_THROW(PKM_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// ----------------------------------------------------------------------------
+// device buffer that grows on demand (plan workspace)
+// ----------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes);
+  void release();
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ----------------------------------------------------------------------------
+// host-built tables (tables.cpp)
+// ----------------------------------------------------------------------------
+struct SplineTables {
+  int nfi = 0, nfo = 0;
+  std::vector<double> A_inv;    // [nfi][nfi]
+  std::vector<int32_t> tap_idx; // [nfo]   first coefficient of the 4-tap window
+  std::vector<double> tap_w;    // [nfo][4]
+};
+void build_spline_tables(int nfi, int nfo, SplineTables& out);
+
+struct FoldTables {
+  int nv = 0, nfi = 0, ne = 0, no = 0;
+  std::vector<double> CR;        // [nfi][ne]
+  std::vector<double> CI;        // [nfi][no]
+  std::vector<int32_t> idx_plus; // [ne]  velocity index of rolled position  u
+  std::vector<int32_t> idx_minus;// [ne]  velocity index of rolled position -u
+};
+void build_fold_tables(int nv, int v0_idx, double dv, const SplineTables& sp, FoldTables& out);
+
+// k-slots of the contraction kernel: groups of KT consecutive output frequencies that
+// share one 4-tap coefficient window; 4 groups form a warp unit.
+constexpr int PKM_KT = 4;       // frequencies per thread
+constexpr int PKM_GPW = 4;      // groups per warp (x 8 pixels = 32 lanes)
+struct SlotTables {
+  int nslot = 0, ngroup = 0, nunit = 0;
+  std::vector<int32_t> slot_k;     // [nslot]  output frequency or -1 (padding)
+  std::vector<double> slot_w;      // [nslot][4]
+  std::vector<int32_t> group_span; // [ngroup] first coefficient row of the group
+};
+void build_slot_tables(const SplineTables& sp, SlotTables& out);
+inline int slot_pos(int unit, int r, int gsub) { return (unit * PKM_KT + r) * PKM_GPW + gsub; }
+
+// chirp-z tables for the arbitrary-length inverse real FFT
+struct CztTables {
+  int n = 0, nfo = 0, M = 0, logM = 0;
+  std::vector<double> chi;     // [n] complex: exp(+i*pi*j^2/n)
+  std::vector<double> alpha;   // [nfo] weights 1,2,...,2,(1 if n even)
+  std::vector<double> twiddle; // [M] complex: exp(-2*pi*i*j/M)
+  std::vector<double> bfilt;   // [M] complex: conj chirp laid out circularly (time domain)
+};
+void build_czt_tables(int n, CztTables& out);
+
+// ----------------------------------------------------------------------------
+// the plan
+// ----------------------------------------------------------------------------
+struct pkm_plan {
+  pkm_cube_desc d;
+  int nfo = 0, nfi = 0, ntz = 0;
+  bool density_ok = false;  // v0_idx >= 0 and nfi >= 4
+  int64_t launches = 0;
+  int num_sms = 148;
+  size_t ws_limit = size_t(4) << 30;
+
+  // density path
+  FoldTables fold;
+  SlotTables slots;
+  int TM = 0, nfiP = 0;         // row tiling of kernel 1 (nfiP = 8*TM padded rows)
+  double* d_CRt = nullptr;      // [ne][nfiP]  (u-major, rows padded with zeros)
+  double* d_CIt = nullptr;      // [no][nfiP]
+  int32_t* d_idx_plus = nullptr;
+  int32_t* d_idx_minus = nullptr;
+  double2* d_Sp = nullptr;      // [ntz][nslot]  S-hat' = FXw*dz*dt in slot order, tz = t*nz+z
+  int32_t* d_slot_k = nullptr;
+  double* d_slot_w = nullptr;
+  int32_t* d_group_span = nullptr;
+
+  // gaussian path
+  int kpadA = 0;
+  double2* d_SA = nullptr;      // [nt][nz][kpadA]  FXw (unscaled), zero padded
+  double* d_omega = nullptr;    // [kpadA]
+
+  // inverse FFT
+  CztTables czt;
+  double2* d_chi = nullptr;
+  double* d_alpha = nullptr;
+  double2* d_twiddle = nullptr;
+  double2* d_Bhat = nullptr;    // [M] forward transform of bfilt, in the kernel's permuted order
+  double2* d_wn = nullptr;      // [n] exp(+2 pi i r / n) for the naive cross-check transform
+
+  // statistics
+  double* d_log_dt = nullptr;   // [nt]
+  double* d_log_dz = nullptr;   // [nz]
+  std::vector<double> h_delta_t, h_delta_z;
+
+  // workspace
+  DevBuf coef, yhat, ypx, stage_in[2], stage_out[2], misc;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
+};
+
+// ----------------------------------------------------------------------------
+// kernel launchers (all asynchronous on `st`)
+// ----------------------------------------------------------------------------
+// kernel 1: density tile -> spline coefficients cT[t][z][m][xpad]
+void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
+                  int64_t pix0, int npix_tile, int xpad, double2* cT, cudaStream_t st);
+// kernel 2: coefficients -> Yhat[xpad][nfo]
+void launch_contract(pkm_plan* pl, const double2* cT, int xpad, double2* yhat, cudaStream_t st);
+// gaussian path -> Yhat[xpad][nfo]
+void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
+                     const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
+                     int64_t pix0, int npix_tile, int xpad, double2* yhat, cudaStream_t st);
+// inverse real FFT: Yhat[npix][nfo] -> out[npix][n] * scale
+void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double scale, double* out,
+                      cudaStream_t st);
+void launch_irfft_naive(pkm_plan* pl, const double2* yhat, int64_t npix, double scale, double* out,
+                        cudaStream_t st);
+void czt_prepare_filter(pkm_plan* pl);  // computes d_Bhat on the device (plan creation)
+// [npix][n] -> cube[m*row_stride + col0 + x]
+void launch_transpose(const double* src, int64_t npix, int64_t n, double* dst, int64_t row_stride,
+                      int64_t col0, cudaStream_t st);
+void launch_axpy(int n_cmps, const double* const* d_ptrs_dev, const double* d_w, int64_t n,
+                 double* out, cudaStream_t st);
+
+// statistics kernels (stats.cu)
+void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const double* d_log_dv,
+                        const double* d_log_lw, uint32_t keep_mask, int density, double* out,
+                        cudaStream_t st);
+void density_tables_upload(pkm_plan* pl);
+int coeff_choose_pxb(const pkm_plan* pl);
+void launch_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,
+                    double* out, cudaStream_t st);
+void launch_max(const double* x, int64_t n, double* d_result, cudaStream_t st);
+void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t seed,
+                  uint64_t offset, const double* d_max, double* yobs, double* sigma,
+                  cudaStream_t st);
+
+bool pkm_is_device_pointer(const void* p);

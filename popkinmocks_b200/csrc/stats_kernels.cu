@@ -1,0 +1,389 @@
+// Satellites of the datacube path: log-marginals of the pixelated density, moments, noise.
+//
+//  * pkm_reduce_logp: every Component._get_log_p_* marginal
+//    (/root/reference/popkinmocks/components/base.py:884-1174) is
+//    logsumexp_{dropped axes}( log p + log dV [+ log L(t,z) - log norm] ) (base.py:1017-1041).
+//    One generic kernel does it in two streaming passes over the 5-D array (per-output maximum,
+//    then sum of exp relative to it) instead of the reference's 3+ full-array temporaries per call.
+//  * pkm_moments: mean and central moments 2..4 of P[nvar][ncond] along axis 0 (base.py:208-260).
+//  * pkm_noise: ShotNoise / ConstantSNR sigma maps and Gaussian sampling (noise.py:29-71),
+//    Philox4x32-10 counter RNG + Box-Muller in FP64.
+#include <cmath>
+
+#include "pkm_internal.h"
+
+namespace {
+
+__device__ __forceinline__ void atomic_max_double(double* addr, double val) {
+  // IEEE-754 ordering trick: non-negative doubles order like signed ints, negative ones like
+  // reversed unsigned ints.  NaN is never passed in.
+  if (val >= 0.0)
+    atomicMax(reinterpret_cast<long long*>(addr), __double_as_longlong(val));
+  else
+    atomicMin(reinterpret_cast<unsigned long long*>(addr),
+              static_cast<unsigned long long>(__double_as_longlong(val)));
+}
+
+struct ReduceGeom {
+  int nt, nv, nz;
+  long long npix;
+  int kt, kv, kx, kz;  // 1 = axis kept
+  double log_dxdy;
+};
+
+__device__ __forceinline__ long long out_index(const ReduceGeom& g, int t, int v, long long x, int z) {
+  long long o = g.kt ? t : 0;
+  o = o * (g.kv ? g.nv : 1) + (g.kv ? v : 0);
+  o = o * (g.kx ? g.npix : 1) + (g.kx ? x : 0);
+  o = o * (g.kz ? g.nz : 1) + (g.kz ? z : 0);
+  return o;
+}
+
+// PASS 0: per-output maximum (atomic max into mx, also global max into gmax)
+// PASS 1: per-output sum of exp(a - mx[o]) (atomic add into out)
+// CTA = one kept (t, v) index (or the full range of a dropped axis) x a chunk of PB whole pixels;
+// thread = one (pixel, z) element, contiguous in memory for fixed (t, v).
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_reduce_pass(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
+              const double* __restrict__ log_dv, const double* __restrict__ log_dz,
+              const double* __restrict__ log_lw, double* __restrict__ mx, double* __restrict__ out,
+              double* __restrict__ gmax, int PB) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  const int nact = PB * g.nz;
+  const long long chunk = blockIdx.x;
+  const int xl = tid / g.nz, z = tid - xl * g.nz;
+  const long long x = chunk * PB + xl;
+  const bool active = tid < nact && x < g.npix;
+  int t0 = 0, t1 = g.nt, v0 = 0, v1 = g.nv;
+  if (g.kt) { t0 = blockIdx.y; t1 = t0 + 1; }
+  if (g.kv) { v0 = blockIdx.z; v1 = v0 + 1; }
+
+  double val = PASS == 0 ? -INFINITY : 0.0;
+  if (active) {
+    const double cz = log_dz[z] + g.log_dxdy;
+    const long long o = out_index(g, t0, v0, x, z);  // kept indices are loop invariant
+    double ref = 0.0;
+    if (PASS == 1) ref = mx[o];
+    if (PASS == 0 || ref > -INFINITY) {
+      for (int t = t0; t < t1; ++t) {
+        const double ct = cz + log_dt[t] + (log_lw ? log_lw[t * g.nz + z] : 0.0);
+        const double* p = logp + (((long long)t * g.nv + v0) * g.npix + chunk * PB) * g.nz + tid;
+        for (int v = v0; v < v1; ++v) {
+          const double a = __ldg(p) + ct + log_dv[v];
+          p += g.npix * g.nz;
+          if (PASS == 0) val = fmax(val, a);
+          else val += exp(a - ref);
+        }
+      }
+    }
+  }
+  // combine over the dropped in-CTA axes
+  if (g.kx && g.kz) {
+    if (active) {
+      long long o = out_index(g, t0, v0, x, z);
+      if (PASS == 0) { if (val > -INFINITY) atomic_max_double(mx + o, val); }
+      else if (val != 0.0) atomicAdd(out + o, val);
+    }
+  } else {
+    red[tid] = active ? val : (PASS == 0 ? -INFINITY : 0.0);
+    __syncthreads();
+    if (g.kx) {          // reduce over z, one thread per pixel
+      if (tid < PB && chunk * PB + tid < g.npix) {
+        double r = PASS == 0 ? -INFINITY : 0.0;
+        for (int zz = 0; zz < g.nz; ++zz) {
+          double e = red[tid * g.nz + zz];
+          r = PASS == 0 ? fmax(r, e) : r + e;
+        }
+        long long o = out_index(g, t0, v0, chunk * PB + tid, 0);
+        if (PASS == 0) { if (r > -INFINITY) atomic_max_double(mx + o, r); }
+        else if (r != 0.0) atomicAdd(out + o, r);
+      }
+    } else if (g.kz) {   // reduce over pixels, one thread per z
+      if (tid < g.nz) {
+        double r = PASS == 0 ? -INFINITY : 0.0;
+        for (int xx = 0; xx < PB; ++xx) {
+          double e = red[xx * g.nz + tid];
+          r = PASS == 0 ? fmax(r, e) : r + e;
+        }
+        long long o = out_index(g, t0, v0, 0, tid);
+        if (PASS == 0) { if (r > -INFINITY) atomic_max_double(mx + o, r); }
+        else if (r != 0.0) atomicAdd(out + o, r);
+      }
+    } else {             // reduce everything in the CTA
+      for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s) red[tid] = PASS == 0 ? fmax(red[tid], red[tid + s]) : red[tid] + red[tid + s];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        long long o = out_index(g, t0, v0, 0, 0);
+        double r = red[0];
+        if (PASS == 0) { if (r > -INFINITY) atomic_max_double(mx + o, r); }
+        else if (r != 0.0) atomicAdd(out + o, r);
+      }
+    }
+  }
+  if (PASS == 0 && gmax) {
+    // global maximum (needed only for the light-weighted normalisation)
+    double r = active ? val : -INFINITY;
+    for (int off = 16; off > 0; off >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, off));
+    if ((tid & 31) == 0 && r > -INFINITY) atomic_max_double(gmax, r);
+  }
+}
+
+// total[0] += sum_o out[o] * exp(mx[o] - gmax)   (log normalisation = gmax + log total)
+__global__ void k_reduce_total(const double* __restrict__ mx, const double* __restrict__ out,
+                               long long nout, const double* __restrict__ gmax, double* total) {
+  double acc = 0.0;
+  const double gm = *gmax;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nout;
+       i += (long long)gridDim.x * blockDim.x) {
+    double m = mx[i];
+    if (m > -INFINITY) acc += out[i] * exp(m - gm);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(total, acc);
+}
+
+__global__ void k_reduce_finalize(double* __restrict__ out, const double* __restrict__ mx,
+                                  long long nout, ReduceGeom g, const double* __restrict__ log_dt,
+                                  const double* __restrict__ log_dv, const double* __restrict__ log_dz,
+                                  const double* gmax, const double* total, int density) {
+  double lognorm = 0.0;
+  if (total) lognorm = *gmax + log(*total);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nout;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    int z = 0, t = 0, v = 0;
+    if (g.kz) { z = (int)(r % g.nz); r /= g.nz; }
+    if (g.kx) { r /= g.npix; }
+    if (g.kv) { v = (int)(r % g.nv); r /= g.nv; }
+    if (g.kt) { t = (int)r; }
+    double m = mx[i];
+    double val = (m > -INFINITY) ? m + log(out[i]) : -INFINITY;
+    val -= lognorm;
+    if (density) {
+      double ldv = 0.0;
+      if (g.kt) ldv += log_dt[t];
+      if (g.kv) ldv += log_dv[v];
+      if (g.kx) ldv += g.log_dxdy;
+      if (g.kz) ldv += log_dz[z];
+      val -= ldv;
+    }
+    out[i] = val;
+  }
+}
+
+// all axes kept: out = log p + log dV (+ log lw) ; also feeds the global max for normalisation
+__global__ void k_reduce_identity(const double* __restrict__ logp, ReduceGeom g,
+                                  const double* __restrict__ log_dt, const double* __restrict__ log_dv,
+                                  const double* __restrict__ log_dz, const double* __restrict__ log_lw,
+                                  double* __restrict__ out, long long ntot) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ntot;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    int z = (int)(r % g.nz); r /= g.nz;
+    r /= g.npix;
+    int v = (int)(r % g.nv); r /= g.nv;
+    int t = (int)r;
+    out[i] = logp[i] + log_dt[t] + log_dv[v] + g.log_dxdy + log_dz[z] + (log_lw ? log_lw[t * g.nz + z] : 0.0);
+  }
+}
+
+// out[i] -= lognorm + (density ? log dV(t,v,x,z) : 0) for the all-axes-kept case
+__global__ void k_sub_density(double* __restrict__ out, long long ntot, ReduceGeom g,
+                              const double* __restrict__ log_dt, const double* __restrict__ log_dv,
+                              const double* __restrict__ log_dz, const double* lognorm, int density) {
+  const double ln = lognorm ? *lognorm : 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ntot;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    int z = (int)(r % g.nz); r /= g.nz;
+    r /= g.npix;
+    int v = (int)(r % g.nv); r /= g.nv;
+    int t = (int)r;
+    double val = out[i] - ln;
+    if (density) val -= log_dt[t] + log_dv[v] + g.log_dxdy + log_dz[z];
+    out[i] = val;
+  }
+}
+
+__global__ void k_fill(double* p, long long n, double v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void k_moments(const double* __restrict__ P, const double* __restrict__ values,
+                          long long nvar, long long ncond, double* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncond) return;
+  double mean = 0.0;
+  for (long long i = 0; i < nvar; ++i) mean += values[i] * P[i * ncond + c];
+  double m2 = 0.0, m3 = 0.0, m4 = 0.0;
+  for (long long i = 0; i < nvar; ++i) {
+    const double d = values[i] - mean, p = P[i * ncond + c];
+    const double d2 = d * d;
+    m2 += d2 * p;
+    m3 += d2 * d * p;
+    m4 += d2 * d2 * p;
+  }
+  out[c] = mean;
+  out[ncond + c] = m2;
+  out[2 * ncond + c] = m3;
+  out[3 * ncond + c] = m4;
+}
+
+// numpy.max semantics: NaN if any element is NaN
+__global__ void k_max(const double* __restrict__ x, long long n, double* result, int* nan_flag) {
+  double m = -INFINITY;
+  bool has_nan = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i];
+    if (v != v) has_nan = true; else m = fmax(m, v);
+  }
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (__any_sync(0xffffffffu, has_nan) && (threadIdx.x & 31) == 0) atomicExch(nan_flag, 1);
+  if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomic_max_double(result, m);
+}
+__global__ void k_max_finish(double* result, const int* nan_flag) {
+  if (*nan_flag) *result = NAN;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (offset+i, stream), key = seed
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void k_noise(const double* __restrict__ ybar, long long n, double snr, int mode,
+                        unsigned long long seed, unsigned long long offset,
+                        const double* __restrict__ d_max, double* __restrict__ yobs,
+                        double* __restrict__ sigma_out) {
+  double K = 0.0;
+  if (mode == 0) K = sqrt(*d_max) / snr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double y = ybar[i];
+    const double sg = (mode == 0) ? K * sqrt(y) : y / snr;
+    if (sigma_out) sigma_out[i] = sg;
+    if (yobs) {
+      const unsigned long long ctr = offset + (unsigned long long)i;
+      uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x706b6d62u, 0u};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      // two 53-bit uniforms in (0,1]
+      const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1];
+      const unsigned long long b = ((unsigned long long)c[2] << 32) | c[3];
+      const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+      const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      const double zn = sqrt(-2.0 * log(u1)) * cs;
+      yobs[i] = y + sg * zn;
+    }
+  }
+}
+
+}  // namespace
+
+void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const double* d_log_dv,
+                        const double* d_log_lw, uint32_t keep_mask, int density, double* out,
+                        cudaStream_t st) {
+  ReduceGeom g;
+  g.nt = pl->d.nt; g.nv = pl->d.nv; g.nz = pl->d.nz; g.npix = npix;
+  g.kt = keep_mask & 1; g.kv = (keep_mask >> 1) & 1; g.kx = (keep_mask >> 2) & 1; g.kz = (keep_mask >> 3) & 1;
+  g.log_dxdy = std::log(pl->d.dx) + std::log(pl->d.dy);
+  PKM_REQUIRE(g.nz <= 256, "nz=%d > 256 unsupported by the reduction kernel", g.nz);
+  const long long ntot = (long long)g.nt * g.nv * npix * g.nz;
+  long long nout = 1;
+  if (g.kt) nout *= g.nt;
+  if (g.kv) nout *= g.nv;
+  if (g.kx) nout *= npix;
+  if (g.kz) nout *= g.nz;
+  const int PB = 256 / g.nz;
+  const long long nchunk = (npix + PB - 1) / PB;
+  PKM_REQUIRE(nchunk < (1LL << 31), "too many pixels");
+  const bool lw = d_log_lw != nullptr;
+  const int fgrid = (int)std::min<long long>((nout + 255) / 256, (long long)pl->num_sms * 16);
+
+  // scratch: [gmax, total] (+ mx[nout] unless all axes are kept)
+  const bool all_kept = keep_mask == 0xF;
+  pl->misc.reserve(sizeof(double) * (size_t)(2 + (all_kept ? 1 : nout) + 2));
+  double* d_gmax = pl->misc.as<double>();
+  double* d_total = d_gmax + 1;
+  double* d_mx = d_gmax + 2;
+  k_fill<<<1, 32, 0, st>>>(d_gmax, 1, -INFINITY);
+  k_fill<<<1, 32, 0, st>>>(d_total, 1, 0.0);
+
+  if (all_kept) {
+    const int grid = (int)std::min<long long>((ntot + 255) / 256, (long long)pl->num_sms * 16);
+    k_reduce_identity<<<grid, 256, 0, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, out, ntot);
+    pl->launches += 3;
+    if (lw) {
+      // normalisation: scalar log-sum-exp of the weighted array (two more passes)
+      ReduceGeom g0 = g;
+      g0.kt = g0.kv = g0.kx = g0.kz = 0;
+      double* d_mx0 = d_mx;      // 1 element
+      double* d_sum0 = d_mx + 1; // 1 element
+      k_fill<<<1, 32, 0, st>>>(d_mx0, 1, -INFINITY);
+      k_fill<<<1, 32, 0, st>>>(d_sum0, 1, 0.0);
+      dim3 grid0((unsigned)nchunk, 1, 1);
+      k_reduce_pass<0><<<grid0, 256, 0, st>>>(logp, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx0, d_sum0, nullptr, PB);
+      k_reduce_pass<1><<<grid0, 256, 0, st>>>(logp, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx0, d_sum0, nullptr, PB);
+      // d_sum0 <- mx0 + log(sum0) = log normalisation (finalize on the 1-element array)
+      k_reduce_finalize<<<1, 32, 0, st>>>(d_sum0, d_mx0, 1, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, nullptr, nullptr, 0);
+      k_sub_density<<<grid, 256, 0, st>>>(out, ntot, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_sum0, density);
+      pl->launches += 6;
+    } else if (density) {
+      k_sub_density<<<grid, 256, 0, st>>>(out, ntot, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, nullptr, density);
+      pl->launches += 1;
+    }
+    PKM_CUDA(cudaGetLastError());
+    return;
+  }
+
+  k_fill<<<fgrid, 256, 0, st>>>(d_mx, nout, -INFINITY);
+  k_fill<<<fgrid, 256, 0, st>>>(out, nout, 0.0);
+  dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
+  k_reduce_pass<0><<<grid, 256, 0, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx, out, lw ? d_gmax : nullptr, PB);
+  k_reduce_pass<1><<<grid, 256, 0, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx, out, nullptr, PB);
+  if (lw) k_reduce_total<<<fgrid, 256, 0, st>>>(d_mx, out, nout, d_gmax, d_total);
+  k_reduce_finalize<<<fgrid, 256, 0, st>>>(out, d_mx, nout, g, pl->d_log_dt, d_log_dv, pl->d_log_dz,
+                                           lw ? d_gmax : nullptr, lw ? d_total : nullptr, density);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches += 6 + (lw ? 1 : 0);
+}
+
+void launch_moments(const double* P, const double* values, int64_t nvar, int64_t ncond, double* out,
+                    cudaStream_t st) {
+  if (ncond <= 0) return;
+  k_moments<<<(unsigned)((ncond + 127) / 128), 128, 0, st>>>(P, values, nvar, ncond, out);
+  PKM_CUDA(cudaGetLastError());
+}
+
+// d_result: 2 doubles of device scratch (value, then an int flag in the second slot)
+void launch_max(const double* x, int64_t n, double* d_result, cudaStream_t st) {
+  int* flag = reinterpret_cast<int*>(d_result + 1);
+  k_fill<<<1, 32, 0, st>>>(d_result, 1, -INFINITY);
+  PKM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8));
+  k_max<<<grid, 256, 0, st>>>(x, n, d_result, flag);
+  k_max_finish<<<1, 1, 0, st>>>(d_result, flag);
+  PKM_CUDA(cudaGetLastError());
+}
+
+void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t seed, uint64_t offset,
+                  const double* d_max, double* yobs, double* sigma, cudaStream_t st) {
+  if (n <= 0) return;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  k_noise<<<grid, 256, 0, st>>>(ybar, n, snr, mode, seed, offset, d_max, yobs, sigma);
+  PKM_CUDA(cudaGetLastError());
+}

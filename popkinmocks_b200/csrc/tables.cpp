@@ -1,0 +1,252 @@
+// Host-side construction of the constant tables used by the kernels.
+//
+// * not-a-knot cubic spline nfi -> nfo on linspace(0,1,.)  : the reference resamples the
+//   velocity spectrum with scipy.interpolate.interp1d(kind="cubic")
+//   (/root/reference/popkinmocks/components/base.py:846-853), which is
+//   make_interp_spline(k=3) with not-a-knot end conditions: knots are the data sites
+//   with the 2nd and the penultimate removed and the ends repeated 4 times.  The
+//   spline is  s(x) = sum_m c_m B_m(x)  with  c = A^{-1} y,  A[j][m] = B_m(x_j).
+// * folded real-DFT matrices composing roll, rfft, *dv (base.py:841-844) with A^{-1}.
+// * slot layout of the contraction kernel and chirp-z tables of the inverse FFT.
+//
+// Everything here is plain C++ (long double accumulation, exact integer phase
+// reduction) and runs without a GPU, so it is unit-tested on CPU against SciPy.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "pkm_internal.h"
+
+namespace {
+
+const long double PI_L = 3.14159265358979323846264338327950288419716939937510L;
+
+// np.linspace(0, 1, n)[j]  (numpy: arange(n) * step with step = 1/(n-1); endpoint forced to 1)
+inline double linspace01(int j, int n) {
+  if (j == n - 1) return 1.0;
+  double step = 1.0 / double(n - 1);
+  return double(j) * step;
+}
+
+struct Knots {
+  std::vector<long double> t;  // nfi + 4 knots
+  int nfi;
+};
+
+Knots not_a_knot_knots(int nfi) {
+  Knots k;
+  k.nfi = nfi;
+  for (int i = 0; i < 4; ++i) k.t.push_back(0.0L);
+  for (int j = 2; j <= nfi - 3; ++j) k.t.push_back((long double)linspace01(j, nfi));
+  for (int i = 0; i < 4; ++i) k.t.push_back(1.0L);
+  return k;
+}
+
+// knot span ell (3 <= ell <= nfi-1) with t[ell] <= x < t[ell+1]; x == 1 maps to the last span
+int find_span(const Knots& k, long double x) {
+  int lo = 3, hi = k.nfi;  // t[nfi] == 1
+  if (x >= k.t[hi]) return k.nfi - 1;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) / 2;
+    if (x >= k.t[mid]) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// the 4 non-zero cubic B-splines B_{ell-3..ell}(x)   (Cox - de Boor, triangular scheme)
+void basis4(const Knots& k, int ell, long double x, long double N[4]) {
+  long double left[4], right[4];
+  N[0] = 1.0L;
+  for (int j = 1; j <= 3; ++j) {
+    left[j] = x - k.t[ell + 1 - j];
+    right[j] = k.t[ell + j] - x;
+    long double saved = 0.0L;
+    for (int r = 0; r < j; ++r) {
+      long double tmp = N[r] / (right[r + 1] + left[j - r]);
+      N[r] = saved + right[r + 1] * tmp;
+      saved = left[j - r] * tmp;
+    }
+    N[j] = saved;
+  }
+}
+
+// dense inverse by Gauss-Jordan with partial pivoting, long double
+void invert(std::vector<long double>& a, int n, std::vector<long double>& inv) {
+  inv.assign(size_t(n) * n, 0.0L);
+  for (int i = 0; i < n; ++i) inv[size_t(i) * n + i] = 1.0L;
+  for (int col = 0; col < n; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < n; ++r)
+      if (fabsl(a[size_t(r) * n + col]) > fabsl(a[size_t(piv) * n + col])) piv = r;
+    if (a[size_t(piv) * n + col] == 0.0L) PKM_THROW(PKM_ERR_INVALID, "singular collocation matrix");
+    if (piv != col)
+      for (int c = 0; c < n; ++c) {
+        std::swap(a[size_t(piv) * n + c], a[size_t(col) * n + c]);
+        std::swap(inv[size_t(piv) * n + c], inv[size_t(col) * n + c]);
+      }
+    long double d = 1.0L / a[size_t(col) * n + col];
+    for (int c = 0; c < n; ++c) {
+      a[size_t(col) * n + c] *= d;
+      inv[size_t(col) * n + c] *= d;
+    }
+    for (int r = 0; r < n; ++r) {
+      if (r == col) continue;
+      long double f = a[size_t(r) * n + col];
+      if (f == 0.0L) continue;
+      for (int c = 0; c < n; ++c) {
+        a[size_t(r) * n + c] -= f * a[size_t(col) * n + c];
+        inv[size_t(r) * n + c] -= f * inv[size_t(col) * n + c];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void build_spline_tables(int nfi, int nfo, SplineTables& out) {
+  PKM_REQUIRE(nfi >= 4, "cubic spline needs at least 4 input frequencies (nv >= 6), got nfi=%d", nfi);
+  PKM_REQUIRE(nfo >= 2, "nfo=%d too small", nfo);
+  out.nfi = nfi;
+  out.nfo = nfo;
+  Knots kn = not_a_knot_knots(nfi);
+  std::vector<long double> A(size_t(nfi) * nfi, 0.0L), Ai;
+  for (int j = 0; j < nfi; ++j) {
+    long double x = (long double)linspace01(j, nfi);
+    int ell = find_span(kn, x);
+    long double N[4];
+    basis4(kn, ell, x, N);
+    for (int q = 0; q < 4; ++q) A[size_t(j) * nfi + (ell - 3 + q)] = N[q];
+  }
+  invert(A, nfi, Ai);
+  out.A_inv.resize(size_t(nfi) * nfi);
+  for (size_t i = 0; i < Ai.size(); ++i) out.A_inv[i] = (double)Ai[i];
+  out.tap_idx.resize(nfo);
+  out.tap_w.resize(size_t(nfo) * 4);
+  for (int k = 0; k < nfo; ++k) {
+    long double x = (long double)linspace01(k, nfo);
+    int ell = find_span(kn, x);
+    long double N[4];
+    basis4(kn, ell, x, N);
+    out.tap_idx[k] = ell - 3;
+    for (int q = 0; q < 4; ++q) out.tap_w[size_t(k) * 4 + q] = (double)N[q];
+  }
+}
+
+void build_fold_tables(int nv, int v0_idx, double dv, const SplineTables& sp, FoldTables& out) {
+  const int nfi = nv / 2 + 1;
+  PKM_REQUIRE(sp.nfi == nfi, "spline tables built for nfi=%d, need %d", sp.nfi, nfi);
+  PKM_REQUIRE(v0_idx >= 0 && v0_idx < nv, "v0_idx=%d out of range", v0_idx);
+  out.nv = nv;
+  out.nfi = nfi;
+  out.ne = nv / 2 + 1;
+  out.no = (nv - 1) / 2;
+  out.idx_plus.resize(out.ne);
+  out.idx_minus.resize(out.ne);
+  for (int u = 0; u < out.ne; ++u) {
+    // rolled[u] = p[(u + v0) mod nv]  (np.roll(p, nv - v0_idx), base.py:843)
+    out.idx_plus[u] = (u + v0_idx) % nv;
+    out.idx_minus[u] = ((v0_idx - u) % nv + nv) % nv;
+  }
+  // F[j] = dv * sum_u rolled[u] exp(-2 pi i j u / nv);  with e[u] = rolled[u] + rolled[nv-u],
+  // o[u] = rolled[u] - rolled[nv-u]:  Re F[j] = dv * sum_{u<ne} g_u e[u] cos(2 pi j u/nv),
+  // Im F[j] = -dv * sum_{1<=u<=no} o[u] sin(2 pi j u/nv), g_u = 1/2 for the self-paired
+  // positions (u = 0, and u = nv/2 when nv is even), 1 otherwise.
+  std::vector<long double> C(size_t(nfi) * out.ne), S(size_t(nfi) * std::max(out.no, 1));
+  for (int j = 0; j < nfi; ++j) {
+    for (int u = 0; u < out.ne; ++u) {
+      long long r = ((long long)j * u) % nv;
+      long double ang = 2.0L * PI_L * (long double)r / (long double)nv;
+      bool self = (out.idx_plus[u] == out.idx_minus[u]);
+      C[size_t(j) * out.ne + u] = (long double)dv * (self ? 0.5L : 1.0L) * cosl(ang);
+      if (u >= 1 && u <= out.no) S[size_t(j) * out.no + (u - 1)] = -(long double)dv * sinl(ang);
+    }
+  }
+  out.CR.assign(size_t(nfi) * out.ne, 0.0);
+  out.CI.assign(size_t(nfi) * std::max(out.no, 1), 0.0);
+  for (int m = 0; m < nfi; ++m) {
+    for (int u = 0; u < out.ne; ++u) {
+      long double acc = 0.0L;
+      for (int j = 0; j < nfi; ++j) acc += (long double)sp.A_inv[size_t(m) * nfi + j] * C[size_t(j) * out.ne + u];
+      out.CR[size_t(m) * out.ne + u] = (double)acc;
+    }
+    for (int u = 0; u < out.no; ++u) {
+      long double acc = 0.0L;
+      for (int j = 0; j < nfi; ++j) acc += (long double)sp.A_inv[size_t(m) * nfi + j] * S[size_t(j) * out.no + u];
+      out.CI[size_t(m) * out.no + u] = (double)acc;
+    }
+  }
+}
+
+void build_slot_tables(const SplineTables& sp, SlotTables& out) {
+  const int nfo = sp.nfo;
+  std::vector<int> gk0, gcnt, gspan;
+  int k = 0;
+  while (k < nfo) {
+    int span = sp.tap_idx[k];
+    int cnt = 1;
+    while (cnt < PKM_KT && k + cnt < nfo && sp.tap_idx[k + cnt] == span) ++cnt;
+    gk0.push_back(k);
+    gcnt.push_back(cnt);
+    gspan.push_back(span);
+    k += cnt;
+  }
+  int ngroup = (int)gk0.size();
+  int nunit = (ngroup + PKM_GPW - 1) / PKM_GPW;
+  out.ngroup = nunit * PKM_GPW;
+  out.nunit = nunit;
+  out.nslot = out.ngroup * PKM_KT;
+  out.slot_k.assign(out.nslot, -1);
+  out.slot_w.assign(size_t(out.nslot) * 4, 0.0);
+  out.group_span.assign(out.ngroup, 0);
+  for (int g = 0; g < ngroup; ++g) {
+    int unit = g / PKM_GPW, gsub = g % PKM_GPW;
+    out.group_span[g] = gspan[g];
+    for (int r = 0; r < gcnt[g]; ++r) {
+      int pos = slot_pos(unit, r, gsub);
+      int kk = gk0[g] + r;
+      out.slot_k[pos] = kk;
+      for (int q = 0; q < 4; ++q) out.slot_w[size_t(pos) * 4 + q] = sp.tap_w[size_t(kk) * 4 + q];
+    }
+  }
+}
+
+void build_czt_tables(int n, CztTables& out) {
+  PKM_REQUIRE(n >= 2, "n_fft=%d too small", n);
+  out.n = n;
+  out.nfo = n / 2 + 1;
+  int need = out.nfo + n - 1;
+  int M = 1, logM = 0;
+  while (M < need) { M <<= 1; ++logM; }
+  if (logM < 2) { M = 4; logM = 2; }
+  out.M = M;
+  out.logM = logM;
+  // chi[j] = exp(+i pi j^2 / n), phase reduced exactly: j^2 mod 2n
+  out.chi.resize(size_t(2) * n);
+  for (long long j = 0; j < n; ++j) {
+    long long r = (j * j) % (2LL * n);
+    long double ang = PI_L * (long double)r / (long double)n;
+    out.chi[2 * j] = (double)cosl(ang);
+    out.chi[2 * j + 1] = (double)sinl(ang);
+  }
+  // numpy.fft.irfft weights: DC and (even n) Nyquist count once and only their real
+  // part is used; all other bins twice (Hermitian pair).
+  out.alpha.assign(out.nfo, 2.0);
+  out.alpha[0] = 1.0;
+  if (n % 2 == 0) out.alpha[out.nfo - 1] = 1.0;
+  out.twiddle.resize(size_t(2) * M);
+  for (int j = 0; j < M; ++j) {
+    long double ang = -2.0L * PI_L * (long double)j / (long double)M;
+    out.twiddle[2 * j] = (double)cosl(ang);
+    out.twiddle[2 * j + 1] = (double)sinl(ang);
+  }
+  // z[m] = chi[m] * sum_k (a[k] chi[k]) conj(chi[m-k]),  m-k in [-(nfo-1), n-1]
+  out.bfilt.assign(size_t(2) * M, 0.0);
+  for (long long j = -(long long)(out.nfo - 1); j <= (long long)(n - 1); ++j) {
+    long long a = j < 0 ? -j : j;
+    long long r = (a * a) % (2LL * n);
+    long double ang = PI_L * (long double)r / (long double)n;
+    long long pos = ((j % M) + M) % M;
+    out.bfilt[2 * pos] = (double)cosl(ang);
+    out.bfilt[2 * pos + 1] = -(double)sinl(ang);
+  }
+}
