@@ -41,6 +41,12 @@ extern "C" {
 
 #define PKM_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define PKM_API __attribute__((visibility("default")))
+#else
+#define PKM_API
+#endif
+
 typedef enum pkm_status {
   PKM_OK = 0,
   PKM_ERR_INVALID = -1,   /* bad argument / shape / unsupported size */
@@ -70,30 +76,30 @@ typedef struct pkm_cube_desc {
 
 typedef struct pkm_plan pkm_plan;
 
-const char* pkm_last_error(void);
-int32_t pkm_abi_version(void);
+PKM_API const char* pkm_last_error(void);
+PKM_API int32_t pkm_abi_version(void);
 /* Number of visible CUDA devices (0 without a GPU/driver; never fails). */
-int32_t pkm_device_count(void);
+PKM_API int32_t pkm_device_count(void);
 
 /* Build the device-resident constant operands.
  *   FXw      host, complex128 [n_fft/2+1][nz][nt]  (ssps.FXw reshaped, model_grids.py:277-281)
  *   delta_t  host [nt], delta_z host [nz]
  * Uploads S-hat' = FXw*dz*dt (density path) and FXw (Gaussian path) in kernel-friendly
  * layouts, builds the not-a-knot spline tables, the folded DFT matrices, chirp-z tables. */
-int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw, const double* delta_t,
+PKM_API int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw, const double* delta_t,
                         const double* delta_z, pkm_plan** plan_out);
-int32_t pkm_plan_destroy(pkm_plan* plan);
+PKM_API int32_t pkm_plan_destroy(pkm_plan* plan);
 /* Cap the device workspace (bytes) used for intermediate spline coefficients; the
  * pixel batch is tiled to fit.  0 restores the default (4 GiB). */
-int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes);
+PKM_API int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes);
 /* Number of kernels launched by this plan since creation (for bench accounting). */
-int64_t pkm_plan_launch_count(const pkm_plan* plan);
+PKM_API int64_t pkm_plan_launch_count(const pkm_plan* plan);
 
 /* Density path.  dens: [nt][nv][nx1][nx2][nz] float64, host or device; is_log != 0 means
  * it holds log p (exp is fused into the first kernel; -inf -> 0).  Rows [row_begin,row_end)
  * of the x1 axis are evaluated (spatial sharding); ybar_out (host or device) receives
  * (row_end-row_begin)*nx2*n_fft float64 in `out_layout`. */
-int32_t pkm_ybar_density(pkm_plan* plan, const double* dens, int32_t is_log, int32_t nx1,
+PKM_API int32_t pkm_ybar_density(pkm_plan* plan, const double* dens, int32_t is_log, int32_t nx1,
                          int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
                          int32_t out_layout, void* stream);
 
@@ -102,7 +108,7 @@ int32_t pkm_ybar_density(pkm_plan* plan, const double* dens, int32_t is_log, int
  * (0 strides allow numpy broadcast views, stream.py:126); omega [n_fft/2+1] is the
  * reference's linspace(0, pi, nfo)/dv (parametric.py:360-362), host.  All of P_txz,
  * mu_v, sig_v must be on the same side (all host or all device). */
-int32_t pkm_ybar_gaussian(pkm_plan* plan, const double* P_txz, const double* mu_v,
+PKM_API int32_t pkm_ybar_gaussian(pkm_plan* plan, const double* P_txz, const double* mu_v,
                           const int64_t mu_strides[3], const double* sig_v,
                           const int64_t sig_strides[3], const double* omega, int32_t nx1,
                           int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
@@ -110,20 +116,20 @@ int32_t pkm_ybar_gaussian(pkm_plan* plan, const double* P_txz, const double* mu_
 
 /* out[i] = sum_c weights[c] * ybars[c][i], i < n.  ybars: host array of n_cmps pointers
  * (all host or all device, same side as out); weights host. */
-int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
+PKM_API int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
                        int64_t n, double* out, int32_t device, void* stream);
 
 /* Spaxel-major [npix][n] -> cube layout [n][npix] (device pointers only). */
-int32_t pkm_transpose_to_cube(const double* pixel_major, int64_t npix, int64_t n, double* cube,
+PKM_API int32_t pkm_transpose_to_cube(const double* pixel_major, int64_t npix, int64_t n, double* cube,
                               int32_t device, void* stream);
 
 /* Batched inverse real FFT of arbitrary length (numpy.fft.irfft semantics, base.py:858):
  * Yhat complex128 [npix][n_fft/2+1] device -> out float64 [npix][n_fft] device, times `scale`.
  * Exposed for tests; pkm_ybar_* call the same kernels. */
-int32_t pkm_irfft_batch(pkm_plan* plan, const double* Yhat, int64_t npix, double scale,
+PKM_API int32_t pkm_irfft_batch(pkm_plan* plan, const double* Yhat, int64_t npix, double scale,
                         double* out, void* stream);
 /* O(n^2) inverse real DFT with exact integer phase reduction - independent cross-check. */
-int32_t pkm_irfft_naive(pkm_plan* plan, const double* Yhat, int64_t npix, double scale,
+PKM_API int32_t pkm_irfft_naive(pkm_plan* plan, const double* Yhat, int64_t npix, double scale,
                         double* out, void* stream);
 
 /* log-marginals of the pixelated density (base.py:884-1174, 1017-1041).
@@ -132,14 +138,14 @@ int32_t pkm_irfft_naive(pkm_plan* plan, const double* Yhat, int64_t npix, double
  *   keep_mask bit0=t bit1=v bit2=x bit3=z: axes kept in the output (others are
  *   log-sum-exp'ed); out (same side as input) has the kept axes in t,v,x,z order.
  *   Returns log P (volume weighted) if density == 0, else log density. */
-int32_t pkm_reduce_logp(pkm_plan* plan, const double* log_p_tvxz, int64_t npix,
+PKM_API int32_t pkm_reduce_logp(pkm_plan* plan, const double* log_p_tvxz, int64_t npix,
                         const double* log_dv, const double* light_weights, uint32_t keep_mask,
                         int32_t density, double* out, void* stream);
 
 /* Moments of a conditional 1-D distribution held as probabilities P[nvar][ncond]
  * (axis 0 = variable, base.py:208-260): out[0][c]=mean, out[1..3][c]= central moments 2,3,4.
  * P, values[nvar], out[4][ncond]: host or device (same side). */
-int32_t pkm_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,
+PKM_API int32_t pkm_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,
                     double* out, int32_t device, void* stream);
 
 /* Observation noise (noise.py:16-71).  mode 0 = ShotNoise (sigma = sqrt(max ybar)/snr * sqrt(ybar)),
@@ -147,20 +153,25 @@ int32_t pkm_moments(const double* P, const double* values, int64_t nvar, int64_t
  * seeded); sigma_out may be NULL.  ybar_max < 0 => the library reduces max(ybar) itself;
  * otherwise it is used as given (multi-GPU: pass the all-reduced maximum).
  * ybar, yobs, sigma_out: host or device (same side). */
-int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t mode, uint64_t seed,
+PKM_API int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t mode, uint64_t seed,
                   uint64_t offset, double ybar_max, double* yobs, double* sigma_out,
                   int32_t device, void* stream);
 /* max over a device/host float64 buffer (NaN-propagating like numpy.max). */
-int32_t pkm_max(const double* x, int64_t n, double* result_host, int32_t device, void* stream);
+PKM_API int32_t pkm_max(const double* x, int64_t n, double* result_host, int32_t device, void* stream);
+
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA; best of `repeats`
+ * timed launches of a register-resident DFMA chain on every SM).  The roofline denominator of
+ * the FP64-pipe-bound kernels; MEASURED_PEAKS.json carries no FP64 figure. */
+PKM_API int32_t pkm_fp64_fma_peak(int32_t device, int32_t repeats, double* tflops_out);
 
 /* Host-only helpers (no GPU needed), exposed so the tables can be checked on CPU.
  * Not-a-knot cubic spline nfi -> nfo on linspace(0,1,.) (base.py:846-853):
  *   A_inv [nfi][nfi]; tap_idx [nfo] first coefficient of the 4-tap window; tap_w [nfo][4]. */
-int32_t pkm_spline_tables(int32_t nfi, int32_t nfo, double* A_inv, int32_t* tap_idx,
+PKM_API int32_t pkm_spline_tables(int32_t nfi, int32_t nfo, double* A_inv, int32_t* tap_idx,
                           double* tap_w);
 /* The folded matrices of the first density kernel: CR [nfi][nv/2+1], CI [nfi][(nv-1)/2] with
  * c = CR * e + i * CI * o, e/o = even/odd parts of the rolled velocity profile. */
-int32_t pkm_fold_tables(int32_t nv, int32_t v0_idx, double dv, double* CR, double* CI,
+PKM_API int32_t pkm_fold_tables(int32_t nv, int32_t v0_idx, double dv, double* CR, double* CI,
                         int32_t* idx_plus, int32_t* idx_minus);
 
 #ifdef __cplusplus

@@ -1,0 +1,675 @@
+// C-ABI entry points of libpkm_b200.so (declared in include/pkm_b200.h).
+//
+// This file owns the plan (constant operands on the device), the pixel tiling of the two
+// ybar paths, the host<->device staging for callers that pass host buffers, and the error
+// plumbing.  All arithmetic lives in the kernel translation units.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "pkm_internal.h"
+
+// ----------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void pkm_set_error(const std::string& msg) { g_last_error = msg; }
+
+template <class F>
+static int32_t guarded(F&& body) {
+  try {
+    body();
+    return PKM_OK;
+  } catch (const pkm_error& e) {
+    pkm_set_error(e.msg);
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    pkm_set_error("host allocation failed");
+    return PKM_ERR_OOM;
+  } catch (const std::exception& e) {
+    pkm_set_error(std::string("unexpected: ") + e.what());
+    return PKM_ERR_INVALID;
+  } catch (...) {
+    pkm_set_error("unknown error");
+    return PKM_ERR_INVALID;
+  }
+}
+
+void DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  PKM_CUDA(cudaMalloc(&p, bytes));
+  cap = bytes;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+bool pkm_is_device_pointer(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // unregistered host memory on old drivers
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static void use_device(int dev) { PKM_CUDA(cudaSetDevice(dev)); }
+
+template <class T>
+static T* upload(const std::vector<T>& h) {
+  T* d = nullptr;
+  PKM_CUDA(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) PKM_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+// ----------------------------------------------------------------------------
+// misc exports
+// ----------------------------------------------------------------------------
+extern "C" const char* pkm_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t pkm_abi_version(void) { return PKM_ABI_VERSION; }
+extern "C" int32_t pkm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int32_t pkm_spline_tables(int32_t nfi, int32_t nfo, double* A_inv, int32_t* tap_idx,
+                                     double* tap_w) {
+  return guarded([&] {
+    SplineTables sp;
+    build_spline_tables(nfi, nfo, sp);
+    if (A_inv) std::memcpy(A_inv, sp.A_inv.data(), sp.A_inv.size() * sizeof(double));
+    if (tap_idx) std::memcpy(tap_idx, sp.tap_idx.data(), sp.tap_idx.size() * sizeof(int32_t));
+    if (tap_w) std::memcpy(tap_w, sp.tap_w.data(), sp.tap_w.size() * sizeof(double));
+  });
+}
+
+extern "C" int32_t pkm_fold_tables(int32_t nv, int32_t v0_idx, double dv, double* CR, double* CI,
+                                   int32_t* idx_plus, int32_t* idx_minus) {
+  return guarded([&] {
+    PKM_REQUIRE(nv >= 6, "nv=%d too small for the cubic spline (needs nv >= 6)", nv);
+    SplineTables sp;
+    build_spline_tables(nv / 2 + 1, 2, sp);
+    FoldTables f;
+    build_fold_tables(nv, v0_idx, dv, sp, f);
+    if (CR) std::memcpy(CR, f.CR.data(), size_t(f.nfi) * f.ne * sizeof(double));
+    if (CI) std::memcpy(CI, f.CI.data(), size_t(f.nfi) * f.no * sizeof(double));
+    if (idx_plus) std::memcpy(idx_plus, f.idx_plus.data(), f.ne * sizeof(int32_t));
+    if (idx_minus) std::memcpy(idx_minus, f.idx_minus.data(), f.ne * sizeof(int32_t));
+  });
+}
+
+// ----------------------------------------------------------------------------
+// plan
+// ----------------------------------------------------------------------------
+static void plan_free(pkm_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->d.device);
+  auto fr = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_idx_plus); fr(pl->d_idx_minus); fr(pl->d_Sp);
+  fr(pl->d_slot_k); fr(pl->d_slot_w); fr(pl->d_group_span); fr(pl->d_SA); fr(pl->d_omega);
+  fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
+  fr(pl->d_log_dt); fr(pl->d_log_dz);
+  pl->coef.release(); pl->yhat.release(); pl->ypx.release(); pl->misc.release(); pl->small.release();
+  for (int i = 0; i < 2; ++i) {
+    pl->stage_in[i].release();
+    pl->stage_out[i].release();
+  }
+  delete pl;
+}
+
+extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
+                                   const double* delta_t, const double* delta_z,
+                                   pkm_plan** plan_out) {
+  pkm_plan* pl = nullptr;
+  int32_t rc = guarded([&] {
+    PKM_REQUIRE(desc && FXw && delta_t && delta_z && plan_out, "null argument");
+    PKM_REQUIRE(desc->nt >= 1 && desc->nz >= 1, "bad SSP grid %d x %d", desc->nt, desc->nz);
+    PKM_REQUIRE(desc->n_fft >= 2, "n_fft=%d too small", desc->n_fft);
+    PKM_REQUIRE(desc->nv >= 1, "nv=%d", desc->nv);
+    PKM_REQUIRE(desc->precision == 0, "precision=%d: only float64 arithmetic is built", desc->precision);
+    int ndev = pkm_device_count();
+    if (ndev <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    PKM_REQUIRE(desc->device >= 0 && desc->device < ndev, "device %d out of range (%d visible)", desc->device, ndev);
+    use_device(desc->device);
+    pl = new pkm_plan();
+    pl->d = *desc;
+    pl->nfo = desc->n_fft / 2 + 1;
+    pl->nfi = desc->nv / 2 + 1;
+    pl->ntz = desc->nt * desc->nz;
+    const int nt = desc->nt, nz = desc->nz, nfo = pl->nfo;
+    cudaDeviceProp prop;
+    PKM_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+    pl->num_sms = prop.multiProcessorCount;
+    pl->h_delta_t.assign(delta_t, delta_t + nt);
+    pl->h_delta_z.assign(delta_z, delta_z + nz);
+
+    // ---- density path tables
+    pl->density_ok = desc->v0_idx >= 0 && desc->v0_idx < desc->nv && pl->nfi >= 4 && pl->nfi <= 64;
+    if (pl->density_ok) {
+      SplineTables sp;
+      build_spline_tables(pl->nfi, nfo, sp);
+      build_fold_tables(desc->nv, desc->v0_idx, desc->dv, sp, pl->fold);
+      build_slot_tables(sp, pl->slots);
+      density_tables_upload(pl);
+      const int nslot = pl->slots.nslot;
+      std::vector<double> Sp(size_t(2) * pl->ntz * nslot, 0.0);
+      for (int t = 0; t < nt; ++t)
+        for (int z = 0; z < nz; ++z) {
+          const double w = delta_z[z] * delta_t[t];
+          double* row = Sp.data() + size_t(2) * (size_t(t) * nz + z) * nslot;
+          for (int pos = 0; pos < nslot; ++pos) {
+            int k = pl->slots.slot_k[pos];
+            if (k < 0) continue;
+            const double* s = FXw + size_t(2) * ((size_t(k) * nz + z) * nt + t);
+            // same rounding order as the reference: F_s * F_p then * (dt*dz); here (S * (dz*dt))
+            row[2 * pos] = s[0] * w;
+            row[2 * pos + 1] = s[1] * w;
+          }
+        }
+      pl->d_Sp = reinterpret_cast<double2*>(upload(Sp));
+      pl->d_slot_k = upload(pl->slots.slot_k);
+      pl->d_slot_w = upload(pl->slots.slot_w);
+      pl->d_group_span = upload(pl->slots.group_span);
+    }
+
+    // ---- gaussian path: FXw as [t][z][kpad]
+    const int kq = PKM_GPW * PKM_KT;
+    pl->kpadA = ((nfo + kq - 1) / kq) * kq;
+    {
+      std::vector<double> SA(size_t(2) * nt * nz * pl->kpadA, 0.0);
+      for (int k = 0; k < nfo; ++k)
+        for (int z = 0; z < nz; ++z)
+          for (int t = 0; t < nt; ++t) {
+            const double* s = FXw + size_t(2) * ((size_t(k) * nz + z) * nt + t);
+            double* o = SA.data() + size_t(2) * ((size_t(t) * nz + z) * pl->kpadA + k);
+            o[0] = s[0];
+            o[1] = s[1];
+          }
+      pl->d_SA = reinterpret_cast<double2*>(upload(SA));
+      std::vector<double> om(pl->kpadA, 0.0);
+      pl->d_omega = upload(om);
+    }
+
+    // ---- inverse FFT tables
+    build_czt_tables(desc->n_fft, pl->czt);
+    pl->d_chi = reinterpret_cast<double2*>(upload(pl->czt.chi));
+    pl->d_alpha = upload(pl->czt.alpha);
+    pl->d_twiddle = reinterpret_cast<double2*>(upload(pl->czt.twiddle));
+    PKM_CUDA(cudaMalloc(&pl->d_Bhat, sizeof(double2) * pl->czt.M));
+    czt_prepare_filter(pl);
+    {
+      const long double PI_L = 3.14159265358979323846264338327950288419716939937510L;
+      std::vector<double> wn(size_t(2) * desc->n_fft);
+      for (int r = 0; r < desc->n_fft; ++r) {
+        long double ang = 2.0L * PI_L * (long double)r / (long double)desc->n_fft;
+        wn[2 * r] = (double)cosl(ang);
+        wn[2 * r + 1] = (double)sinl(ang);
+      }
+      pl->d_wn = reinterpret_cast<double2*>(upload(wn));
+    }
+
+    // ---- statistics
+    {
+      std::vector<double> ldt(nt), ldz(nz);
+      for (int t = 0; t < nt; ++t) ldt[t] = std::log(delta_t[t]);
+      for (int z = 0; z < nz; ++z) ldz[z] = std::log(delta_z[z]);
+      pl->d_log_dt = upload(ldt);
+      pl->d_log_dz = upload(ldz);
+    }
+    PKM_CUDA(cudaDeviceSynchronize());
+    *plan_out = pl;
+  });
+  if (rc != PKM_OK) {
+    plan_free(pl);
+    if (plan_out) *plan_out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" int32_t pkm_plan_destroy(pkm_plan* plan) {
+  return guarded([&] { plan_free(plan); });
+}
+
+extern "C" int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes) {
+  return guarded([&] {
+    PKM_REQUIRE(plan, "null plan");
+    PKM_REQUIRE(bytes >= 0, "negative workspace limit");
+    plan->ws_limit = bytes == 0 ? (size_t(4) << 30) : size_t(bytes);
+  });
+}
+
+extern "C" int64_t pkm_plan_launch_count(const pkm_plan* plan) { return plan ? plan->launches : 0; }
+
+// ----------------------------------------------------------------------------
+// shared tail of the two ybar paths: Yhat tile -> irfft -> output layout
+// ----------------------------------------------------------------------------
+namespace {
+
+struct OutSpec {
+  double* out;       // caller buffer (host or device)
+  bool host;
+  int layout;
+  int64_t npix_out;  // pixels of the whole call
+  int n;
+};
+
+int pixel_tile(const pkm_plan* pl, int64_t npix, size_t bytes_per_px) {
+  int64_t t = (int64_t)(pl->ws_limit / std::max<size_t>(bytes_per_px, 1));
+  t = std::min<int64_t>(t, npix + 15);
+  t = std::min<int64_t>(t, 65535LL * 8);
+  t &= ~int64_t(15);
+  return (int)std::max<int64_t>(t, 16);
+}
+
+// ypx tile [np][n] (device) -> caller's buffer
+void emit_tile(pkm_plan* pl, const OutSpec& o, const double* ypx, int64_t pix_off, int np,
+               int slot, cudaStream_t st) {
+  const size_t n = o.n;
+  if (o.layout == PKM_LAYOUT_PIXEL_MAJOR) {
+    double* dst = o.out + (size_t)pix_off * n;
+    PKM_CUDA(cudaMemcpyAsync(dst, ypx, sizeof(double) * n * np,
+                             o.host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  if (!o.host) {
+    launch_transpose(ypx, np, n, o.out, o.npix_out, pix_off, st);
+    pl->launches++;
+    return;
+  }
+  pl->stage_out[slot].reserve(sizeof(double) * n * np);
+  double* tmp = pl->stage_out[slot].as<double>();
+  launch_transpose(ypx, np, n, tmp, np, 0, st);
+  pl->launches++;
+  PKM_CUDA(cudaMemcpy2DAsync(o.out + pix_off, sizeof(double) * o.npix_out, tmp, sizeof(double) * np,
+                             sizeof(double) * np, n, cudaMemcpyDeviceToHost, st));
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------
+// density path
+// ----------------------------------------------------------------------------
+extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
+                                    int32_t nx2, int32_t row_begin, int32_t row_end,
+                                    double* ybar_out, int32_t out_layout, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(pl && dens && ybar_out, "null argument");
+    PKM_REQUIRE(nx1 >= 1 && nx2 >= 1 && row_begin >= 0 && row_end <= nx1 && row_begin <= row_end,
+                "bad pixel range rows [%d,%d) of %d x %d", row_begin, row_end, nx1, nx2);
+    PKM_REQUIRE(out_layout == PKM_LAYOUT_CUBE || out_layout == PKM_LAYOUT_PIXEL_MAJOR, "bad out_layout %d", out_layout);
+    if (pl->d.v0_idx < 0)
+      PKM_THROW(PKM_ERR_NO_ZERO_BIN, "no velocity bin centred on zero (nv=%d): the density path is undefined", pl->d.nv);
+    PKM_REQUIRE(pl->density_ok, "density path unavailable for nv=%d (needs 6 <= nv <= 127)", pl->d.nv);
+    use_device(pl->d.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool in_host = !pkm_is_device_pointer(dens);
+    const bool out_host = !pkm_is_device_pointer(ybar_out);
+    const int nt = pl->d.nt, nv = pl->d.nv, nz = pl->d.nz, n = pl->d.n_fft;
+    const int64_t npix_total = (int64_t)nx1 * nx2;
+    const int64_t pix_begin = (int64_t)row_begin * nx2;
+    const int64_t npix = (int64_t)(row_end - row_begin) * nx2;
+    if (npix == 0) return;
+    const int pxb = coeff_choose_pxb(pl);
+
+    size_t per_px = sizeof(double2) * (size_t)pl->ntz * pl->nfi + sizeof(double2) * pl->nfo + sizeof(double) * n;
+    if (in_host) per_px += sizeof(double) * (size_t)nt * nv * nz;
+    if (out_host && out_layout == PKM_LAYOUT_CUBE) per_px += sizeof(double) * n;
+    int tile = pixel_tile(pl, npix, per_px);
+    tile = std::max(tile / pxb * pxb, pxb);
+    if (tile % 16) tile = (tile + 15) & ~15;
+
+    pl->coef.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
+    pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
+    pl->ypx.reserve(sizeof(double) * (size_t)n * tile);
+    OutSpec o{ybar_out, out_host, out_layout, npix, n};
+
+    for (int64_t p0 = 0; p0 < npix; p0 += tile) {
+      const int np = (int)std::min<int64_t>(tile, npix - p0);
+      const double* src = dens;
+      int64_t src_npix = npix_total, src_pix0 = pix_begin + p0;
+      if (in_host) {
+        pl->stage_in[0].reserve(sizeof(double) * (size_t)nt * nv * nz * np);
+        PKM_CUDA(cudaMemcpy2DAsync(pl->stage_in[0].p, sizeof(double) * (size_t)np * nz,
+                                   dens + (size_t)(pix_begin + p0) * nz,
+                                   sizeof(double) * (size_t)npix_total * nz,
+                                   sizeof(double) * (size_t)np * nz, (size_t)nt * nv,
+                                   cudaMemcpyHostToDevice, st));
+        src = pl->stage_in[0].as<double>();
+        src_npix = np;
+        src_pix0 = 0;
+      }
+      launch_coeff(pl, src, is_log, src_npix, src_pix0, np, tile, pl->coef.as<double2>(), st);
+      launch_contract(pl, pl->coef.as<double2>(), np, tile, pl->yhat.as<double2>(), st);
+      launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
+      emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);
+    }
+    if (in_host || out_host) PKM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// ----------------------------------------------------------------------------
+// Gaussian-LOSVD path
+// ----------------------------------------------------------------------------
+extern "C" int32_t pkm_ybar_gaussian(pkm_plan* pl, const double* P_txz, const double* mu_v,
+                                     const int64_t mu_strides[3], const double* sig_v,
+                                     const int64_t sig_strides[3], const double* omega,
+                                     int32_t nx1, int32_t nx2, int32_t row_begin, int32_t row_end,
+                                     double* ybar_out, int32_t out_layout, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(pl && P_txz && mu_v && sig_v && omega && ybar_out && mu_strides && sig_strides, "null argument");
+    PKM_REQUIRE(nx1 >= 1 && nx2 >= 1 && row_begin >= 0 && row_end <= nx1 && row_begin <= row_end,
+                "bad pixel range rows [%d,%d) of %d x %d", row_begin, row_end, nx1, nx2);
+    PKM_REQUIRE(out_layout == PKM_LAYOUT_CUBE || out_layout == PKM_LAYOUT_PIXEL_MAJOR, "bad out_layout %d", out_layout);
+    use_device(pl->d.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool in_host = !pkm_is_device_pointer(P_txz);
+    PKM_REQUIRE(in_host == !pkm_is_device_pointer(mu_v) && in_host == !pkm_is_device_pointer(sig_v),
+                "P_txz, mu_v and sig_v must all be host or all be device buffers");
+    const bool out_host = !pkm_is_device_pointer(ybar_out);
+    const int nt = pl->d.nt, nz = pl->d.nz, n = pl->d.n_fft;
+    const int64_t npix_total = (int64_t)nx1 * nx2;
+    const int64_t pix_begin = (int64_t)row_begin * nx2;
+    const int64_t npix = (int64_t)(row_end - row_begin) * nx2;
+    if (npix == 0) return;
+
+    // omega is tiny: stage it through the stream (ordered with earlier kernels using it)
+    PKM_CUDA(cudaMemcpyAsync(pl->d_omega, omega, sizeof(double) * pl->nfo, cudaMemcpyDefault, st));
+    PKM_CUDA(cudaStreamSynchronize(st));  // omega may be a pageable temporary of the caller
+
+    size_t per_px = sizeof(double2) * pl->nfo + sizeof(double) * n;
+    if (in_host) per_px += sizeof(double) * (size_t)nt * (nz + 2);
+    if (out_host && out_layout == PKM_LAYOUT_CUBE) per_px += sizeof(double) * n;
+    const int tile = pixel_tile(pl, npix, per_px);
+    pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
+    pl->ypx.reserve(sizeof(double) * (size_t)n * tile);
+    OutSpec o{ybar_out, out_host, out_layout, npix, n};
+    std::vector<double> hmu, hsg;
+
+    for (int64_t p0 = 0; p0 < npix; p0 += tile) {
+      const int np = (int)std::min<int64_t>(tile, npix - p0);
+      const double *dP = P_txz, *dmu = mu_v, *dsg = sig_v;
+      int64_t ms[3] = {mu_strides[0], mu_strides[1], mu_strides[2]};
+      int64_t ss[3] = {sig_strides[0], sig_strides[1], sig_strides[2]};
+      int64_t k_nx2 = nx2, k_npix_total = npix_total, k_pix0 = pix_begin + p0;
+      if (in_host) {
+        const size_t nP = (size_t)nt * np * nz, nM = (size_t)nt * np;
+        pl->stage_in[0].reserve(sizeof(double) * (nP + 2 * nM));
+        double* base = pl->stage_in[0].as<double>();
+        PKM_CUDA(cudaMemcpy2DAsync(base, sizeof(double) * (size_t)np * nz,
+                                   P_txz + (size_t)(pix_begin + p0) * nz,
+                                   sizeof(double) * (size_t)npix_total * nz,
+                                   sizeof(double) * (size_t)np * nz, (size_t)nt,
+                                   cudaMemcpyHostToDevice, st));
+        hmu.resize(nM);
+        hsg.resize(nM);
+        for (int t = 0; t < nt; ++t)
+          for (int i = 0; i < np; ++i) {
+            const int64_t xg = pix_begin + p0 + i, x1 = xg / nx2, x2 = xg % nx2;
+            hmu[(size_t)t * np + i] = mu_v[t * ms[0] + x1 * ms[1] + x2 * ms[2]];
+            hsg[(size_t)t * np + i] = sig_v[t * ss[0] + x1 * ss[1] + x2 * ss[2]];
+          }
+        PKM_CUDA(cudaMemcpyAsync(base + nP, hmu.data(), sizeof(double) * nM, cudaMemcpyHostToDevice, st));
+        PKM_CUDA(cudaMemcpyAsync(base + nP + nM, hsg.data(), sizeof(double) * nM, cudaMemcpyHostToDevice, st));
+        PKM_CUDA(cudaStreamSynchronize(st));  // hmu / hsg are reused by the next tile
+        dP = base;
+        dmu = base + nP;
+        dsg = base + nP + nM;
+        ms[0] = ss[0] = np; ms[1] = ss[1] = 1; ms[2] = ss[2] = 0;
+        k_nx2 = 1; k_npix_total = np; k_pix0 = 0;
+      }
+      launch_gaussian(pl, dP, dmu, ms, dsg, ss, k_nx2, k_npix_total, k_pix0, np, tile,
+                      pl->yhat.as<double2>(), st);
+      launch_irfft_czt(pl, pl->yhat.as<double2>(), np, 1.0, pl->ypx.as<double>(), st);
+      emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);
+    }
+    if (in_host || out_host) PKM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// ----------------------------------------------------------------------------
+// small operators
+// ----------------------------------------------------------------------------
+extern "C" int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
+                                  int64_t n, double* out, int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(n_cmps >= 1 && ybars && weights && out && n >= 0, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool host = !pkm_is_device_pointer(out);
+    for (int c = 0; c < n_cmps; ++c)
+      PKM_REQUIRE(host == !pkm_is_device_pointer(ybars[c]), "all cubes must be on the same side as out");
+    DevBuf tab, data;
+    std::vector<const double*> ptrs(ybars, ybars + n_cmps);
+    double* d_out = out;
+    if (host) {
+      data.reserve(sizeof(double) * (size_t)n * (n_cmps + 1));
+      double* base = data.as<double>();
+      for (int c = 0; c < n_cmps; ++c) {
+        PKM_CUDA(cudaMemcpyAsync(base + (size_t)c * n, ybars[c], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        ptrs[c] = base + (size_t)c * n;
+      }
+      d_out = base + (size_t)n_cmps * n;
+    }
+    tab.reserve(sizeof(double*) * n_cmps + sizeof(double) * n_cmps);
+    const double** d_ptrs = tab.as<const double*>();
+    double* d_w = reinterpret_cast<double*>(d_ptrs + n_cmps);
+    PKM_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), sizeof(double*) * n_cmps, cudaMemcpyHostToDevice, st));
+    PKM_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * n_cmps, cudaMemcpyHostToDevice, st));
+    launch_axpy(n_cmps, d_ptrs, d_w, n, d_out, st);
+    if (host) PKM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    PKM_CUDA(cudaStreamSynchronize(st));  // the pointer table is a local
+    tab.release();
+    data.release();
+  });
+}
+
+extern "C" int32_t pkm_transpose_to_cube(const double* pixel_major, int64_t npix, int64_t n,
+                                         double* cube, int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(pixel_major && cube, "null argument");
+    PKM_REQUIRE(pkm_is_device_pointer(pixel_major) && pkm_is_device_pointer(cube), "device pointers required");
+    use_device(device);
+    launch_transpose(pixel_major, npix, n, cube, npix, 0, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
+static void irfft_common(pkm_plan* pl, const double* Yhat, int64_t npix, double scale, double* out,
+                         void* stream, bool naive) {
+  PKM_REQUIRE(pl && Yhat && out && npix >= 0, "bad argument");
+  use_device(pl->d.device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool in_host = !pkm_is_device_pointer(Yhat), out_host = !pkm_is_device_pointer(out);
+  const double2* dY = reinterpret_cast<const double2*>(Yhat);
+  double* dO = out;
+  if (in_host) {
+    pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * npix);
+    PKM_CUDA(cudaMemcpyAsync(pl->yhat.p, Yhat, sizeof(double2) * (size_t)pl->nfo * npix, cudaMemcpyHostToDevice, st));
+    dY = pl->yhat.as<double2>();
+  }
+  if (out_host) {
+    pl->ypx.reserve(sizeof(double) * (size_t)pl->d.n_fft * npix);
+    dO = pl->ypx.as<double>();
+  }
+  if (naive) launch_irfft_naive(pl, dY, npix, scale, dO, st);
+  else launch_irfft_czt(pl, dY, npix, scale, dO, st);
+  if (out_host) PKM_CUDA(cudaMemcpyAsync(out, dO, sizeof(double) * (size_t)pl->d.n_fft * npix, cudaMemcpyDeviceToHost, st));
+  if (in_host || out_host) PKM_CUDA(cudaStreamSynchronize(st));
+}
+
+extern "C" int32_t pkm_irfft_batch(pkm_plan* pl, const double* Yhat, int64_t npix, double scale,
+                                   double* out, void* stream) {
+  return guarded([&] { irfft_common(pl, Yhat, npix, scale, out, stream, false); });
+}
+extern "C" int32_t pkm_irfft_naive(pkm_plan* pl, const double* Yhat, int64_t npix, double scale,
+                                   double* out, void* stream) {
+  return guarded([&] { irfft_common(pl, Yhat, npix, scale, out, stream, true); });
+}
+
+// ----------------------------------------------------------------------------
+// statistics
+// ----------------------------------------------------------------------------
+extern "C" int32_t pkm_reduce_logp(pkm_plan* pl, const double* log_p_tvxz, int64_t npix,
+                                   const double* log_dv, const double* light_weights,
+                                   uint32_t keep_mask, int32_t density, double* out, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(pl && log_p_tvxz && log_dv && out && npix >= 1, "bad argument");
+    PKM_REQUIRE(keep_mask <= 0xF, "bad keep_mask");
+    use_device(pl->d.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nt = pl->d.nt, nv = pl->d.nv, nz = pl->d.nz;
+    const bool host = !pkm_is_device_pointer(log_p_tvxz);
+    PKM_REQUIRE(host == !pkm_is_device_pointer(out), "input and output must be on the same side");
+    size_t nout = 1;
+    if (keep_mask & 1) nout *= nt;
+    if (keep_mask & 2) nout *= nv;
+    if (keep_mask & 4) nout *= (size_t)npix;
+    if (keep_mask & 8) nout *= nz;
+    const size_t ntot = (size_t)nt * nv * npix * nz;
+    // small constants: log_dv [nv], log light weights [nt][nz]
+    std::vector<double> h(nv + (size_t)nt * nz);
+    for (int v = 0; v < nv; ++v) h[v] = log_dv[v];
+    if (light_weights)
+      for (int i = 0; i < nt * nz; ++i) h[nv + i] = std::log(light_weights[i]);
+    pl->small.reserve(sizeof(double) * h.size());
+    PKM_CUDA(cudaMemcpyAsync(pl->small.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+    PKM_CUDA(cudaStreamSynchronize(st));
+    const double* d_ldv = pl->small.as<double>();
+    const double* d_llw = light_weights ? d_ldv + nv : nullptr;
+    const double* d_in = log_p_tvxz;
+    double* d_out = out;
+    if (host) {
+      pl->stage_in[0].reserve(sizeof(double) * ntot);
+      pl->stage_out[0].reserve(sizeof(double) * nout);
+      PKM_CUDA(cudaMemcpyAsync(pl->stage_in[0].p, log_p_tvxz, sizeof(double) * ntot, cudaMemcpyHostToDevice, st));
+      d_in = pl->stage_in[0].as<double>();
+      d_out = pl->stage_out[0].as<double>();
+    }
+    launch_reduce_logp(pl, d_in, npix, d_ldv, d_llw, keep_mask, density, d_out, st);
+    if (host) {
+      PKM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+      PKM_CUDA(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+extern "C" int32_t pkm_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,
+                               double* out, int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(P && values && out && nvar >= 1 && ncond >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool host = !pkm_is_device_pointer(P);
+    PKM_REQUIRE(host == !pkm_is_device_pointer(out) && host == !pkm_is_device_pointer(values),
+                "P, values and out must be on the same side");
+    if (!host) {
+      launch_moments(P, values, nvar, ncond, out, st);
+      return;
+    }
+    DevBuf buf;
+    const size_t nP = (size_t)nvar * ncond;
+    buf.reserve(sizeof(double) * (nP + nvar + 4 * (size_t)ncond));
+    double* dP = buf.as<double>();
+    double* dV = dP + nP;
+    double* dO = dV + nvar;
+    PKM_CUDA(cudaMemcpyAsync(dP, P, sizeof(double) * nP, cudaMemcpyHostToDevice, st));
+    PKM_CUDA(cudaMemcpyAsync(dV, values, sizeof(double) * nvar, cudaMemcpyHostToDevice, st));
+    launch_moments(dP, dV, nvar, ncond, dO, st);
+    PKM_CUDA(cudaMemcpyAsync(out, dO, sizeof(double) * 4 * (size_t)ncond, cudaMemcpyDeviceToHost, st));
+    PKM_CUDA(cudaStreamSynchronize(st));
+    buf.release();
+  });
+}
+
+extern "C" int32_t pkm_max(const double* x, int64_t n, double* result_host, int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(x && result_host && n >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool host = !pkm_is_device_pointer(x);
+    DevBuf buf;
+    buf.reserve(sizeof(double) * (2 + (host ? (size_t)n : 0)));
+    double* d_res = buf.as<double>();
+    const double* dx = x;
+    if (host) {
+      PKM_CUDA(cudaMemcpyAsync(d_res + 2, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+      dx = d_res + 2;
+    }
+    launch_max(dx, n, d_res, st);
+    PKM_CUDA(cudaMemcpyAsync(result_host, d_res, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PKM_CUDA(cudaStreamSynchronize(st));
+    buf.release();
+  });
+}
+
+extern "C" int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t mode, uint64_t seed,
+                             uint64_t offset, double ybar_max, double* yobs, double* sigma_out,
+                             int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(ybar && n >= 1 && (yobs || sigma_out), "bad argument");
+    PKM_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (ShotNoise) or 1 (ConstantSNR)");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool host = !pkm_is_device_pointer(ybar);
+    if (yobs) PKM_REQUIRE(host == !pkm_is_device_pointer(yobs), "ybar and yobs must be on the same side");
+    if (sigma_out) PKM_REQUIRE(host == !pkm_is_device_pointer(sigma_out), "ybar and sigma_out must be on the same side");
+    DevBuf buf;
+    const size_t nn = (size_t)n;
+    buf.reserve(sizeof(double) * (2 + (host ? 3 * nn : 0)));
+    double* d_max = buf.as<double>();
+    const double* dy = ybar;
+    double *dobs = yobs, *dsig = sigma_out;
+    if (host) {
+      double* base = d_max + 2;
+      PKM_CUDA(cudaMemcpyAsync(base, ybar, sizeof(double) * nn, cudaMemcpyHostToDevice, st));
+      dy = base;
+      dobs = yobs ? base + nn : nullptr;
+      dsig = sigma_out ? base + 2 * nn : nullptr;
+    }
+    if (mode == 0) {
+      // numpy: max(ybar)**0.5 - a negative or NaN maximum gives NaN everywhere (noise.py:68-70)
+      if (ybar_max >= 0.0 || ybar_max != ybar_max) {
+        PKM_CUDA(cudaMemcpyAsync(d_max, &ybar_max, sizeof(double), cudaMemcpyHostToDevice, st));
+        PKM_CUDA(cudaStreamSynchronize(st));
+      } else {
+        launch_max(dy, n, d_max, st);
+      }
+    }
+    launch_noise(dy, n, snr, mode, seed, offset, d_max, dobs, dsig, st);
+    if (host) {
+      if (yobs) PKM_CUDA(cudaMemcpyAsync(yobs, dobs, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+      if (sigma_out) PKM_CUDA(cudaMemcpyAsync(sigma_out, dsig, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+    }
+    PKM_CUDA(cudaStreamSynchronize(st));
+    buf.release();
+  });
+}
+
+extern "C" int32_t pkm_fp64_fma_peak(int32_t device, int32_t repeats, double* tflops_out) {
+  return guarded([&] {
+    PKM_REQUIRE(tflops_out && repeats >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible");
+    use_device(device);
+    cudaDeviceProp prop;
+    PKM_CUDA(cudaGetDeviceProperties(&prop, device));
+    *tflops_out = run_fma_probe(prop.multiProcessorCount, repeats);
+  });
+}

@@ -277,8 +277,9 @@ k_contract(const double2* __restrict__ Sp, const double2* __restrict__ cT,
   }
 }
 
-void launch_contract(pkm_plan* pl, const double2* cT, int xpad, double2* yhat, cudaStream_t st) {
-  dim3 grid((pl->slots.nunit + 7) / 8, xpad / 8);
+void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
+                     cudaStream_t st) {
+  dim3 grid((pl->slots.nunit + 7) / 8, (npix_tile + 7) / 8);
   k_contract<<<grid, 256, 0, st>>>(pl->d_Sp, cT, pl->d_group_span, pl->d_slot_w, pl->d_slot_k, yhat,
                                    pl->ntz, pl->nfi, xpad, pl->slots.nslot, pl->slots.nunit, pl->nfo);
   PKM_CUDA(cudaGetLastError());

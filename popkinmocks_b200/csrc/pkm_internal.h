@@ -136,7 +136,7 @@ struct pkm_plan {
   std::vector<double> h_delta_t, h_delta_z;
 
   // workspace
-  DevBuf coef, yhat, ypx, stage_in[2], stage_out[2], misc;
+  DevBuf coef, yhat, ypx, stage_in[2], stage_out[2], misc, small;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr};
@@ -149,7 +149,8 @@ struct pkm_plan {
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
                   int64_t pix0, int npix_tile, int xpad, double2* cT, cudaStream_t st);
 // kernel 2: coefficients -> Yhat[xpad][nfo]
-void launch_contract(pkm_plan* pl, const double2* cT, int xpad, double2* yhat, cudaStream_t st);
+void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
+                     cudaStream_t st);
 // gaussian path -> Yhat[xpad][nfo]
 void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
@@ -180,3 +181,4 @@ void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t 
                   cudaStream_t st);
 
 bool pkm_is_device_pointer(const void* p);
+double run_fma_probe(int num_sms, int repeats);  // TFLOP/s

@@ -8,6 +8,7 @@
 //  * pkm_moments: mean and central moments 2..4 of P[nvar][ncond] along axis 0 (base.py:208-260).
 //  * pkm_noise: ShotNoise / ConstantSNR sigma maps and Gaussian sampling (noise.py:29-71),
 //    Philox4x32-10 counter RNG + Box-Muller in FP64.
+#include <algorithm>
 #include <cmath>
 
 #include "pkm_internal.h"
@@ -386,4 +387,50 @@ void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t 
   int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   k_noise<<<grid, 256, 0, st>>>(ybar, n, snr, mode, seed, offset, d_max, yobs, sigma);
   PKM_CUDA(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------
+// FP64 FMA throughput probe (roofline denominator of the FP64-pipe-bound kernels; the
+// driver-written MEASURED_PEAKS.json has no FP64 figure).  8 independent DFMA chains per
+// thread, 256 threads x 8 CTAs per SM.
+// ----------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+k_fma_probe(double* sink, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) sink[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace
+
+double run_fma_probe(int num_sms, int repeats) {
+  double* sink = nullptr;
+  PKM_CUDA(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  PKM_CUDA(cudaEventCreate(&e0));
+  PKM_CUDA(cudaEventCreate(&e1));
+  const int iters = 4096, grid = num_sms * 8;
+  double best = 0.0;
+  for (int r = 0; r < repeats + 1; ++r) {
+    PKM_CUDA(cudaEventRecord(e0));
+    k_fma_probe<<<grid, 256>>>(sink, iters, 0.999999, 1e-9);
+    PKM_CUDA(cudaEventRecord(e1));
+    PKM_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PKM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * iters * 256.0 * grid;
+    if (r > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return best;
 }

@@ -1,0 +1,254 @@
+"""Host-side driver of the CUDA hot path: plans and marshalling.
+
+A `Plan` wraps one `pkm_plan*` (include/pkm_b200.h): the device-resident constant
+operands of one (IFUCube, milesSSPs) pair - S-hat' = FXw*dz*dt, the folded
+DFT x spline matrices, the 4-tap spline tables, chirp-z FFT tables - plus its
+workspace.  Plans are cached on the cube (`cube._pkm_plans`), one per device.
+
+Everything numerical happens inside libpkm_b200.so; this module only validates,
+shapes and hands over pointers.  NumPy arrays are host buffers (the library
+stages them), torch CUDA tensors are passed through as device pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _is_cuda_tensor(x):
+    return _is_torch(x) and x.is_cuda
+
+
+def find_v0_idx(cube):
+    """Index of the velocity bin centred on zero, or -1 (base.py:820-823 raises IndexError)."""
+    v = (cube.v_edg[:-1] + cube.v_edg[1:]) / 2.0
+    hit = np.where(np.isclose(v, 0.0))[0]
+    return int(hit[0]) if hit.size else -1
+
+
+class Plan:
+    """Device-resident constants of one cube on one GPU."""
+
+    def __init__(self, cube, device=0):
+        _lib.require_gpu()
+        ssps = cube.ssps
+        nz, nt = ssps.par_dims
+        self.nt, self.nz, self.nv = int(nt), int(nz), int(cube.nv)
+        self.n_fft = int(ssps.n_fft)
+        self.nfo = self.n_fft // 2 + 1
+        self.device = int(device)
+        desc = _lib.CubeDesc(nt=self.nt, nz=self.nz, nv=self.nv, n_fft=self.n_fft,
+                             v0_idx=find_v0_idx(cube), device=self.device, precision=0,
+                             reserved=0, dv=float(ssps.dv), dx=float(cube.dx), dy=float(cube.dy))
+        FXw = np.ascontiguousarray(ssps.FXw, dtype=np.complex128)
+        if FXw.shape != (self.nfo, self.nz * self.nt):
+            raise ValueError(f"ssps.FXw has shape {FXw.shape}, expected {(self.nfo, self.nz * self.nt)}")
+        dt = _lib.as_f64(ssps.delta_t)
+        dz = _lib.as_f64(ssps.delta_z)
+        handle = C.c_void_p()
+        _lib.check(_lib.load().pkm_plan_create(C.byref(desc), _lib.ptr(FXw), _lib.ptr(dt),
+                                               _lib.ptr(dz), C.byref(handle)))
+        self._h = handle
+        # omega_k of the Gaussian path: linspace(0, pi, nfo)/dv (parametric.py:360-362)
+        self.omega = np.linspace(0, np.pi, self.nfo)
+        self.omega /= ssps.dv
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.load().pkm_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    @property
+    def launches(self):
+        return int(_lib.load().pkm_plan_launch_count(self._h))
+
+    def set_workspace_limit(self, nbytes):
+        _lib.check(_lib.load().pkm_plan_set_workspace_limit(self._h, int(nbytes)))
+
+    # ------------------------------------------------------------------
+    def _alloc_out(self, like_device, rows, nx2, layout):
+        shape = (self.n_fft, rows, nx2) if layout == _lib.LAYOUT_CUBE else (rows * nx2, self.n_fft)
+        if like_device:
+            import torch
+            return torch.empty(shape, dtype=torch.float64, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype=np.float64)
+
+    def ybar_density(self, dens, is_log=True, rows=None, out=None, layout=_lib.LAYOUT_CUBE,
+                     stream=None):
+        """Component.evaluate_ybar (base.py:789-882) for x1 rows `rows=(begin, end)`.
+
+        dens: [nt, nv, nx1, nx2, nz] float64 - log p if `is_log` else p; NumPy (host) or a
+        torch CUDA tensor.  Returns ybar for the rows, [n_fft, nrows, nx2] (cube layout) or
+        [nrows*nx2, n_fft] (pixel-major), on the same side as the input unless `out` is given."""
+        if tuple(dens.shape[:2]) != (self.nt, self.nv) or dens.shape[-1] != self.nz or len(dens.shape) != 5:
+            raise ValueError(f"density has shape {tuple(dens.shape)}, expected (nt={self.nt}, "
+                             f"nv={self.nv}, nx1, nx2, nz={self.nz})")
+        nx1, nx2 = int(dens.shape[2]), int(dens.shape[3])
+        r0, r1 = (0, nx1) if rows is None else (int(rows[0]), int(rows[1]))
+        on_dev = _is_cuda_tensor(dens)
+        if on_dev:
+            import torch
+            if dens.dtype != torch.float64 or not dens.is_contiguous():
+                dens = dens.to(torch.float64).contiguous()
+        else:
+            dens = _lib.as_f64(dens)
+        if out is None:
+            out = self._alloc_out(on_dev, r1 - r0, nx2, layout)
+        _lib.check(_lib.load().pkm_ybar_density(self._h, _lib.ptr(dens), int(bool(is_log)), nx1, nx2,
+                                                r0, r1, _lib.ptr(out), layout,
+                                                _lib.stream_ptr(stream)))
+        return out
+
+    def ybar_gaussian(self, P_txz, mu_v, sig_v, rows=None, out=None, layout=_lib.LAYOUT_CUBE,
+                      stream=None):
+        """ParametricComponent.evaluate_ybar (parametric.py:335-407) for x1 rows `rows`.
+
+        P_txz [nt, nx1, nx2, nz]; mu_v, sig_v broadcastable to [nt, nx1, nx2] (NumPy broadcast
+        views are passed by stride, not copied)."""
+        if len(P_txz.shape) != 4 or P_txz.shape[0] != self.nt or P_txz.shape[-1] != self.nz:
+            raise ValueError(f"P_txz has shape {tuple(P_txz.shape)}, expected (nt={self.nt}, nx1, "
+                             f"nx2, nz={self.nz})")
+        nx1, nx2 = int(P_txz.shape[1]), int(P_txz.shape[2])
+        r0, r1 = (0, nx1) if rows is None else (int(rows[0]), int(rows[1]))
+        on_dev = _is_cuda_tensor(P_txz)
+        if on_dev:
+            import torch
+            P_txz = P_txz.to(torch.float64).contiguous()
+            mu_v = torch.broadcast_to(mu_v.to(torch.float64), (self.nt, nx1, nx2))
+            sig_v = torch.broadcast_to(sig_v.to(torch.float64), (self.nt, nx1, nx2))
+            mstr = [int(s) for s in mu_v.stride()]
+            sstr = [int(s) for s in sig_v.stride()]
+        else:
+            P_txz = _lib.as_f64(P_txz)
+            mu_v = np.broadcast_to(np.asarray(mu_v, dtype=np.float64), (self.nt, nx1, nx2))
+            sig_v = np.broadcast_to(np.asarray(sig_v, dtype=np.float64), (self.nt, nx1, nx2))
+            mstr = [s // 8 for s in mu_v.strides]
+            sstr = [s // 8 for s in sig_v.strides]
+        if out is None:
+            out = self._alloc_out(on_dev, r1 - r0, nx2, layout)
+        ms = (C.c_int64 * 3)(*mstr)
+        ss = (C.c_int64 * 3)(*sstr)
+        _lib.check(_lib.load().pkm_ybar_gaussian(self._h, _lib.ptr(P_txz), _lib.ptr(mu_v), ms,
+                                                 _lib.ptr(sig_v), ss, _lib.ptr(self.omega), nx1, nx2,
+                                                 r0, r1, _lib.ptr(out), layout,
+                                                 _lib.stream_ptr(stream)))
+        return out
+
+    def irfft(self, Yhat, scale=1.0, naive=False):
+        """Batched inverse real FFT of length n_fft: Yhat [npix, nfo] complex128 -> [npix, n_fft]."""
+        Yhat = np.ascontiguousarray(Yhat, dtype=np.complex128)
+        npix = Yhat.shape[0]
+        out = np.empty((npix, self.n_fft))
+        fn = _lib.load().pkm_irfft_naive if naive else _lib.load().pkm_irfft_batch
+        _lib.check(fn(self._h, _lib.ptr(Yhat), npix, float(scale), _lib.ptr(out), None))
+        return out
+
+    def reduce_logp(self, log_p_tvxz, log_dv, keep, density, light_weights=None):
+        """log-marginal of the pixelated density over the axes NOT in `keep` (subset of 'tvxz').
+
+        Returns the array with kept axes in (t, v, x1, x2, z) order (base.py:884-1174)."""
+        on_dev = _is_cuda_tensor(log_p_tvxz)
+        if not on_dev:
+            log_p_tvxz = _lib.as_f64(log_p_tvxz)
+        nt, nv, nx1, nx2, nz = [int(s) for s in log_p_tvxz.shape]
+        mask = sum(bit for ax, bit in zip("tvxz", (1, 2, 4, 8)) if ax in keep)
+        shape = []
+        if "t" in keep:
+            shape.append(nt)
+        if "v" in keep:
+            shape.append(nv)
+        if "x" in keep:
+            shape += [nx1, nx2]
+        if "z" in keep:
+            shape.append(nz)
+        if on_dev:
+            import torch
+            out = torch.empty(tuple(shape), dtype=torch.float64, device=log_p_tvxz.device)
+        else:
+            out = np.empty(tuple(shape), dtype=np.float64)
+        lw = None if light_weights is None else _lib.as_f64(light_weights)
+        ldv = _lib.as_f64(log_dv)
+        _lib.check(_lib.load().pkm_reduce_logp(self._h, _lib.ptr(log_p_tvxz), nx1 * nx2, _lib.ptr(ldv),
+                                               _lib.ptr(lw), mask, int(bool(density)), _lib.ptr(out),
+                                               None))
+        return out
+
+
+def get_plan(cube, device=0):
+    """The cube's plan for `device` (created on first use)."""
+    cache = cube.__dict__.setdefault("_pkm_plans", {})
+    key = int(device)
+    if key not in cache:
+        cache[key] = Plan(cube, device=key)
+    return cache[key]
+
+
+def axpy_cubes(ybars, weights, device=0):
+    """sum_i w_i * ybar_i (Mixture.evaluate_ybar, mixture.py:35-48)."""
+    _lib.require_gpu()
+    on_dev = _is_cuda_tensor(ybars[0])
+    if on_dev:
+        import torch
+        ybars = [y.contiguous() for y in ybars]
+        out = torch.empty_like(ybars[0])
+    else:
+        ybars = [_lib.as_f64(y) for y in ybars]
+        out = np.empty_like(ybars[0])
+    n = int(np.prod(ybars[0].shape))
+    ptrs = (C.c_void_p * len(ybars))(*[_lib.ptr(y) for y in ybars])
+    w = _lib.as_f64(weights)
+    _lib.check(_lib.load().pkm_axpy_cubes(len(ybars), ptrs, _lib.ptr(w), n, _lib.ptr(out), int(device), None))
+    return out
+
+
+def moments(P, values, device=0):
+    """Mean and central moments 2..4 along axis 0 of P[nvar, ...] (base.py:208-260).
+
+    Returns an array [4, ...]: mean, mu2, mu3, mu4."""
+    _lib.require_gpu()
+    P = _lib.as_f64(P)
+    values = _lib.as_f64(values)
+    nvar = P.shape[0]
+    ncond = int(np.prod(P.shape[1:])) if P.ndim > 1 else 1
+    out = np.empty((4,) + P.shape[1:])
+    _lib.check(_lib.load().pkm_moments(_lib.ptr(P), _lib.ptr(values), nvar, ncond, _lib.ptr(out),
+                                       int(device), None))
+    return out
+
+
+def noise(ybar, snr, mode, seed=0, offset=0, ybar_max=-1.0, want_sigma=True, want_sample=True,
+          device=0):
+    """ShotNoise (mode 0) / ConstantSNR (mode 1) sigma map and one noisy realisation (noise.py:16-71)."""
+    _lib.require_gpu()
+    on_dev = _is_cuda_tensor(ybar)
+    if on_dev:
+        import torch
+        ybar = ybar.contiguous()
+        yobs = torch.empty_like(ybar) if want_sample else None
+        sigma = torch.empty_like(ybar) if want_sigma else None
+    else:
+        ybar = _lib.as_f64(ybar)
+        yobs = np.empty_like(ybar) if want_sample else None
+        sigma = np.empty_like(ybar) if want_sigma else None
+    n = int(np.prod(ybar.shape))
+    _lib.check(_lib.load().pkm_noise(_lib.ptr(ybar), n, float(snr), int(mode), int(seed), int(offset),
+                                     float(ybar_max), _lib.ptr(yobs), _lib.ptr(sigma), int(device), None))
+    return yobs, sigma
+
+
+def fp64_fma_peak(device=0, repeats=5):
+    """Measured FP64 FMA throughput (TFLOP/s) - roofline denominator of the FP64-bound kernels."""
+    out = C.c_double(0.0)
+    _lib.check(_lib.load().pkm_fp64_fma_peak(int(device), int(repeats), C.byref(out)))
+    return out.value

@@ -1,0 +1,125 @@
+"""GPU parity tests: the CUDA hot path (through the C ABI) against reference outputs.
+
+tests/golden/*.npz were produced by executing the unmodified reference
+(oracle/make_golden.py); the NumPy restatement (oracle/restatement.py) is used for inputs
+the golden files do not cover.  Tolerances: fp64 path <= 1e-10 max-norm relative
+(BASELINE.json north_star); indexing / layout exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_cube, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _plan(name):
+    from popkinmocks_b200 import engine
+    return engine.get_plan(golden_cube(name))
+
+
+@pytest.mark.parametrize("name,tags", [
+    ("g1_conftest_full_nv41", ["d1_", "d2_", "s1_"]),
+    ("g2_rebin_nv21_prime", ["d1_", "s1_"]),
+    ("g3_full_nv101_odd", ["d1_"]),
+    ("g4_even_nv40", ["d2_"]),
+])
+def test_gaussian_path_matches_reference(gpu_ok, name, tags):
+    g = load_golden(name)
+    plan = _plan(name)
+    for tag in tags:
+        y = plan.ybar_gaussian(g[tag + "P_txz"], g[tag + "mu_v"], g[tag + "sig_v"])
+        ref = g[tag + "ybar"]
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < TOL, (name, tag, rel_err(y, ref))
+
+
+@pytest.mark.parametrize("name,tags", [
+    ("g1_conftest_full_nv41", ["b_"]),
+    ("g2_rebin_nv21_prime", ["b_", "wn_"]),
+    ("g3_full_nv101_odd", ["wn_"]),
+])
+def test_density_path_matches_reference(gpu_ok, name, tags):
+    g = load_golden(name)
+    plan = _plan(name)
+    for tag in tags:
+        y = plan.ybar_density(g[tag + "log_p_tvxz"], is_log=True)
+        ref = g[tag + "ybar"]
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < TOL, (name, tag, rel_err(y, ref))
+        # linear-density input gives the same cube
+        with np.errstate(over="ignore"):
+            y2 = plan.ybar_density(np.exp(g[tag + "log_p_tvxz"]), is_log=False)
+        assert rel_err(y2, ref) < TOL
+
+
+def test_density_even_nv_raises_index_error(gpu_ok):
+    g = load_golden("g4_even_nv40")
+    assert str(g["b_error"]) == "IndexError"
+    plan = _plan("g4_even_nv40")
+    cube = golden_cube("g4_even_nv40")
+    p = np.zeros(cube.get_distribution_shape("tvxz"))
+    with pytest.raises(IndexError):
+        plan.ybar_density(p, is_log=False)
+
+
+@pytest.mark.parametrize("name", ["g1_conftest_full_nv41", "g2_rebin_nv21_prime", "g3_full_nv101_odd"])
+def test_irfft_matches_numpy(gpu_ok, name):
+    plan = _plan(name)
+    rng = np.random.default_rng(7)
+    Y = rng.standard_normal((5, plan.nfo)) + 1j * rng.standard_normal((5, plan.nfo))
+    ref = np.fft.irfft(Y, plan.n_fft, axis=1)
+    assert rel_err(plan.irfft(Y), ref) < 1e-13
+    assert rel_err(plan.irfft(Y, naive=True), ref) < 1e-12
+
+
+def test_row_ranges_and_pixel_major_layout(gpu_ok):
+    from popkinmocks_b200 import _lib
+    g = load_golden("g2_rebin_nv21_prime")
+    plan = _plan("g2_rebin_nv21_prime")
+    ref = g["wn_ybar"]                                   # [n_fft, 4, 5]
+    logp = g["wn_log_p_tvxz"]
+    part = plan.ybar_density(logp, rows=(1, 3))
+    assert part.shape == (plan.n_fft, 2, 5)
+    assert rel_err(part, ref[:, 1:3]) < TOL
+    pm = plan.ybar_density(logp, rows=(2, 4), layout=_lib.LAYOUT_PIXEL_MAJOR)
+    assert pm.shape == (10, plan.n_fft)
+    assert rel_err(pm.reshape(2, 5, -1), np.moveaxis(ref[:, 2:4], 0, -1)) < TOL
+    pa = plan.ybar_gaussian(g["d1_P_txz"], g["d1_mu_v"], g["d1_sig_v"], rows=(3, 4))
+    assert rel_err(pa, g["d1_ybar"][:, 3:4]) < TOL
+
+
+def test_small_workspace_tiles_pixels(gpu_ok):
+    g = load_golden("g2_rebin_nv21_prime")
+    plan = _plan("g2_rebin_nv21_prime")
+    plan.set_workspace_limit(1 << 16)      # forces 16-pixel tiles -> 2 tiles for 20 pixels
+    try:
+        y = plan.ybar_density(g["wn_log_p_tvxz"])
+        ya = plan.ybar_gaussian(g["s1_P_txz"], g["s1_mu_v"], g["s1_sig_v"])
+    finally:
+        plan.set_workspace_limit(0)
+    assert rel_err(y, g["wn_ybar"]) < TOL
+    assert rel_err(ya, g["s1_ybar"]) < TOL
+
+
+def test_device_resident_inputs(gpu_ok):
+    import torch
+    g = load_golden("g2_rebin_nv21_prime")
+    plan = _plan("g2_rebin_nv21_prime")
+    d = torch.from_numpy(g["wn_log_p_tvxz"]).cuda()
+    y = plan.ybar_density(d)
+    torch.cuda.synchronize()
+    assert y.is_cuda and tuple(y.shape) == g["wn_ybar"].shape
+    assert rel_err(y.cpu().numpy(), g["wn_ybar"]) < TOL
+    P, mu, sg = (torch.from_numpy(np.ascontiguousarray(g["s1_" + k])).cuda() for k in ("P_txz", "mu_v", "sig_v"))
+    ya = plan.ybar_gaussian(P, mu, sg)
+    torch.cuda.synchronize()
+    assert rel_err(ya.cpu().numpy(), g["s1_ybar"]) < TOL
+
+
+def test_mixture_axpy(gpu_ok):
+    from popkinmocks_b200 import engine
+    g = load_golden("g1_conftest_full_nv41")
+    out = engine.axpy_cubes([g["d1_ybar"], g["d2_ybar"], g["s1_ybar"]], g["mix_weights"])
+    assert rel_err(out, g["mix_ybar"]) < 1e-15
