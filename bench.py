@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py - evaluate_ybar cube voxels/s on B200 (the BASELINE.json metric).
+
+Workload: the density path `Component.evaluate_ybar`
+(reference: popkinmocks/components/base.py:789-882) on a synthetic 201x201-pixel cube over the
+full MILES_BASTI grid (nt=53, nz=12), nv=101, lambda 4700-6500 A -> n_fft=4907; voxel = one
+(omega, x1, x2) sample.  One "step" = one whole-cube evaluate_ybar.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                        # the reference's CPU algorithm
+
+N > 1 (torchrun, one rank per GPU): weak scaling - every rank evaluates its own 201x201-pixel
+row block of a (201*N)x201 mosaic (pixels are independent) and the blocks are
+gathered on rank 0 over NCCL inside the timed region; `--scaling strong` shards ONE 201x201
+cube by x1 rows instead.
+
+The JSON line printed by rank 0 follows the driver contract: `value` = device-resident
+throughput, `e2e` = the same call through the C ABI with pinned HOST buffers (H2D of the
+density and D2H of the cube inside the timed region), `roofline` for the dominant kernel
+(timed live with CUDA events on its launch stream), `cpu_baseline` = the oracle port on the
+box's host cores (bounded sample), `clocks` sampled with nvidia-smi during the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "evaluate_ybar cube voxels/s"
+UNIT = "voxel/s"
+B_VOX_NOTE = "SURVEY.md 8d canonical bytes/voxel with P-hat staged through HBM once"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=201, help="pixels per side of one cube")
+    ap.add_argument("--nv", type=int, default=101)
+    ap.add_argument("--lmd", type=float, nargs=2, default=(4700.0, 6500.0))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="host processes of the CPU legs (0 = all cores, max 64)")
+    ap.add_argument("--cpu-px", type=int, default=2, help="pixels per CPU task")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# workload description shared by both arms
+# ----------------------------------------------------------------------------------------------
+def build_cube(args, nx1=None):
+    import popkinmocks_b200 as pkm
+    ssps = pkm.milesSSPs(lmd_min=args.lmd[0], lmd_max=args.lmd[1])
+    # x1 extent scales with the number of rows so dx (and the result per pixel) is unchanged
+    nx1 = nx1 or args.nx
+    return pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx1, nx2=args.nx, nv=args.nv,
+                                x1rng=(-1.0 * nx1 / args.nx, 1.0 * nx1 / args.nx),
+                                x2rng=(-1.0, 1.0), vrng=(-1000.0, 1000.0))
+
+
+def workload_config(args, cube):
+    nz, nt = cube.ssps.par_dims
+    return {
+        "workload": f"C4 synthetic density cube {args.nx}x{args.nx} px per GPU-block, full MILES_BASTI grid "
+                    f"nt={nt} nz={nz}, nv={args.nv}, lmd {args.lmd[0]:.0f}-{args.lmd[1]:.0f} A, "
+                    f"n_fft={cube.ssps.n_fft} (path B: Component.evaluate_ybar on log_p_tvxz)",
+        "nx1": args.nx, "nx2": args.nx, "nv": args.nv, "nt": int(nt), "nz": int(nz),
+        "n_fft": int(cube.ssps.n_fft),
+        "l2": "inputs (20.8 GB density per cube) are far larger than the 126 MB L2; no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs: the oracle port of the reference algorithm on host cores
+# ----------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(consts):
+    _CPU.update(consts)
+
+
+def _cpu_task(seed):
+    """One tile of `px` pixels through the reference's literal algorithm (oracle/restatement.py)."""
+    from oracle import restatement as R
+    c = _CPU
+    rng = np.random.default_rng(seed)
+    p = rng.random((c["nt"], c["nv"], 1, c["px"], c["nz"]))
+    t0 = time.perf_counter()
+    y = R.ybar_density_literal(p, c["v_edg"], c["FXw"], c["par_dims"], c["n_fft"], c["dv"],
+                               c["delta_t"], c["delta_z"], c["dx"], c["dy"])
+    return time.perf_counter() - t0, float(y.sum())
+
+
+def cpu_consts(cube, px):
+    s = cube.ssps
+    nz, nt = s.par_dims
+    return dict(nt=int(nt), nz=int(nz), nv=cube.nv, px=px, v_edg=cube.v_edg, FXw=s.FXw,
+                par_dims=tuple(s.par_dims), n_fft=s.n_fft, dv=s.dv, delta_t=s.delta_t,
+                delta_z=s.delta_z, dx=cube.dx, dy=cube.dy)
+
+
+def cpu_procs(args):
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    return max(1, min(args.cpu_procs or n, 64))
+
+
+class CpuArm:
+    """A fork pool of host workers, created BEFORE CUDA is initialised in this process."""
+
+    def __init__(self, args, cube):
+        import multiprocessing as mp
+        self.nproc = cpu_procs(args)
+        self.px = args.cpu_px
+        self.n_fft = cube.ssps.n_fft
+        self.pool = mp.get_context("fork").Pool(self.nproc, initializer=_cpu_init,
+                                                initargs=(cpu_consts(cube, self.px),))
+        self.seed = 1000
+
+    def step(self):
+        """One bounded sample: every worker evaluates one tile.  Returns (seconds, voxels)."""
+        seeds = list(range(self.seed, self.seed + self.nproc))
+        self.seed += self.nproc
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_task, seeds, chunksize=1)
+        dt = time.perf_counter() - t0
+        return dt, self.nproc * self.px * self.n_fft
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cube = build_cube(args)
+    arm = CpuArm(args, cube)
+    for _ in range(args.warmup):
+        arm.step()
+    tot_s, tot_v = 0.0, 0
+    for _ in range(args.steps):
+        s, v = arm.step()
+        tot_s += s
+        tot_v += v
+    arm.close()
+    value = tot_v / tot_s
+    sample = (f"{arm.nproc} workers x {arm.px} px per step (oracle port of base.py:836-859, "
+              f"irfft per (t,z)); reference is single-threaded, one tile per core")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, cube),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.nproc, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.proc = None
+        self.path = f"/tmp/pkm_clocks_{os.getpid()}.csv"
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001 - nvidia-smi missing
+            self.proc = None
+        self.marks = []
+
+    def mark(self):
+        """Current number of lines written (to cut out the timed window later)."""
+        try:
+            self.fh.flush()
+            with open(self.path) as f:
+                return sum(1 for _ in f)
+        except Exception:  # noqa: BLE001
+            return 0
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.fh.close()
+        rows = []
+        with open(self.path) as f:
+            lines = [ln.strip() for ln in f if ln.strip()]
+        os.unlink(self.path)
+        keep = []
+        for a, b in windows:
+            keep += lines[a:max(b, a + 1)]
+        if not keep:
+            keep = lines
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        power = []
+        for ln in keep:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                rows.append((float(parts[0]), float(parts[1])))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": max(r[1] for r in rows),
+                "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------------------------
+# the CUDA arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    # ---- host-side setup and the CPU baseline leg (fork pool: before any CUDA initialisation)
+    cube = build_cube(args)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        arm = CpuArm(args, cube)
+        arm.step()                      # warm the workers (imports, first-touch)
+        tot_s, tot_v = 0.0, 0
+        while tot_s < 8.0:
+            s, v = arm.step()
+            tot_s += s
+            tot_v += v
+        arm.close()
+        cpu = {"value": tot_v / tot_s, "unit": UNIT, "cores": arm.nproc, "kind": "port",
+               "sample": f"{tot_v // cube.ssps.n_fft} pixels in {tot_s:.1f} s wall: {arm.nproc} workers x "
+                         f"{arm.px} px tiles of the same synthetic workload through oracle/restatement.py "
+                         f"ybar_density_literal (reference order: irfft per (t,z), base.py:836-859)"}
+
+    import torch
+    import torch.distributed as dist
+    from popkinmocks_b200 import _lib, engine
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nz, nt = cube.ssps.par_dims
+    nv, nx, n_fft = args.nv, args.nx, int(cube.ssps.n_fft)
+    plan = engine.Plan(cube, device=local)
+
+    # ---- this rank's share
+    if args.scaling == "weak" or world == 1:
+        rows = nx                       # one whole nx x nx block per rank
+    else:
+        r0 = rank * nx // world
+        rows = (rank + 1) * nx // world - r0
+    npix = rows * nx
+    total_pix = npix if world == 1 else (nx * nx * world if args.scaling == "weak" else nx * nx)
+    voxels_per_step = total_pix * n_fft
+
+    # ---- synthetic density (log p, as Component(cube, log_p_tvxz) holds it), generated on device
+    gen = torch.Generator(device=dev).manual_seed(20241019 + rank)
+    logp = torch.empty((nt, nv, rows, nx, nz), dtype=torch.float64, device=dev)
+    for t in range(nt):                 # slab-wise to keep the temporary small
+        logp[t] = torch.rand((nv, rows, nx, nz), dtype=torch.float64, device=dev, generator=gen)
+    dV = float(np.mean(cube.ssps.delta_t) * np.mean(cube.ssps.delta_z) * cube.dx * cube.dy * cube.ssps.dv)
+    logp.mul_(1.0 / (0.5 * logp.numel() * dV)).clamp_(min=1e-300).log_()
+
+    out = torch.empty((n_fft, rows, nx), dtype=torch.float64, device=dev)
+    gathered = None
+    pm = None
+    if world > 1:
+        pm = torch.empty((npix, n_fft), dtype=torch.float64, device=dev)
+        if rank == 0:
+            gathered = torch.empty((total_pix, n_fft), dtype=torch.float64, device=dev)
+            full = torch.empty((n_fft, total_pix), dtype=torch.float64, device=dev)
+        counts = [None] * world
+        dist.all_gather_object(counts, npix)
+
+    def step():
+        if world == 1:
+            plan.ybar_density(logp, is_log=True, out=out)
+            return
+        # rank-local rows -> pixel-major tile -> gather on rank 0 -> one transpose to [n_fft, x1, x2]
+        plan.ybar_density(logp, is_log=True, out=pm, layout=_lib.LAYOUT_PIXEL_MAJOR)
+        if rank == 0:
+            offs = np.concatenate(([0], np.cumsum(counts)))
+            parts = [gathered[offs[i]:offs[i + 1]] for i in range(world)]
+            dist.gather(pm, parts, dst=0)
+            _lib.check(_lib.load().pkm_transpose_to_cube(_lib.ptr(gathered), total_pix, n_fft,
+                                                         _lib.ptr(full), local, None))
+        else:
+            dist.gather(pm, None, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", "")
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    fp64_peak = engine.fp64_fma_peak(local)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    plan.set_profiling(True)
+    l0 = plan.launches
+    w0 = sampler.mark() if sampler else 0
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    w1 = sampler.mark() if sampler else 0
+    ms_total = e0.elapsed_time(e1)
+    ktimes = plan.kernel_times()
+    plan.set_profiling(False)
+    launches = plan.launches - l0 + (args.steps if world > 1 and rank == 0 else 0)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = voxels_per_step / (ms_step * 1e-3)
+
+    # ---- e2e: same call through the C ABI with pinned host buffers
+    e2e = None
+    windows = [(w0, w1)]
+    if not args.no_e2e:
+        h_in = torch.empty(logp.shape, dtype=torch.float64, pin_memory=True)
+        h_in.copy_(logp)
+        h_out = torch.empty((n_fft, rows, nx), dtype=torch.float64, pin_memory=True)
+        np_in, np_out = h_in.numpy(), h_out.numpy()
+        if world > 1:
+            del pm
+        del logp
+        torch.cuda.empty_cache()
+
+        def step_e2e():
+            plan.ybar_density(np_in, is_log=True, out=np_out)
+
+        step_e2e()
+        barrier()
+        w2 = sampler.mark() if sampler else 0
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        w3 = sampler.mark() if sampler else 0
+        windows.append((w2, w3))
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": voxels_per_step * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "note": "per rank: pinned host log_p_tvxz -> pkm_ybar_density -> pinned host cube; "
+                       "multi-GPU ranks leave their row blocks on their own host buffers"}
+
+    clocks = sampler.stop(windows) if sampler else None
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (live CUDA-event times of this run)
+        nfo, ntz, nfi = n_fft // 2 + 1, nt * nz, nv // 2 + 1
+        flops_px = {"contract": 24.0 * nfo * ntz, "coeff": 2.0 * nfi * nv * ntz}
+        tot_k = sum(m for m, _ in ktimes.values()) or 1.0
+        kern = {k: {"ms_per_step": m / args.steps, "launches_per_step": c / args.steps, "share": m / tot_k}
+                for k, (m, c) in ktimes.items() if c}
+        dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+        roof = None
+        if dom in flops_px:
+            ach = flops_px[dom] * npix / (kern[dom]["ms_per_step"] * 1e-3) / 1e12
+            roof = {"bound": "fp64", "kernel": "k_" + dom, "achieved": ach, "peak": fp64_peak,
+                    "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": ncu_traffic(dom, npix),
+                    "peak_source": "pkm_fp64_fma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                    "flops_per_pixel": flops_px[dom],
+                    "note": "P-hat is never materialised (SURVEY.md 8f rank 1): the contraction is "
+                            "FP64-pipe bound, not HBM bound; see roofline_hbm for the canonical byte figure"}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        b_vox = (8.0 * nt * nv * nz + 2 * 16.0 * nfo * ntz + 8.0 * n_fft) / n_fft
+        b_min = (8.0 * nt * nv * nz + 8.0 * n_fft) / n_fft
+        per_gpu = value / world
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, cube),
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof,
+            "roofline_hbm": {"bound": "hbm", "achieved": b_vox * per_gpu / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": b_vox * per_gpu / 1e9 / hbm_peak,
+                             "bytes_per_voxel": b_vox, "note": B_VOX_NOTE,
+                             "compulsory": {"bytes_per_voxel": b_min, "achieved": b_min * per_gpu / 1e9,
+                                            "frac": b_min * per_gpu / 1e9 / hbm_peak},
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
+            "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, npix):
+    """DRAM bytes per launch from the committed ncu capture of the same launch geometry, or None."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tab.get(kernel)
+        if ent and ent.get("npix") == npix:
+            return ent["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

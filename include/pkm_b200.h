@@ -95,6 +95,15 @@ PKM_API int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes);
 /* Number of kernels launched by this plan since creation (for bench accounting). */
 PKM_API int64_t pkm_plan_launch_count(const pkm_plan* plan);
 
+/* Per-kernel device timing.  While enabled, every hot-path launch of this plan is bracketed by
+ * a CUDA-event pair recorded on the launch stream.  pkm_plan_kernel_times waits for the pending
+ * launches and returns, per kernel class, the summed milliseconds and the launch count since
+ * profiling was (re-)enabled.  Classes: 0 coefficient GEMM, 1 spline contraction, 2 Gaussian
+ * contraction, 3 inverse FFT, 4 transpose. */
+#define PKM_NUM_KERNEL_CLASSES 5
+PKM_API int32_t pkm_plan_set_profiling(pkm_plan* plan, int32_t enable);
+PKM_API int32_t pkm_plan_kernel_times(pkm_plan* plan, double* ms_out, int64_t* count_out);
+
 /* Density path.  dens: [nt][nv][nx1][nx2][nz] float64, host or device; is_log != 0 means
  * it holds log p (exp is fused into the first kernel; -inf -> 0).  Rows [row_begin,row_end)
  * of the x1 axis are evaluated (spatial sharding); ybar_out (host or device) receives

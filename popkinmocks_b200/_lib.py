@@ -50,6 +50,8 @@ SIGNATURES = {
     "pkm_plan_destroy": (_I32, [_P]),
     "pkm_plan_set_workspace_limit": (_I32, [_P, _I64]),
     "pkm_plan_launch_count": (_I64, [_P]),
+    "pkm_plan_set_profiling": (_I32, [_P, _I32]),
+    "pkm_plan_kernel_times": (_I32, [_P, _P, _P]),
     "pkm_ybar_density": (_I32, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "pkm_ybar_gaussian": (_I32, [_P, _P, _P, C.POINTER(_I64), _P, C.POINTER(_I64), _P, _I32, _I32,
                                  _I32, _I32, _P, _I32, _P]),

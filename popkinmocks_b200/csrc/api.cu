@@ -113,6 +113,8 @@ extern "C" int32_t pkm_fold_tables(int32_t nv, int32_t v0_idx, double dv, double
 // ----------------------------------------------------------------------------
 // plan
 // ----------------------------------------------------------------------------
+static void collect_timers(pkm_plan* pl);
+
 static void plan_free(pkm_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->d.device);
@@ -124,6 +126,7 @@ static void plan_free(pkm_plan* pl) {
   fr(pl->d_slot_k); fr(pl->d_slot_w); fr(pl->d_group_span); fr(pl->d_SA); fr(pl->d_omega);
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz);
+  collect_timers(pl);
   pl->coef.release(); pl->yhat.release(); pl->ypx.release(); pl->misc.release(); pl->small.release();
   for (int i = 0; i < 2; ++i) {
     pl->stage_in[i].release();
@@ -255,6 +258,44 @@ extern "C" int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes) {
 
 extern "C" int64_t pkm_plan_launch_count(const pkm_plan* plan) { return plan ? plan->launches : 0; }
 
+static void collect_timers(pkm_plan* pl) {
+  for (TimedLaunch& t : pl->timed) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+      pl->k_ms[t.cls] += ms;
+      pl->k_count[t.cls] += 1;
+    }
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  pl->timed.clear();
+}
+
+extern "C" int32_t pkm_plan_set_profiling(pkm_plan* plan, int32_t enable) {
+  return guarded([&] {
+    PKM_REQUIRE(plan, "null plan");
+    use_device(plan->d.device);
+    collect_timers(plan);
+    plan->profiling = enable != 0;
+    for (int i = 0; i < PKM_K_NCLASS; ++i) {
+      plan->k_ms[i] = 0.0;
+      plan->k_count[i] = 0;
+    }
+  });
+}
+
+extern "C" int32_t pkm_plan_kernel_times(pkm_plan* plan, double* ms_out, int64_t* count_out) {
+  return guarded([&] {
+    PKM_REQUIRE(plan && ms_out && count_out, "null argument");
+    use_device(plan->d.device);
+    collect_timers(plan);
+    for (int i = 0; i < PKM_K_NCLASS; ++i) {
+      ms_out[i] = plan->k_ms[i];
+      count_out[i] = plan->k_count[i];
+    }
+  });
+}
+
 // ----------------------------------------------------------------------------
 // shared tail of the two ybar paths: Yhat tile -> irfft -> output layout
 // ----------------------------------------------------------------------------
@@ -287,13 +328,19 @@ void emit_tile(pkm_plan* pl, const OutSpec& o, const double* ypx, int64_t pix_of
     return;
   }
   if (!o.host) {
-    launch_transpose(ypx, np, n, o.out, o.npix_out, pix_off, st);
+    {
+      KernelTimer tm(pl, PKM_K_TRANSPOSE, st);
+      launch_transpose(ypx, np, n, o.out, o.npix_out, pix_off, st);
+    }
     pl->launches++;
     return;
   }
   pl->stage_out[slot].reserve(sizeof(double) * n * np);
   double* tmp = pl->stage_out[slot].as<double>();
-  launch_transpose(ypx, np, n, tmp, np, 0, st);
+  {
+    KernelTimer tm(pl, PKM_K_TRANSPOSE, st);
+    launch_transpose(ypx, np, n, tmp, np, 0, st);
+  }
   pl->launches++;
   PKM_CUDA(cudaMemcpy2DAsync(o.out + pix_off, sizeof(double) * o.npix_out, tmp, sizeof(double) * np,
                              sizeof(double) * np, n, cudaMemcpyDeviceToHost, st));

@@ -195,6 +195,7 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   PKM_CUDA(cudaFuncSetAttribute(k_coeff<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t ntile = (int64_t)((npix_tile + pxb - 1) / pxb) * pl->d.nt;
   int grid = (int)std::min<int64_t>(ntile, pl->num_sms);
+  KernelTimer tm(pl, PKM_K_COEFF, st);
   k_coeff<TM><<<grid, K1_THREADS, smem, st>>>(dens, is_log, npix_total, pix0, npix_tile, xpad,
                                               pl->d.nv, pl->d.nz, pl->nfi, pl->fold.ne, pl->fold.no,
                                               pxb, pl->d.nt, pl->d_CRt, pl->d_CIt, pl->d_idx_plus,
@@ -280,6 +281,7 @@ k_contract(const double2* __restrict__ Sp, const double2* __restrict__ cT,
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
                      cudaStream_t st) {
   dim3 grid((pl->slots.nunit + 7) / 8, (npix_tile + 7) / 8);
+  KernelTimer tm(pl, PKM_K_CONTRACT, st);
   k_contract<<<grid, 256, 0, st>>>(pl->d_Sp, cT, pl->d_group_span, pl->d_slot_w, pl->d_slot_k, yhat,
                                    pl->ntz, pl->nfi, xpad, pl->slots.nslot, pl->slots.nunit, pl->nfo);
   PKM_CUDA(cudaGetLastError());

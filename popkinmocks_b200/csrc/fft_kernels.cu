@@ -227,6 +227,7 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
     pl->misc.reserve(sizeof(double2) * (size_t)c.M * grid);
     scratch = pl->misc.as<double2>();
   }
+  KernelTimer tm(pl, PKM_K_IRFFT, st);
   k_irfft_czt<<<grid, 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_chi, pl->d_alpha,
                                        pl->d_twiddle, pl->d_Bhat, out, scratch);
   PKM_CUDA(cudaGetLastError());

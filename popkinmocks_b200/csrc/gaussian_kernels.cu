@@ -77,7 +77,8 @@ void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const 
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
                      int64_t pix0, int npix_tile, int xpad, double2* yhat, cudaStream_t st) {
   const int nunit = pl->kpadA / (PKM_GPW * PKM_KT);
-  dim3 grid((nunit + 7) / 8, xpad / 8);
+  dim3 grid((nunit + 7) / 8, (npix_tile + 7) / 8);
+  KernelTimer tm(pl, PKM_K_GAUSSIAN, st);
   k_gaussian<<<grid, 256, 0, st>>>(pl->d_SA, pl->d_omega, P_txz, mu, mu_st[0], mu_st[1], mu_st[2], sig,
                                    sig_st[0], sig_st[1], sig_st[2], nx2, npix_total, pix0, npix_tile,
                                    pl->d.nt, pl->d.nz, pl->kpadA, nunit, pl->nfo, xpad, yhat);

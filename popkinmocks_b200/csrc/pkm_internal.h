@@ -96,11 +96,22 @@ void build_czt_tables(int n, CztTables& out);
 // ----------------------------------------------------------------------------
 // the plan
 // ----------------------------------------------------------------------------
+enum { PKM_K_COEFF = 0, PKM_K_CONTRACT = 1, PKM_K_GAUSSIAN = 2, PKM_K_IRFFT = 3, PKM_K_TRANSPOSE = 4,
+       PKM_K_NCLASS = 5 };
+struct TimedLaunch {
+  int cls;
+  cudaEvent_t e0, e1;
+};
+
 struct pkm_plan {
   pkm_cube_desc d;
   int nfo = 0, nfi = 0, ntz = 0;
   bool density_ok = false;  // v0_idx >= 0 and nfi >= 4
   int64_t launches = 0;
+  bool profiling = false;              // CUDA-event pair around every hot-path launch
+  std::vector<TimedLaunch> timed;      // pending (not yet collected) launches
+  double k_ms[PKM_K_NCLASS] = {0, 0, 0, 0, 0};
+  int64_t k_count[PKM_K_NCLASS] = {0, 0, 0, 0, 0};
   int num_sms = 148;
   size_t ws_limit = size_t(4) << 30;
 
@@ -181,4 +192,24 @@ void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t 
                   cudaStream_t st);
 
 bool pkm_is_device_pointer(const void* p);
+
+// RAII CUDA-event bracket of one launch on its own stream (no-op unless plan->profiling)
+struct KernelTimer {
+  pkm_plan* pl;
+  cudaStream_t st;
+  TimedLaunch t;
+  bool on;
+  KernelTimer(pkm_plan* pl_, int cls, cudaStream_t st_) : pl(pl_), st(st_), on(pl_->profiling) {
+    if (!on) return;
+    t.cls = cls;
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    cudaEventRecord(t.e0, st);
+  }
+  ~KernelTimer() {
+    if (!on) return;
+    cudaEventRecord(t.e1, st);
+    pl->timed.push_back(t);
+  }
+};
 double run_fma_probe(int num_sms, int repeats);  // TFLOP/s

@@ -73,6 +73,19 @@ class Plan:
     def launches(self):
         return int(_lib.load().pkm_plan_launch_count(self._h))
 
+    KERNEL_CLASSES = ("coeff", "contract", "gaussian", "irfft", "transpose")
+
+    def set_profiling(self, enable):
+        """Bracket every hot-path launch with CUDA events (resets the accumulated times)."""
+        _lib.check(_lib.load().pkm_plan_set_profiling(self._h, int(bool(enable))))
+
+    def kernel_times(self):
+        """{class: (total ms, launches)} since profiling was enabled (waits for the launches)."""
+        ms = np.zeros(len(self.KERNEL_CLASSES))
+        cnt = np.zeros(len(self.KERNEL_CLASSES), dtype=np.int64)
+        _lib.check(_lib.load().pkm_plan_kernel_times(self._h, _lib.ptr(ms), _lib.ptr(cnt)))
+        return {k: (float(m), int(c)) for k, m, c in zip(self.KERNEL_CLASSES, ms, cnt)}
+
     def set_workspace_limit(self, nbytes):
         _lib.check(_lib.load().pkm_plan_set_workspace_limit(self._h, int(nbytes)))
 
