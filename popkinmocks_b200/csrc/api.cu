@@ -122,8 +122,8 @@ static void plan_free(pkm_plan* pl) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_idx_plus); fr(pl->d_idx_minus); fr(pl->d_Sp);
-  fr(pl->d_slot_k); fr(pl->d_slot_w); fr(pl->d_group_span); fr(pl->d_SA); fr(pl->d_omega);
+  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_idx_plus); fr(pl->d_idx_minus); fr(pl->d_Sw);
+  fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_omega);
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz);
   collect_timers(pl);
@@ -167,31 +167,33 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
       SplineTables sp;
       build_spline_tables(pl->nfi, nfo, sp);
       build_fold_tables(desc->nv, desc->v0_idx, desc->dv, sp, pl->fold);
-      build_slot_tables(sp, pl->slots);
+      build_wseg_tables(sp, pl->wsegs);
       density_tables_upload(pl);
-      const int nslot = pl->slots.nslot;
-      std::vector<double> Sp(size_t(2) * pl->ntz * nslot, 0.0);
-      for (int t = 0; t < nt; ++t)
-        for (int z = 0; z < nz; ++z) {
-          const double w = delta_z[z] * delta_t[t];
-          double* row = Sp.data() + size_t(2) * (size_t(t) * nz + z) * nslot;
-          for (int pos = 0; pos < nslot; ++pos) {
-            int k = pl->slots.slot_k[pos];
-            if (k < 0) continue;
-            const double* s = FXw + size_t(2) * ((size_t(k) * nz + z) * nt + t);
-            // same rounding order as the reference: F_s * F_p then * (dt*dz); here (S * (dz*dt))
-            row[2 * pos] = s[0] * w;
-            row[2 * pos + 1] = s[1] * w;
+      // S-hat' per warp segment: [nwseg][nchunk*TZC][KT], rows beyond ntz and slots beyond the
+      // segment's count are zero, so every staged chunk is one full-size contiguous bulk copy
+      pl->nchunk = (pl->ntz + PKM_TZC - 1) / PKM_TZC;
+      const size_t rows = size_t(pl->nchunk) * PKM_TZC;
+      std::vector<double> Sw(size_t(2) * pl->wsegs.nwseg * rows * PKM_KT, 0.0);
+      for (int ws = 0; ws < pl->wsegs.nwseg; ++ws) {
+        const int k0 = pl->wsegs.seg[4 * ws + 1], cnt = pl->wsegs.seg[4 * ws + 2];
+        for (int t = 0; t < nt; ++t)
+          for (int z = 0; z < nz; ++z) {
+            const double w = delta_z[z] * delta_t[t];
+            double* row = Sw.data() + size_t(2) * ((size_t(ws) * rows + size_t(t) * nz + z) * PKM_KT);
+            for (int r = 0; r < cnt; ++r) {
+              const double* sv = FXw + size_t(2) * ((size_t(k0 + r) * nz + z) * nt + t);
+              row[2 * r] = sv[0] * w;
+              row[2 * r + 1] = sv[1] * w;
+            }
           }
-        }
-      pl->d_Sp = reinterpret_cast<double2*>(upload(Sp));
-      pl->d_slot_k = upload(pl->slots.slot_k);
-      pl->d_slot_w = upload(pl->slots.slot_w);
-      pl->d_group_span = upload(pl->slots.group_span);
+      }
+      pl->d_Sw = reinterpret_cast<double2*>(upload(Sw));
+      pl->d_wseg = upload(pl->wsegs.seg);
+      pl->d_wseg_w = upload(pl->wsegs.w);
     }
 
     // ---- gaussian path: FXw as [t][z][kpad]
-    const int kq = PKM_GPW * PKM_KT;
+    const int kq = 16;
     pl->kpadA = ((nfo + kq - 1) / kq) * kq;
     {
       std::vector<double> SA(size_t(2) * nt * nz * pl->kpadA, 0.0);

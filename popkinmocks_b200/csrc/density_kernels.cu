@@ -11,105 +11,197 @@
 //                      spline on the fly and accumulates over (t,z) in registers.
 // P-hat (25 MB per pixel in the reference, base.py:846-853) is never materialised.
 #include <cstdio>
+#include <cstdlib>
 
 #include "pkm_internal.h"
+
+// ============================================================================
+// async-copy helpers (1-D TMA bulk copies completing on an mbarrier)
+// ============================================================================
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 
 // ============================================================================
 // kernel 1
 // ============================================================================
 // Persistent CTAs (one per SM), each looping over tiles = (age t, block of PXB pixels), i.e.
 // NC = PXB*nz density columns of nv velocities.  The folded DFT*spline matrices stay resident
-// in shared memory for the CTA's lifetime.  Per tile:
-//   phase 1: load the [nv][NC] slab (coalesced: for fixed v the columns are contiguous), exp fused
-//   phase 2: fold v <-> -v in place (e = sum, o = difference of the rolled profile)
-//   phase 3: warp-tiled FP64 GEMM; lanes = 8 row groups x 4 column groups, thread tile TM x 4;
+// in shared memory for the CTA's lifetime.  The density slab is double buffered: while tile i is
+// being transformed, the [nv][NC] slab of tile i+1 streams into the other buffer as nv 1-D TMA
+// bulk copies (for fixed v the NC columns are contiguous in global memory) that complete on an
+// mbarrier.  Per tile:
+//   phase 1: fold v <-> -v in place (e = sum, o = difference of the rolled profile), exp(log p)
+//            fused here when the caller passes log densities
+//   phase 2: warp-tiled FP64 GEMM; lanes = 8 row groups x 4 column groups, thread tile TM x 4;
 //            one work item = (16-column chunk, real | imaginary part) per warp
-//   phase 4: results staged as [z][m][x] in shared memory, written as 16*PXB-byte runs so the
-//            contraction kernel reads pixel-contiguous coefficient rows.
+//   phase 3: results staged as [z][m][x] in the (now consumed) slab buffer
+//   phase 4: written as 16*PXB-byte runs so the contraction kernel reads pixel-contiguous rows.
+// The kernel sits at the FP64 / HBM balance point: 10.3 kFLOP and 1.6 KB of traffic per column.
 constexpr int K1_THREADS = 384;
 constexpr int K1_WARPS = K1_THREADS / 32;
 
+struct K1Geom {
+  long long npix_total, pix0;
+  int npix_tile, xpad, nv, nz, nfi, ne, no, pxb, nt, is_log, use_tma, v0;
+};
+
+// velocity row holding rolled position +u / -u  (np.roll(p, nv - v0), base.py:843)
+__device__ __forceinline__ int row_plus(int u, int v0, int nv) {
+  int r = u + v0;
+  return r >= nv ? r - nv : r;
+}
+__device__ __forceinline__ int row_minus(int u, int v0, int nv) {
+  int r = v0 - u;
+  return r < 0 ? r + nv : r;
+}
+
 template <int TM>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-k_coeff(const double* __restrict__ dens, int is_log, long long npix_total, long long pix0,
-        int npix_tile, int xpad, int nv, int nz, int nfi, int ne, int no, int pxb, int nt,
-        const double* __restrict__ CRt, const double* __restrict__ CIt,
-        const int* __restrict__ idx_plus, const int* __restrict__ idx_minus,
-        double2* __restrict__ cT) {
-  extern __shared__ double smem[];
+k_coeff(const double* __restrict__ dens, K1Geom g, const double* __restrict__ CRt,
+        const double* __restrict__ CIt, double2* __restrict__ cT) {
+  extern __shared__ __align__(128) double smem[];
   constexpr int TMP = TM + (TM & 1);  // even row padding -> 16-byte aligned double2 loads
   constexpr int NFIP = 8 * TMP;
+  const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, pxb = g.pxb;
   const int NC = pxb * nz;
   const int NCp = (NC + 15) & ~15;
+  // one slab buffer holds the [nv][NCp] density slab and later the [nz][nfi][pxb] complex staging
+  const int buf_elems = max(nv * NCp, 2 * nz * nfi * pxb);
   double* As_r = smem;                                   // [ne][NFIP]
   double* As_i = As_r + (size_t)ne * NFIP;               // [max(no,1)][NFIP]
-  double* Bs = As_i + (size_t)max(no, 1) * NFIP;         // [nv][NCp]
-  double* Cs = Bs + (size_t)nv * NCp;                    // [nz][nfi][pxb][2]
-  int* rows_e = reinterpret_cast<int*>(Cs + (size_t)nz * nfi * pxb * 2);  // [ne]
-  int* rows_o = rows_e + ne;                             // [ne] (entry u-1 used for u>=1)
+  double* Bbuf = As_i + (size_t)max(no, 1) * NFIP;       // [2][buf_elems]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Bbuf + 2 * (size_t)buf_elems);
+  const int v0 = g.v0;
+  const int xmask = pxb - 1;                             // staging swizzle (pxb is a power of two)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int rg = lane & 7, cg = lane >> 3;
 
   for (int i = tid; i < ne * NFIP; i += K1_THREADS) As_r[i] = CRt[i];
   for (int i = tid; i < no * NFIP; i += K1_THREADS) As_i[i] = CIt[i];
-  for (int i = tid; i < ne; i += K1_THREADS) {
-    rows_e[i] = idx_plus[i];
-    rows_o[i] = idx_minus[i];
+  for (int i = tid; i < 2 * buf_elems; i += K1_THREADS) Bbuf[i] = 0.0;
+  const unsigned bar0 = smem_u32(bars);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // generic-proxy writes above (zero fill) must be ordered before async-proxy writes (TMA)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  const int nxb = (npix_tile + pxb - 1) / pxb;
-  const long long ntile = (long long)nxb * nt;
+  const int nxb = (g.npix_tile + pxb - 1) / pxb;
+  const long long ntile = (long long)nxb * g.nt;
   const int nchunk = NCp >> 4;
   const int nitem = nchunk * 2;
+  const size_t vstride = (size_t)g.npix_total * nz;      // elements between velocity rows
 
-  for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+  // load of one tile's slab into buffer `b`; returns true if it was issued as TMA (uniform)
+  auto load_tile = [&](long long tile, int b) -> bool {
     const int t = (int)(tile / nxb);
     const int xb = (int)(tile - (long long)t * nxb);
-    // phase 1
-    const long long col_base = (pix0 + (long long)xb * pxb) * nz;
-    const int ncol_valid = min(pxb, npix_tile - xb * pxb) * nz;
-    for (int i = tid; i < nv * NCp; i += K1_THREADS) {
-      int v = i / NCp, col = i - v * NCp;
-      double val = 0.0;
-      if (col < ncol_valid) {
-        val = __ldg(dens + ((long long)t * nv + v) * npix_total * nz + col_base + col);
-        if (is_log) val = exp(val);
+    const int ncol_valid = min(pxb, g.npix_tile - xb * pxb) * nz;
+    const double* src = dens + (size_t)t * nv * vstride + (size_t)(g.pix0 + (long long)xb * pxb) * nz;
+    double* dst = Bbuf + (size_t)b * buf_elems;
+    const bool tma = g.use_tma && ((ncol_valid & 1) == 0);
+    if (tma) {
+      if (warp == 0) {
+        const unsigned bar = bar0 + 8u * b;
+        const unsigned row_bytes = (unsigned)ncol_valid * 8u;
+        if (lane == 0) mbar_expect_tx(bar, row_bytes * (unsigned)nv);
+        __syncwarp();
+        for (int v = lane; v < nv; v += 32)
+          bulk_g2s(smem_u32(dst + (size_t)v * NCp), src + (size_t)v * vstride, row_bytes, bar);
       }
-      Bs[(size_t)v * NCp + col] = val;
+    } else {
+      for (int i = tid; i < nv * NCp; i += K1_THREADS) {
+        const int v = i / NCp, col = i - v * NCp;
+        dst[i] = col < ncol_valid ? __ldg(src + (size_t)v * vstride + col) : 0.0;
+      }
+    }
+    return tma;
+  };
+
+  unsigned phases = 0u;      // bit b = parity the next TMA completion on buffer b will have
+  bool cur_tma = false, next_tma = false;
+  long long tile = blockIdx.x;
+  if (tile < ntile) cur_tma = load_tile(tile, 0);
+  for (int it = 0; tile < ntile; tile += gridDim.x, ++it, cur_tma = next_tma) {
+    const int b = it & 1;
+    // the other buffer was released by the barrier that ended the previous iteration
+    if (tile + gridDim.x < ntile) next_tma = load_tile(tile + gridDim.x, b ^ 1);
+    if (cur_tma) {
+      mbar_wait(bar0 + 8u * b, (phases >> b) & 1u);
+      phases ^= 1u << b;
+    } else {
+      __syncthreads();
+    }
+    const int t = (int)(tile / nxb);
+    const int xb = (int)(tile - (long long)t * nxb);
+    double* Bs = Bbuf + (size_t)b * buf_elems;
+    // phase 1 (self-paired rows carry weight 1/2 in CRt, so e = a + b unconditionally)
+    for (int i = tid; i < ne * (NCp >> 1); i += K1_THREADS) {
+      const int u = i / (NCp >> 1), c2 = i - u * (NCp >> 1);
+      const int rp = row_plus(u, v0, nv), rm = row_minus(u, v0, nv);
+      double2* pa = reinterpret_cast<double2*>(Bs + (size_t)rp * NCp) + c2;
+      double2* pb = reinterpret_cast<double2*>(Bs + (size_t)rm * NCp) + c2;
+      double2 a = *pa, bb = *pb;
+      if (g.is_log) {
+        a.x = exp(a.x); a.y = exp(a.y);
+        bb.x = exp(bb.x); bb.y = exp(bb.y);
+      }
+      *pa = make_double2(a.x + bb.x, a.y + bb.y);
+      if (rp != rm) *pb = make_double2(a.x - bb.x, a.y - bb.y);
     }
     __syncthreads();
-    // phase 2 (self-paired rows carry weight 1/2 in CRt, so e = a + b unconditionally)
-    for (int i = tid; i < ne * NCp; i += K1_THREADS) {
-      int u = i / NCp, col = i - u * NCp;
-      int rp = rows_e[u], rm = rows_o[u];
-      double a = Bs[(size_t)rp * NCp + col], b = Bs[(size_t)rm * NCp + col];
-      Bs[(size_t)rp * NCp + col] = a + b;
-      if (rp != rm) Bs[(size_t)rm * NCp + col] = a - b;
-    }
-    __syncthreads();
-    // phase 3 + staging
-    for (int item = warp; item < nitem; item += K1_WARPS) {
-      const int part = item & 1, chunk = item >> 1;
-      const double* A = part ? As_i : As_r;
-      const int* rows = part ? (rows_o + 1) : rows_e;
+    // phase 2
+    // (the host picks PXB so that there is at most one item per warp: accumulators stay in
+    // registers across the barrier that frees the slab for staging)
+    double acc[TM][4];
+    const int item = warp;
+    const int part = item & 1, chunk = item >> 1;
+    if (item < nitem) {
+      const double* A = (part ? As_i : As_r) + rg * 2;
       const int K = part ? no : ne;
       const int col0 = chunk * 16 + cg * 4;
-      double acc[TM][4];
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 #pragma unroll 2
       for (int u = 0; u < K; ++u) {
-        const double2* bp = reinterpret_cast<const double2*>(Bs + (size_t)rows[u] * NCp + col0);
+        // E[u] lives in row +u, O[u] (u >= 1) in row -u of the folded slab
+        const int row = part ? row_minus(u + 1, v0, nv) : row_plus(u, v0, nv);
+        const double2* bp = reinterpret_cast<const double2*>(Bs + (size_t)row * NCp + col0);
         const double2 b01 = bp[0], b23 = bp[1];
-        const double2* ap = reinterpret_cast<const double2*>(A + (size_t)u * NFIP + rg * TMP);
+        const double2* ap = reinterpret_cast<const double2*>(A + (size_t)u * NFIP);
         double a[TMP];
 #pragma unroll
         for (int i = 0; i < TMP / 2; ++i) {
-          double2 v2 = ap[i];
+          double2 v2 = ap[i * 8];  // rows (2i, 2i+1) of the 8 row groups are 128 contiguous bytes
           a[2 * i] = v2.x;
           a[2 * i + 1] = v2.y;
         }
@@ -121,15 +213,21 @@ k_coeff(const double* __restrict__ dens, int is_log, long long npix_total, long 
           acc[i][3] = fma(a[i], b23.y, acc[i][3]);
         }
       }
+    }
+    __syncthreads();  // every warp is done reading the slab: reuse it as the staging area
+    // phase 3: Cs[z][m][x] complex
+    double* Cs = Bs;
+    if (item < nitem) {
+      const int col0 = chunk * 16 + cg * 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        int col = col0 + j;
+        const int col = col0 + j;
         if (col < NC) {
-          int x = col / nz, z = col - x * nz;
+          const int x = col / nz, z = col - x * nz;
 #pragma unroll
           for (int i = 0; i < TM; ++i) {
-            int m = rg * TM + i;
-            if (m < nfi) Cs[(((size_t)z * nfi + m) * pxb + x) * 2 + part] = acc[i][j];
+            const int m = rg * TM + i;
+            if (m < nfi) Cs[(((size_t)z * nfi + m) * pxb + (x ^ ((m + (z >> 2)) & xmask))) * 2 + part] = acc[i][j];
           }
         }
       }
@@ -137,15 +235,20 @@ k_coeff(const double* __restrict__ dens, int is_log, long long npix_total, long 
     __syncthreads();
     // phase 4: cT[((t*nz + z)*nfi + m)*xpad + xb*pxb + x]
     for (int i = tid; i < nz * nfi * pxb; i += K1_THREADS) {
-      int zm = i / pxb, x = i - zm * pxb;
-      double2 v = reinterpret_cast<const double2*>(Cs)[i];
-      cT[((size_t)t * nz * nfi + zm) * xpad + (size_t)xb * pxb + x] = v;
+      const int zm = i / pxb, xs = i - zm * pxb;
+      const int z = zm / nfi, m = zm - z * nfi;
+      const int x = xs ^ ((m + (z >> 2)) & xmask);
+      const double2 v = reinterpret_cast<const double2*>(Cs)[i];
+      cT[((size_t)t * nz * nfi + zm) * g.xpad + (size_t)xb * pxb + x] = v;
     }
-    // the next tile's phase 1/2 only touch Bs; Cs is rewritten after two more barriers
+    // order this tile's generic-proxy accesses to the buffer before the TMA refill of it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
   }
 }
 
-// The GEMM phase reads A rows as As[u][rg*TMP + i]; the host stores row m = rg*TM + i there.
+// The GEMM phase reads rows (2*ip, 2*ip+1) of row group rg as the double2 at
+// As[u][ip*16 + rg*2]; the host stores row m = rg*TM + 2*ip + e at As[u][ip*16 + rg*2 + e].
 static void upload_padded_transposed(const std::vector<double>& C, int nfi, int K, int TM,
                                      double** d_out) {
   const int TMP = TM + (TM & 1), NFIP = 8 * TMP;
@@ -153,7 +256,7 @@ static void upload_padded_transposed(const std::vector<double>& C, int nfi, int 
   for (int u = 0; u < K; ++u)
     for (int m = 0; m < nfi; ++m) {
       int rg = m / TM, i = m % TM;
-      h[(size_t)u * NFIP + rg * TMP + i] = C[(size_t)m * K + u];
+      h[(size_t)u * NFIP + (i / 2) * 16 + rg * 2 + (i & 1)] = C[(size_t)m * K + u];
     }
   PKM_CUDA(cudaMalloc(d_out, h.size() * sizeof(double)));
   PKM_CUDA(cudaMemcpy(*d_out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -167,23 +270,23 @@ void density_tables_upload(pkm_plan* pl) {
   pl->nfiP = 8 * TMP;
   upload_padded_transposed(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, &pl->d_CRt);
   upload_padded_transposed(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, &pl->d_CIt);
-  PKM_CUDA(cudaMalloc(&pl->d_idx_plus, pl->fold.ne * sizeof(int32_t)));
-  PKM_CUDA(cudaMalloc(&pl->d_idx_minus, pl->fold.ne * sizeof(int32_t)));
-  PKM_CUDA(cudaMemcpy(pl->d_idx_plus, pl->fold.idx_plus.data(), pl->fold.ne * sizeof(int32_t), cudaMemcpyHostToDevice));
-  PKM_CUDA(cudaMemcpy(pl->d_idx_minus, pl->fold.idx_minus.data(), pl->fold.ne * sizeof(int32_t), cudaMemcpyHostToDevice));
 }
 
 static size_t coeff_smem_bytes(const pkm_plan* pl, int pxb) {
   const int NC = pxb * pl->d.nz, NCp = (NC + 15) & ~15;
-  size_t dbl = (size_t)(pl->fold.ne + std::max(pl->fold.no, 1)) * pl->nfiP + (size_t)pl->d.nv * NCp +
-               (size_t)pl->d.nz * pl->nfi * pxb * 2;
-  return dbl * sizeof(double) + 2 * (size_t)pl->fold.ne * sizeof(int);
+  const size_t buf_elems = std::max<size_t>((size_t)pl->d.nv * NCp, (size_t)2 * pl->d.nz * pl->nfi * pxb);
+  size_t dbl = (size_t)(pl->fold.ne + std::max(pl->fold.no, 1)) * pl->nfiP + 2 * buf_elems;
+  return dbl * sizeof(double) + 2 * sizeof(unsigned long long);
 }
 
-// pixels per tile: largest of {16, 8, 4, 2, 1} whose slab + staging fits shared memory
+// pixels per tile: largest of {16, 8, 4, 2} whose two slab buffers fit shared memory and whose
+// GEMM items (2 per 16 columns) do not exceed one per warp
 int coeff_choose_pxb(const pkm_plan* pl) {
-  for (int pxb : {16, 8, 4, 2, 1})
+  for (int pxb : {16, 8, 4, 2}) {
+    const int NCp = (pxb * pl->d.nz + 15) & ~15;
+    if ((NCp >> 4) * 2 > K1_WARPS) continue;
     if (coeff_smem_bytes(pl, pxb) <= 227 * 1024) return pxb;
+  }
   PKM_THROW(PKM_ERR_INVALID, "coefficient kernel: nv=%d nz=%d does not fit shared memory", pl->d.nv, pl->d.nz);
 }
 
@@ -195,11 +298,17 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   PKM_CUDA(cudaFuncSetAttribute(k_coeff<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t ntile = (int64_t)((npix_tile + pxb - 1) / pxb) * pl->d.nt;
   int grid = (int)std::min<int64_t>(ntile, pl->num_sms);
+  K1Geom g;
+  g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile; g.xpad = xpad;
+  g.nv = pl->d.nv; g.nz = pl->d.nz; g.nfi = pl->nfi; g.ne = pl->fold.ne; g.no = pl->fold.no;
+  g.pxb = pxb; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
+  // 1-D bulk copies need 16-byte aligned row starts and sizes
+  const int nz = pl->d.nz;
+  g.use_tma = (reinterpret_cast<uintptr_t>(dens) % 16 == 0) && ((npix_total * nz) % 2 == 0) &&
+              ((pix0 * nz) % 2 == 0) && ((pxb * nz) % 2 == 0);
+  if (getenv("PKM_COEFF_NO_TMA")) g.use_tma = 0;
   KernelTimer tm(pl, PKM_K_COEFF, st);
-  k_coeff<TM><<<grid, K1_THREADS, smem, st>>>(dens, is_log, npix_total, pix0, npix_tile, xpad,
-                                              pl->d.nv, pl->d.nz, pl->nfi, pl->fold.ne, pl->fold.no,
-                                              pxb, pl->d.nt, pl->d_CRt, pl->d_CIt, pl->d_idx_plus,
-                                              pl->d_idx_minus, cT);
+  k_coeff<TM><<<grid, K1_THREADS, smem, st>>>(dens, g, pl->d_CRt, pl->d_CIt, cT);
   PKM_CUDA(cudaGetLastError());
   pl->launches++;
 }
@@ -219,71 +328,130 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 // ============================================================================
 // kernel 2
 // ============================================================================
-// warp = 4 groups x 8 pixels; thread = KT consecutive frequencies (one spline span) of one pixel.
-// Per (t,z): 4 complex S' values (64 B contiguous per instruction across the 4 groups of the
-// warp), the 4 coefficient taps of the pixel (128 B contiguous across the 8 pixel lanes), then
-// 12 flops per frequency: 8 for the real-weight spline evaluation, 4 for the complex MAC.
-__global__ void __launch_bounds__(256, 2)
-k_contract(const double2* __restrict__ Sp, const double2* __restrict__ cT,
-           const int* __restrict__ group_span, const double* __restrict__ slot_w,
-           const int* __restrict__ slot_k, double2* __restrict__ yhat, int ntz, int nfi, int xpad,
-           int nslot, int nunit, int nfo) {
+// Y-hat[k,x] = sum_{tz} S'[k,tz] * sum_{q<4} w[k][q] c[i_k+q, tz, x]     (12 FP64 FMA per (k,tz,x))
+//
+// The kernel is bound by the FP64 pipe, so everything else is arranged to stay out of its way:
+//   * work item = one warp = (warp segment, block of 32 pixels): the lanes are 32 consecutive
+//     pixels, every lane owns the SAME KT <= 10 consecutive frequencies of one spline span,
+//     so the 4 coefficient rows it needs are shared by all its frequencies (4 coalesced
+//     512-byte loads per (t,z), prefetched one (t,z) ahead in registers) and the spline tap
+//     weights live in registers for the whole (t,z) loop;
+//   * S' is warp-uniform: it is staged in shared memory by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), one 1920-byte chunk = 12 (t,z) rows x KT
+//     frequencies per copy, 3 stages per warp, and read back as broadcast LDS.128;
+//   * warps are fully independent pipelines (own stages, own mbarriers, no CTA barrier):
+//     CTA = 4 warps, 3 CTAs per SM -> 12 warps per SM, 3 per scheduler.
+constexpr int K2_WARPS = 4;
+constexpr int K2_STAGES = 3;
+constexpr int K2_CHUNK_ELEMS = PKM_TZC * PKM_KT;                      // double2 per staged chunk
+constexpr unsigned K2_CHUNK_BYTES = K2_CHUNK_ELEMS * sizeof(double2);  // 1920
+
+__global__ void __launch_bounds__(K2_WARPS * 32, 3)
+k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
+           const int4* __restrict__ wsegs, const double2* __restrict__ cT,
+           double2* __restrict__ yhat, int nwseg, int ntz, int nchunk, int nfi, int xpad, int np,
+           int nfo, long long nitems) {
+  __shared__ __align__(128) double2 sS[K2_WARPS][K2_STAGES][K2_CHUNK_ELEMS];
+  __shared__ __align__(8) unsigned long long sBar[K2_WARPS][K2_STAGES];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * 8 + warp;
-  if (unit >= nunit) return;
-  const int px = lane & 7, gsub = lane >> 3;
-  const int x = blockIdx.y * 8 + px;
-  const int g = unit * PKM_GPW + gsub;
-  const int span = group_span[g];
+  const long long item = (long long)blockIdx.x * K2_WARPS + warp;
+  if (item >= nitems) return;  // warps never synchronise with each other
+  const int pg = (int)(item / nwseg), ws = (int)(item - (long long)pg * nwseg);
+  const int4 sg = __ldg(wsegs + ws);  // {first coefficient row, k0, count, -}
+  const int x = pg * 32 + lane;
+  const int xl = min(x, np - 1);      // lanes past the tile re-read the last pixel, never store
+
   double w[PKM_KT][4];
 #pragma unroll
   for (int r = 0; r < PKM_KT; ++r)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w[r][q] = slot_w[(size_t)((unit * PKM_KT + r) * PKM_GPW + gsub) * 4 + q];
+    for (int q = 0; q < 4; ++q) w[r][q] = __ldg(Ww + ((size_t)ws * PKM_KT + r) * 4 + q);
   double2 acc[PKM_KT];
 #pragma unroll
   for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
 
-  const double2* sp = Sp + (size_t)unit * PKM_KT * PKM_GPW + gsub;
-  const double2* cp = cT + (size_t)span * xpad + x;
-  const size_t c_step = (size_t)nfi * xpad;
-#pragma unroll 2
-  for (int tz = 0; tz < ntz; ++tz) {
-    double2 s[PKM_KT], c[4];
+  const double2* Sg = Sw + (size_t)ws * nchunk * K2_CHUNK_ELEMS;
+  const unsigned bar0 = smem_u32(&sBar[warp][0]);   // + 8 * stage
+  const unsigned buf0 = smem_u32(&sS[warp][0][0]);  // + K2_CHUNK_BYTES * stage
+  if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) s[r] = __ldg(sp + r * PKM_GPW);
+    for (int s = 0; s < K2_STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
-    for (int q = 0; q < 4; ++q) c[q] = __ldg(cp + (size_t)q * xpad);
-    sp += nslot;
-    cp += c_step;
-#pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) {
-      double pr = w[r][0] * c[0].x;
-      double pi = w[r][0] * c[0].y;
-#pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        pr = fma(w[r][q], c[q].x, pr);
-        pi = fma(w[r][q], c[q].y, pi);
+    for (int s = 0; s < K2_STAGES; ++s)
+      if (s < nchunk) {
+        mbar_expect_tx(bar0 + 8u * s, K2_CHUNK_BYTES);
+        bulk_g2s(buf0 + K2_CHUNK_BYTES * s, Sg + (size_t)s * K2_CHUNK_ELEMS, K2_CHUNK_BYTES, bar0 + 8u * s);
       }
-      acc[r].x = fma(s[r].x, pr, acc[r].x);
-      acc[r].x = fma(-s[r].y, pi, acc[r].x);
-      acc[r].y = fma(s[r].x, pi, acc[r].y);
-      acc[r].y = fma(s[r].y, pr, acc[r].y);
+  }
+  __syncwarp();
+
+  const size_t c_step = (size_t)nfi * xpad;
+  const double2* cp = cT + (size_t)sg.x * xpad + xl;
+  double2 cn[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) cn[q] = __ldg(cp + (size_t)q * xpad);
+
+  int stage = 0;
+  unsigned parity = 0;
+  int tz = 0;
+  for (int ci = 0; ci < nchunk; ++ci) {
+    mbar_wait(bar0 + 8u * stage, parity);
+    const double2* sbuf = &sS[warp][stage][0];
+    const int nrow = min(PKM_TZC, ntz - ci * PKM_TZC);
+    for (int j = 0; j < nrow; ++j, ++tz) {
+      double2 c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] = cn[q];
+      if (tz + 1 < ntz) {
+        cp += c_step;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cn[q] = __ldg(cp + (size_t)q * xpad);
+      }
+#pragma unroll
+      for (int r = 0; r < PKM_KT; ++r) {
+        const double2 s = sbuf[j * PKM_KT + r];
+        double pr = w[r][0] * c[0].x;
+        double pi = w[r][0] * c[0].y;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          pr = fma(w[r][q], c[q].x, pr);
+          pi = fma(w[r][q], c[q].y, pi);
+        }
+        acc[r].x = fma(s.x, pr, acc[r].x);
+        acc[r].x = fma(-s.y, pi, acc[r].x);
+        acc[r].y = fma(s.x, pi, acc[r].y);
+        acc[r].y = fma(s.y, pr, acc[r].y);
+      }
+    }
+    __syncwarp();  // every lane is done reading this stage
+    if (lane == 0 && ci + K2_STAGES < nchunk) {
+      mbar_expect_tx(bar0 + 8u * stage, K2_CHUNK_BYTES);
+      bulk_g2s(buf0 + K2_CHUNK_BYTES * stage, Sg + (size_t)(ci + K2_STAGES) * K2_CHUNK_ELEMS, K2_CHUNK_BYTES,
+               bar0 + 8u * stage);
+    }
+    if (++stage == K2_STAGES) {
+      stage = 0;
+      parity ^= 1u;
     }
   }
+  if (x < np) {
+    double2* yo = yhat + (size_t)x * nfo + sg.y;
 #pragma unroll
-  for (int r = 0; r < PKM_KT; ++r) {
-    int k = slot_k[(unit * PKM_KT + r) * PKM_GPW + gsub];
-    if (k >= 0) yhat[(size_t)x * nfo + k] = acc[r];
+    for (int r = 0; r < PKM_KT; ++r)
+      if (r < sg.z) yo[r] = acc[r];
   }
 }
 
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
                      cudaStream_t st) {
-  dim3 grid((pl->slots.nunit + 7) / 8, (npix_tile + 7) / 8);
+  const long long npg = (npix_tile + 31) / 32;
+  const long long nitems = npg * pl->wsegs.nwseg;
+  const unsigned grid = (unsigned)((nitems + K2_WARPS - 1) / K2_WARPS);
   KernelTimer tm(pl, PKM_K_CONTRACT, st);
-  k_contract<<<grid, 256, 0, st>>>(pl->d_Sp, cT, pl->d_group_span, pl->d_slot_w, pl->d_slot_k, yhat,
-                                   pl->ntz, pl->nfi, xpad, pl->slots.nslot, pl->slots.nunit, pl->nfo);
+  k_contract<<<grid, K2_WARPS * 32, 0, st>>>(pl->d_Sw, pl->d_wseg_w, reinterpret_cast<const int4*>(pl->d_wseg),
+                                            cT, yhat, pl->wsegs.nwseg, pl->ntz, pl->nchunk, pl->nfi, xpad,
+                                            npix_tile, pl->nfo, nitems);
   PKM_CUDA(cudaGetLastError());
   pl->launches++;
 }

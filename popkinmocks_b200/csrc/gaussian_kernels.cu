@@ -10,6 +10,9 @@
 // FFT is shared with the density path (fft_kernels.cu).
 #include "pkm_internal.h"
 
+constexpr int GA_KT = 4;   // frequencies per thread
+constexpr int GA_GPW = 4;  // frequency groups per warp (x 8 pixels = 32 lanes)
+
 __global__ void __launch_bounds__(256, 2)
 k_gaussian(const double2* __restrict__ SA, const double* __restrict__ omega,
            const double* __restrict__ P, const double* __restrict__ mu, long long mu_s0,
@@ -25,26 +28,26 @@ k_gaussian(const double2* __restrict__ SA, const double* __restrict__ omega,
   const bool live = x < npix_tile;
   const long long xg = pix0 + (live ? x : 0);
   const long long x1 = xg / nx2, x2 = xg - x1 * nx2;
-  const int k0 = (unit * PKM_GPW + gsub) * PKM_KT;
-  double om[PKM_KT];
+  const int k0 = (unit * GA_GPW + gsub) * GA_KT;
+  double om[GA_KT];
 #pragma unroll
-  for (int r = 0; r < PKM_KT; ++r) om[r] = omega[k0 + r];  // padded with zeros
-  double2 acc[PKM_KT];
+  for (int r = 0; r < GA_KT; ++r) om[r] = omega[k0 + r];  // padded with zeros
+  double2 acc[GA_KT];
 #pragma unroll
-  for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
+  for (int r = 0; r < GA_KT; ++r) acc[r] = make_double2(0.0, 0.0);
 
   for (int t = 0; t < nt; ++t) {
     const double m = mu[t * mu_s0 + x1 * mu_s1 + x2 * mu_s2];
     const double sg = sig[t * sg_s0 + x1 * sg_s1 + x2 * sg_s2];
-    double2 q[PKM_KT];
+    double2 q[GA_KT];
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) q[r] = make_double2(0.0, 0.0);
+    for (int r = 0; r < GA_KT; ++r) q[r] = make_double2(0.0, 0.0);
     const double* pp = P + ((long long)t * npix_total + xg) * nz;
     const double2* sp = SA + (size_t)t * nz * kpad + k0;
     for (int z = 0; z < nz; ++z) {
       const double pz = __ldg(pp + z);
 #pragma unroll
-      for (int r = 0; r < PKM_KT; ++r) {
+      for (int r = 0; r < GA_KT; ++r) {
         double2 s = __ldg(sp + r);
         q[r].x = fma(pz, s.x, q[r].x);
         q[r].y = fma(pz, s.y, q[r].y);
@@ -52,7 +55,7 @@ k_gaussian(const double2* __restrict__ SA, const double* __restrict__ omega,
       sp += kpad;
     }
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) {
+    for (int r = 0; r < GA_KT; ++r) {
       const double so = sg * om[r];
       const double g = exp(-0.5 * (so * so));
       double sn, cs;
@@ -66,17 +69,17 @@ k_gaussian(const double2* __restrict__ SA, const double* __restrict__ omega,
   }
   if (!live) {
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
+    for (int r = 0; r < GA_KT; ++r) acc[r] = make_double2(0.0, 0.0);
   }
 #pragma unroll
-  for (int r = 0; r < PKM_KT; ++r)
+  for (int r = 0; r < GA_KT; ++r)
     if (k0 + r < nfo) yhat[(size_t)x * nfo + k0 + r] = acc[r];
 }
 
 void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
                      int64_t pix0, int npix_tile, int xpad, double2* yhat, cudaStream_t st) {
-  const int nunit = pl->kpadA / (PKM_GPW * PKM_KT);
+  const int nunit = pl->kpadA / (GA_GPW * GA_KT);
   dim3 grid((nunit + 7) / 8, (npix_tile + 7) / 8);
   KernelTimer tm(pl, PKM_K_GAUSSIAN, st);
   k_gaussian<<<grid, 256, 0, st>>>(pl->d_SA, pl->d_omega, P_txz, mu, mu_st[0], mu_st[1], mu_st[2], sig,

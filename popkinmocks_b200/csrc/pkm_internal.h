@@ -70,18 +70,16 @@ struct FoldTables {
 };
 void build_fold_tables(int nv, int v0_idx, double dv, const SplineTables& sp, FoldTables& out);
 
-// k-slots of the contraction kernel: groups of KT consecutive output frequencies that
-// share one 4-tap coefficient window; 4 groups form a warp unit.
-constexpr int PKM_KT = 4;       // frequencies per thread
-constexpr int PKM_GPW = 4;      // groups per warp (x 8 pixels = 32 lanes)
-struct SlotTables {
-  int nslot = 0, ngroup = 0, nunit = 0;
-  std::vector<int32_t> slot_k;     // [nslot]  output frequency or -1 (padding)
-  std::vector<double> slot_w;      // [nslot][4]
-  std::vector<int32_t> group_span; // [ngroup] first coefficient row of the group
+// Work items of the contraction kernel: a "warp segment" is a run of at most PKM_KT consecutive
+// output frequencies that share one 4-tap coefficient window (one spline span).
+constexpr int PKM_KT = 10;      // frequencies per thread of the contraction kernels
+constexpr int PKM_TZC = 12;     // (t,z) rows per staged S-hat' chunk (one bulk copy)
+struct WsegTables {
+  int nwseg = 0;
+  std::vector<int32_t> seg;     // [nwseg][4] = {first coefficient row, first frequency k0, count, 0}
+  std::vector<double> w;        // [nwseg][PKM_KT][4] spline tap weights (zero for padding slots)
 };
-void build_slot_tables(const SplineTables& sp, SlotTables& out);
-inline int slot_pos(int unit, int r, int gsub) { return (unit * PKM_KT + r) * PKM_GPW + gsub; }
+void build_wseg_tables(const SplineTables& sp, WsegTables& out);
 
 // chirp-z tables for the arbitrary-length inverse real FFT
 struct CztTables {
@@ -117,16 +115,16 @@ struct pkm_plan {
 
   // density path
   FoldTables fold;
-  SlotTables slots;
+  WsegTables wsegs;
+  int nchunk = 0;               // ceil(ntz / PKM_TZC)
   int TM = 0, nfiP = 0;         // row tiling of kernel 1 (nfiP = 8*TM padded rows)
   double* d_CRt = nullptr;      // [ne][nfiP]  (u-major, rows padded with zeros)
   double* d_CIt = nullptr;      // [no][nfiP]
   int32_t* d_idx_plus = nullptr;
   int32_t* d_idx_minus = nullptr;
-  double2* d_Sp = nullptr;      // [ntz][nslot]  S-hat' = FXw*dz*dt in slot order, tz = t*nz+z
-  int32_t* d_slot_k = nullptr;
-  double* d_slot_w = nullptr;
-  int32_t* d_group_span = nullptr;
+  double2* d_Sw = nullptr;      // [nwseg][nchunk*TZC][KT]  S-hat' = FXw*dz*dt, tz = t*nz+z, zero padded
+  int32_t* d_wseg = nullptr;    // [nwseg][4]
+  double* d_wseg_w = nullptr;   // [nwseg][KT][4]
 
   // gaussian path
   int kpadA = 0;

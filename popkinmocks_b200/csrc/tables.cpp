@@ -177,37 +177,24 @@ void build_fold_tables(int nv, int v0_idx, double dv, const SplineTables& sp, Fo
   }
 }
 
-void build_slot_tables(const SplineTables& sp, SlotTables& out) {
+void build_wseg_tables(const SplineTables& sp, WsegTables& out) {
   const int nfo = sp.nfo;
-  std::vector<int> gk0, gcnt, gspan;
+  out.seg.clear();
+  out.w.clear();
   int k = 0;
   while (k < nfo) {
-    int span = sp.tap_idx[k];
+    const int span = sp.tap_idx[k];
     int cnt = 1;
     while (cnt < PKM_KT && k + cnt < nfo && sp.tap_idx[k + cnt] == span) ++cnt;
-    gk0.push_back(k);
-    gcnt.push_back(cnt);
-    gspan.push_back(span);
+    out.seg.push_back(span);
+    out.seg.push_back(k);
+    out.seg.push_back(cnt);
+    out.seg.push_back(0);
+    for (int r = 0; r < PKM_KT; ++r)
+      for (int q = 0; q < 4; ++q) out.w.push_back(r < cnt ? sp.tap_w[size_t(k + r) * 4 + q] : 0.0);
     k += cnt;
   }
-  int ngroup = (int)gk0.size();
-  int nunit = (ngroup + PKM_GPW - 1) / PKM_GPW;
-  out.ngroup = nunit * PKM_GPW;
-  out.nunit = nunit;
-  out.nslot = out.ngroup * PKM_KT;
-  out.slot_k.assign(out.nslot, -1);
-  out.slot_w.assign(size_t(out.nslot) * 4, 0.0);
-  out.group_span.assign(out.ngroup, 0);
-  for (int g = 0; g < ngroup; ++g) {
-    int unit = g / PKM_GPW, gsub = g % PKM_GPW;
-    out.group_span[g] = gspan[g];
-    for (int r = 0; r < gcnt[g]; ++r) {
-      int pos = slot_pos(unit, r, gsub);
-      int kk = gk0[g] + r;
-      out.slot_k[pos] = kk;
-      for (int q = 0; q < 4; ++q) out.slot_w[size_t(pos) * 4 + q] = sp.tap_w[size_t(kk) * 4 + q];
-    }
-  }
+  out.nwseg = (int)out.seg.size() / 4;
 }
 
 void build_czt_tables(int n, CztTables& out) {

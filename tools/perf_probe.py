@@ -37,9 +37,12 @@ def timeit(fn, reps=5):
 
 
 vox = plan.n_fft * nx * nx
+plan.set_profiling(True)
 ms = timeit(lambda: plan.ybar_density(p, is_log=False))
-print(f"density  {nx}x{nx} nv={nv}: {ms:.2f} ms  {vox/ms/1e3:.3e} voxel/s")
+print(f"density  {nx}x{nx} nv={nv}: {ms:.2f} ms  {vox/ms*1e3:.3e} voxel/s", {k: round(v[0]/6, 3) for k, v in plan.kernel_times().items()})
+plan.set_profiling(True)
 ms = timeit(lambda: plan.ybar_density(p, is_log=True))
-print(f"density(log) : {ms:.2f} ms  {vox/ms/1e3:.3e} voxel/s")
+print(f"density(log) : {ms:.2f} ms  {vox/ms*1e3:.3e} voxel/s", {k: round(v[0]/6, 3) for k, v in plan.kernel_times().items()})
+plan.set_profiling(True)
 ms = timeit(lambda: plan.ybar_gaussian(P, mu, sg))
-print(f"gaussian {nx}x{nx}: {ms:.2f} ms  {vox/ms/1e3:.3e} voxel/s")
+print(f"gaussian {nx}x{nx}: {ms:.2f} ms  {vox/ms*1e3:.3e} voxel/s", {k: round(v[0]/6, 3) for k, v in plan.kernel_times().items()})
