@@ -10,8 +10,12 @@
 // kernel 2 (contract): streams S' (L2 resident) and the coefficient rows, evaluates the 4-tap
 //                      spline on the fly and accumulates over (t,z) in registers.
 // P-hat (25 MB per pixel in the reference, base.py:846-853) is never materialised.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "pkm_internal.h"
 
@@ -38,6 +42,12 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// one 2-D box of a tiled tensor map -> shared memory (dense [box rows][box cols])
+__device__ __forceinline__ void tensor2d_g2s(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -50,9 +60,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 // Persistent CTAs (one per SM), each looping over tiles = (age t, block of PXB pixels), i.e.
 // NC = PXB*nz density columns of nv velocities.  The folded DFT*spline matrices stay resident
 // in shared memory for the CTA's lifetime.  The density slab is double buffered: while tile i is
-// being transformed, the [nv][NC] slab of tile i+1 streams into the other buffer as nv 1-D TMA
-// bulk copies (for fixed v the NC columns are contiguous in global memory) that complete on an
-// mbarrier.  Per tile:
+// being transformed, the [nv][NC] slab of tile i+1 streams into the other buffer as ONE 2-D TMA
+// tensor copy (box = nv velocity rows x NC contiguous columns of the [nt*nv][npix*nz] matrix view
+// of the density) completing on an mbarrier; layouts the tensor map cannot describe fall back
+// to nv 1-D bulk copies, unaligned ones to plain loads.  Per tile:
 //   phase 1: fold v <-> -v in place (e = sum, o = difference of the rolled profile), exp(log p)
 //            fused here when the caller passes log densities
 //   phase 2: warp-tiled FP64 GEMM; lanes = 8 row groups x 4 column groups, thread tile TM x 4;
@@ -65,7 +76,8 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 
 struct K1Geom {
   long long npix_total, pix0;
-  int npix_tile, xpad, nv, nz, nfi, ne, no, pxb, nt, is_log, use_tma, v0;
+  int npix_tile, xpad, nv, nz, nfi, ne, no, pxb, nt, is_log, v0;
+  int use_tma;  // 0 = plain loads, 1 = one 1-D bulk copy per velocity row, 2 = one 2-D tensor copy per tile
 };
 
 // velocity row holding rolled position +u / -u  (np.roll(p, nv - v0), base.py:843)
@@ -80,8 +92,8 @@ __device__ __forceinline__ int row_minus(int u, int v0, int nv) {
 
 template <int TM>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-k_coeff(const double* __restrict__ dens, K1Geom g, const double* __restrict__ CRt,
-        const double* __restrict__ CIt, double2* __restrict__ cT) {
+k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tmap, K1Geom g,
+        const double* __restrict__ CRt, const double* __restrict__ CIt, double2* __restrict__ cT) {
   extern __shared__ __align__(128) double smem[];
   constexpr int TMP = TM + (TM & 1);  // even row padding -> 16-byte aligned double2 loads
   constexpr int NFIP = 8 * TMP;
@@ -89,7 +101,7 @@ k_coeff(const double* __restrict__ dens, K1Geom g, const double* __restrict__ CR
   const int NC = pxb * nz;
   const int NCp = (NC + 15) & ~15;
   // one slab buffer holds the [nv][NCp] density slab and later the [nz][nfi][pxb] complex staging
-  const int buf_elems = max(nv * NCp, 2 * nz * nfi * pxb);
+  const int buf_elems = (max(nv * NCp, 2 * nz * nfi * pxb) + 15) & ~15;
   double* As_r = smem;                                   // [ne][NFIP]
   double* As_i = As_r + (size_t)ne * NFIP;               // [max(no,1)][NFIP]
   double* Bbuf = As_i + (size_t)max(no, 1) * NFIP;       // [2][buf_elems]
@@ -126,8 +138,16 @@ k_coeff(const double* __restrict__ dens, K1Geom g, const double* __restrict__ CR
     const int ncol_valid = min(pxb, g.npix_tile - xb * pxb) * nz;
     const double* src = dens + (size_t)t * nv * vstride + (size_t)(g.pix0 + (long long)xb * pxb) * nz;
     double* dst = Bbuf + (size_t)b * buf_elems;
-    const bool tma = g.use_tma && ((ncol_valid & 1) == 0);
-    if (tma) {
+    const bool tma = g.use_tma == 2 || (g.use_tma == 1 && (ncol_valid & 1) == 0);
+    if (g.use_tma == 2) {
+      // out-of-range columns / rows of the box are zero filled by the TMA unit; columns past
+      // this call's pixel range but inside the array are real (finite) data of other pixels
+      if (tid == 0) {
+        const unsigned bar = bar0 + 8u * b;
+        mbar_expect_tx(bar, (unsigned)(nv * NC) * 8u);
+        tensor2d_g2s(smem_u32(dst), &tmap, (int)((g.pix0 + (long long)xb * pxb) * nz), t * nv, bar);
+      }
+    } else if (tma) {
       if (warp == 0) {
         const unsigned bar = bar0 + 8u * b;
         const unsigned row_bytes = (unsigned)ncol_valid * 8u;
@@ -272,9 +292,35 @@ void density_tables_upload(pkm_plan* pl) {
   upload_padded_transposed(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, &pl->d_CIt);
 }
 
+// [rows][cols] float64 matrix view of the density, box = box_rows x box_cols (tiled, no swizzle)
+static bool encode_density_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows,
+                               int box_cols, int box_rows) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    else
+      cudaGetLastError();
+  }
+  if (!encode) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static size_t coeff_smem_bytes(const pkm_plan* pl, int pxb) {
   const int NC = pxb * pl->d.nz, NCp = (NC + 15) & ~15;
-  const size_t buf_elems = std::max<size_t>((size_t)pl->d.nv * NCp, (size_t)2 * pl->d.nz * pl->nfi * pxb);
+  const size_t buf_elems = (std::max<size_t>((size_t)pl->d.nv * NCp, (size_t)2 * pl->d.nz * pl->nfi * pxb) + 15) & ~size_t(15);
   size_t dbl = (size_t)(pl->fold.ne + std::max(pl->fold.no, 1)) * pl->nfiP + 2 * buf_elems;
   return dbl * sizeof(double) + 2 * sizeof(unsigned long long);
 }
@@ -302,13 +348,20 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile; g.xpad = xpad;
   g.nv = pl->d.nv; g.nz = pl->d.nz; g.nfi = pl->nfi; g.ne = pl->fold.ne; g.no = pl->fold.no;
   g.pxb = pxb; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
-  // 1-D bulk copies need 16-byte aligned row starts and sizes
+  // 1-D bulk copies need 16-byte aligned row starts and sizes; the tensor map needs a 16-byte
+  // aligned base and row pitch and writes a dense [nv][NC] box (so NC must equal the padded pitch)
   const int nz = pl->d.nz;
-  g.use_tma = (reinterpret_cast<uintptr_t>(dens) % 16 == 0) && ((npix_total * nz) % 2 == 0) &&
-              ((pix0 * nz) % 2 == 0) && ((pxb * nz) % 2 == 0);
-  if (getenv("PKM_COEFF_NO_TMA")) g.use_tma = 0;
+  const int NC = pxb * nz;
+  const bool base_ok = reinterpret_cast<uintptr_t>(dens) % 16 == 0 && (npix_total * nz) % 2 == 0;
+  g.use_tma = (base_ok && (pix0 * nz) % 2 == 0 && NC % 2 == 0) ? 1 : 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (base_ok && NC % 16 == 0 && NC <= 256 && pl->d.nv <= 256 && npix_total * nz < (1LL << 31) &&
+      encode_density_map(&tmap, dens, npix_total * nz, (int64_t)pl->d.nt * pl->d.nv, NC, pl->d.nv))
+    g.use_tma = 2;
+  if (const char* e = getenv("PKM_COEFF_TMA_MODE")) g.use_tma = std::min(g.use_tma, atoi(e));
   KernelTimer tm(pl, PKM_K_COEFF, st);
-  k_coeff<TM><<<grid, K1_THREADS, smem, st>>>(dens, g, pl->d_CRt, pl->d_CIt, cT);
+  k_coeff<TM><<<grid, K1_THREADS, smem, st>>>(dens, tmap, g, pl->d_CRt, pl->d_CIt, cT);
   PKM_CUDA(cudaGetLastError());
   pl->launches++;
 }
