@@ -381,7 +381,7 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 // ============================================================================
 // kernel 2
 // ============================================================================
-// Y-hat[k,x] = sum_{tz} S'[k,tz] * sum_{q<4} w[k][q] c[i_k+q, tz, x]     (12 FP64 FMA per (k,tz,x))
+// Y-hat[k,x] = sum_{tz} S'[k,tz] * sum_{q<4} w[k][q] c[i_k+q, tz, x]     (10.6 FP64 ops per (k,tz,x))
 //
 // The kernel is bound by the FP64 pipe, so everything else is arranged to stay out of its way:
 //   * work item = one warp = (warp segment, block of 32 pixels): the lanes are 32 consecutive
@@ -396,8 +396,15 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 //     CTA = 4 warps, 3 CTAs per SM -> 12 warps per SM, 3 per scheduler.
 constexpr int K2_WARPS = 4;
 constexpr int K2_STAGES = 3;
+constexpr int K2_G = 2;        // frequencies whose FMA chains are interleaved (PKM_KT % K2_G == 0)
 constexpr int K2_CHUNK_ELEMS = PKM_TZC * PKM_KT;                      // double2 per staged chunk
 constexpr unsigned K2_CHUNK_BYTES = K2_CHUNK_ELEMS * sizeof(double2);  // 1920
+
+__device__ __forceinline__ double2 ldg_nc_f64x2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 
 __global__ void __launch_bounds__(K2_WARPS * 32, 3)
 k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
@@ -414,11 +421,13 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
   const int x = pg * 32 + lane;
   const int xl = min(x, np - 1);      // lanes past the tile re-read the last pixel, never store
 
-  double w[PKM_KT][4];
+  // The 4 B-spline taps of a frequency sum to one, so P-hat = c3 + sum_{q<3} w_q (c_q - c3):
+  // three weights per frequency in registers and 3 instead of 4 FP64 ops per component.
+  double w[PKM_KT][3];
 #pragma unroll
   for (int r = 0; r < PKM_KT; ++r)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w[r][q] = __ldg(Ww + ((size_t)ws * PKM_KT + r) * 4 + q);
+    for (int q = 0; q < 3; ++q) w[r][q] = __ldg(Ww + ((size_t)ws * PKM_KT + r) * 4 + q);
   double2 acc[PKM_KT];
 #pragma unroll
   for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
@@ -441,9 +450,9 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
 
   const size_t c_step = (size_t)nfi * xpad;
   const double2* cp = cT + (size_t)sg.x * xpad + xl;
-  double2 cn[4];
+  double2 c[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) cn[q] = __ldg(cp + (size_t)q * xpad);
+  for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + (size_t)q * xpad);
 
   int stage = 0;
   unsigned parity = 0;
@@ -453,28 +462,45 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
     const double2* sbuf = &sS[warp][stage][0];
     const int nrow = min(PKM_TZC, ntz - ci * PKM_TZC);
     for (int j = 0; j < nrow; ++j, ++tz) {
-      double2 c[4];
+      // d_q = c_q - c_3 frees the c registers: the loads of the next (t,z) step are issued
+      // right here, a whole step ahead of their use (pinned with volatile asm)
+      double2 d[3];
+      const double2 c3 = c[3];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] = cn[q];
-      if (tz + 1 < ntz) {
-        cp += c_step;
+      for (int q = 0; q < 3; ++q) d[q] = make_double2(c[q].x - c3.x, c[q].y - c3.y);
+      cp += (tz + 1 < ntz) ? c_step : 0;  // branch-free: the last step re-reads its own rows
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cn[q] = __ldg(cp + (size_t)q * xpad);
-      }
+      for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + (size_t)q * xpad);
+      // B200's FP64 pipe needs >= 4 independent DFMAs per warp to reach its issue rate (8-cycle
+      // latency, one warp instruction per ~2.2 cycles per scheduler): frequencies are processed
+      // in groups of K2_G with their chains interleaved.
 #pragma unroll
-      for (int r = 0; r < PKM_KT; ++r) {
-        const double2 s = sbuf[j * PKM_KT + r];
-        double pr = w[r][0] * c[0].x;
-        double pi = w[r][0] * c[0].y;
+      for (int h = 0; h < PKM_KT; h += K2_G) {
+        double pr[K2_G], pi[K2_G];
+        double2 sv[K2_G];
 #pragma unroll
-        for (int q = 1; q < 4; ++q) {
-          pr = fma(w[r][q], c[q].x, pr);
-          pi = fma(w[r][q], c[q].y, pi);
+        for (int g = 0; g < K2_G; ++g) {
+          sv[g] = sbuf[j * PKM_KT + h + g];
+          pr[g] = c3.x;
+          pi[g] = c3.y;
         }
-        acc[r].x = fma(s.x, pr, acc[r].x);
-        acc[r].x = fma(-s.y, pi, acc[r].x);
-        acc[r].y = fma(s.x, pi, acc[r].y);
-        acc[r].y = fma(s.y, pr, acc[r].y);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int g = 0; g < K2_G; ++g) {
+            pr[g] = fma(w[h + g][q], d[q].x, pr[g]);
+            pi[g] = fma(w[h + g][q], d[q].y, pi[g]);
+          }
+#pragma unroll
+        for (int g = 0; g < K2_G; ++g) {
+          acc[h + g].x = fma(sv[g].x, pr[g], acc[h + g].x);
+          acc[h + g].y = fma(sv[g].x, pi[g], acc[h + g].y);
+        }
+#pragma unroll
+        for (int g = 0; g < K2_G; ++g) {
+          acc[h + g].x = fma(-sv[g].y, pi[g], acc[h + g].x);
+          acc[h + g].y = fma(sv[g].y, pr[g], acc[h + g].y);
+        }
       }
     }
     __syncwarp();  // every lane is done reading this stage
