@@ -313,10 +313,10 @@ struct OutSpec {
 
 int pixel_tile(const pkm_plan* pl, int64_t npix, size_t bytes_per_px) {
   int64_t t = (int64_t)(pl->ws_limit / std::max<size_t>(bytes_per_px, 1));
-  t = std::min<int64_t>(t, npix + 15);
+  t = std::min<int64_t>(t, npix + 31);
   t = std::min<int64_t>(t, 65535LL * 8);
-  t &= ~int64_t(15);
-  return (int)std::max<int64_t>(t, 16);
+  t &= ~int64_t(31);
+  return (int)std::max<int64_t>(t, 32);
 }
 
 // ypx tile [np][n] (device) -> caller's buffer
@@ -379,8 +379,8 @@ extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is
     if (in_host) per_px += sizeof(double) * (size_t)nt * nv * nz;
     if (out_host && out_layout == PKM_LAYOUT_CUBE) per_px += sizeof(double) * n;
     int tile = pixel_tile(pl, npix, per_px);
-    tile = std::max(tile / pxb * pxb, pxb);
-    if (tile % 16) tile = (tile + 15) & ~15;
+    tile = std::max((tile / 32) * 32, 32);  // the coefficient layout groups pixels by 32
+    (void)pxb;
 
     pl->coef.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
     pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);

@@ -253,13 +253,14 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
       }
     }
     __syncthreads();
-    // phase 4: cT[((t*nz + z)*nfi + m)*xpad + xb*pxb + x]
+    // phase 4: cT[x/32][t*nz + z][m][x%32]
     for (int i = tid; i < nz * nfi * pxb; i += K1_THREADS) {
       const int zm = i / pxb, xs = i - zm * pxb;
       const int z = zm / nfi, m = zm - z * nfi;
       const int x = xs ^ ((m + (z >> 2)) & xmask);
       const double2 v = reinterpret_cast<const double2*>(Cs)[i];
-      cT[((size_t)t * nz * nfi + zm) * g.xpad + (size_t)xb * pxb + x] = v;
+      const int xg = xb * pxb + x;  // pixel-group-major layout, see coef_index()
+      cT[(((size_t)(xg >> 5) * g.nt * nz + (size_t)t * nz + z) * nfi + m) * 32 + (xg & 31)] = v;
     }
     // order this tile's generic-proxy accesses to the buffer before the TMA refill of it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -369,7 +370,7 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total, int64_t pix0,
                   int npix_tile, int xpad, double2* cT, cudaStream_t st) {
   const int pxb = coeff_choose_pxb(pl);
-  PKM_REQUIRE(xpad % pxb == 0 && xpad >= npix_tile, "internal: xpad=%d not a multiple of %d", xpad, pxb);
+  PKM_REQUIRE(xpad % 32 == 0 && xpad >= npix_tile, "internal: xpad=%d not a multiple of 32", xpad);
   switch (pl->TM) {
 #define CASE(T) case T: launch_coeff_t<T>(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, pxb, cT, st); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
@@ -396,6 +397,7 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 //     CTA = 4 warps, 3 CTAs per SM -> 12 warps per SM, 3 per scheduler.
 constexpr int K2_WARPS = 4;
 constexpr int K2_STAGES = 3;
+constexpr int K2_PF = 6;       // L2 prefetch distance of the coefficient rows in (t,z) steps
 constexpr int K2_G = 2;        // frequencies whose FMA chains are interleaved (PKM_KT % K2_G == 0)
 constexpr int K2_CHUNK_ELEMS = PKM_TZC * PKM_KT;                      // double2 per staged chunk
 constexpr unsigned K2_CHUNK_BYTES = K2_CHUNK_ELEMS * sizeof(double2);  // 1920
@@ -448,11 +450,13 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
   }
   __syncwarp();
 
-  const size_t c_step = (size_t)nfi * xpad;
-  const double2* cp = cT + (size_t)sg.x * xpad + xl;
+  // coefficients are stored pixel-group major, cT[x/32][tz][m][x%32]: the ntz*nfi rows one warp
+  // walks are a single contiguous 16 MB stream (TLB and DRAM-page friendly), 512 bytes per row
+  const size_t c_step = (size_t)nfi * 32;
+  const double2* cp = cT + (((size_t)pg * ntz) * nfi + sg.x) * 32 + (xl & 31);
   double2 c[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + (size_t)q * xpad);
+  for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + q * 32);
 
   int stage = 0;
   unsigned parity = 0;
@@ -469,8 +473,12 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
 #pragma unroll
       for (int q = 0; q < 3; ++q) d[q] = make_double2(c[q].x - c3.x, c[q].y - c3.y);
       cp += (tz + 1 < ntz) ? c_step : 0;  // branch-free: the last step re-reads its own rows
+      // the coefficient tile streams from HBM: each warp pulls one of the span's 4 rows a few
+      // steps ahead into L2 (the ~5 warps of a span cover all four), hiding the DRAM latency
+      if (tz + K2_PF < ntz)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)(K2_PF - 1) * c_step + (ws & 3) * 32));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + (size_t)q * xpad);
+      for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + q * 32);
       // B200's FP64 pipe needs >= 4 independent DFMAs per warp to reach its issue rate (8-cycle
       // latency, one warp instruction per ~2.2 cycles per scheduler): frequencies are processed
       // in groups of K2_G with their chains interleaved.
