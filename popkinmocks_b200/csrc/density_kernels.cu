@@ -394,9 +394,10 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 //     (cp.async.bulk + mbarrier complete_tx), one 1920-byte chunk = 12 (t,z) rows x KT
 //     frequencies per copy, 3 stages per warp, and read back as broadcast LDS.128;
 //   * warps are fully independent pipelines (own stages, own mbarriers, no CTA barrier):
-//     CTA = 4 warps, 3 CTAs per SM -> 12 warps per SM, 3 per scheduler.
+//     CTA = 4 warps, K2_CTAS_PER_SM CTAs per SM.
 constexpr int K2_WARPS = 4;
 constexpr int K2_STAGES = 3;
+constexpr int K2_CTAS_PER_SM = 3;
 constexpr int K2_PF = 6;       // L2 prefetch distance of the coefficient rows in (t,z) steps
 constexpr int K2_G = 2;        // frequencies whose FMA chains are interleaved (PKM_KT % K2_G == 0)
 constexpr int K2_CHUNK_ELEMS = PKM_TZC * PKM_KT;                      // double2 per staged chunk
@@ -408,13 +409,15 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const double2* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32, 3)
+__global__ void __launch_bounds__(K2_WARPS * 32, K2_CTAS_PER_SM)
 k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
            const int4* __restrict__ wsegs, const double2* __restrict__ cT,
            double2* __restrict__ yhat, int nwseg, int ntz, int nchunk, int nfi, int xpad, int np,
            int nfo, long long nitems) {
-  __shared__ __align__(128) double2 sS[K2_WARPS][K2_STAGES][K2_CHUNK_ELEMS];
-  __shared__ __align__(8) unsigned long long sBar[K2_WARPS][K2_STAGES];
+  extern __shared__ __align__(128) unsigned char k2_smem[];
+  double2 (*sS)[K2_STAGES][K2_CHUNK_ELEMS] = reinterpret_cast<double2 (*)[K2_STAGES][K2_CHUNK_ELEMS]>(k2_smem);
+  unsigned long long (*sBar)[K2_STAGES] = reinterpret_cast<unsigned long long (*)[K2_STAGES]>(
+      k2_smem + sizeof(double2) * K2_WARPS * K2_STAGES * K2_CHUNK_ELEMS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * K2_WARPS + warp;
   if (item >= nitems) return;  // warps never synchronise with each other
@@ -488,6 +491,7 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
         double2 sv[K2_G];
 #pragma unroll
         for (int g = 0; g < K2_G; ++g) {
+          if (h + g >= PKM_KT) continue;
           sv[g] = sbuf[j * PKM_KT + h + g];
           pr[g] = c3.x;
           pi[g] = c3.y;
@@ -496,16 +500,19 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
         for (int q = 0; q < 3; ++q)
 #pragma unroll
           for (int g = 0; g < K2_G; ++g) {
+            if (h + g >= PKM_KT) continue;
             pr[g] = fma(w[h + g][q], d[q].x, pr[g]);
             pi[g] = fma(w[h + g][q], d[q].y, pi[g]);
           }
 #pragma unroll
         for (int g = 0; g < K2_G; ++g) {
+          if (h + g >= PKM_KT) continue;
           acc[h + g].x = fma(sv[g].x, pr[g], acc[h + g].x);
           acc[h + g].y = fma(sv[g].x, pi[g], acc[h + g].y);
         }
 #pragma unroll
         for (int g = 0; g < K2_G; ++g) {
+          if (h + g >= PKM_KT) continue;
           acc[h + g].x = fma(-sv[g].y, pi[g], acc[h + g].x);
           acc[h + g].y = fma(sv[g].y, pr[g], acc[h + g].y);
         }
@@ -535,8 +542,11 @@ void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, d
   const long long npg = (npix_tile + 31) / 32;
   const long long nitems = npg * pl->wsegs.nwseg;
   const unsigned grid = (unsigned)((nitems + K2_WARPS - 1) / K2_WARPS);
+  const size_t smem = sizeof(double2) * K2_WARPS * K2_STAGES * K2_CHUNK_ELEMS +
+                      sizeof(unsigned long long) * K2_WARPS * K2_STAGES;
+  PKM_CUDA(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelTimer tm(pl, PKM_K_CONTRACT, st);
-  k_contract<<<grid, K2_WARPS * 32, 0, st>>>(pl->d_Sw, pl->d_wseg_w, reinterpret_cast<const int4*>(pl->d_wseg),
+  k_contract<<<grid, K2_WARPS * 32, smem, st>>>(pl->d_Sw, pl->d_wseg_w, reinterpret_cast<const int4*>(pl->d_wseg),
                                             cT, yhat, pl->wsegs.nwseg, pl->ntz, pl->nchunk, pl->nfi, xpad,
                                             npix_tile, pl->nfo, nitems);
   PKM_CUDA(cudaGetLastError());
