@@ -8,3 +8,5 @@ CPU fallback.
 from .model_grids import milesSSPs  # noqa: F401
 from . import ifu_cube  # noqa: F401
 from . import engine  # noqa: F401
+from . import components  # noqa: F401
+from . import noise  # noqa: F401

@@ -1,0 +1,341 @@
+"""`ParametricComponent`: factorised densities with a Gaussian line-of-sight velocity law.
+
+    p(t, v, x, z) = p(t) p(x|t) p(z|t,x) N(v; mu_v(t,x), sig_v(t,x))
+
+Host-side model construction (off the hot path) behind the reference's
+API (/root/reference/popkinmocks/components/parametric.py): `set_p_t`, the chemical
+enrichment model for p(z|t,x), every `_get_log_p_<dist>` marginal, the analytic velocity
+moments, and `evaluate_ybar`, which hands `P_txz`, `mu_v`, `sig_v` to the CUDA Gaussian-LOSVD
+kernel (pkm_ybar_gaussian <- parametric.py:335-407).
+
+The marginals are organised differently from the reference: all of them are reductions of two
+arrays, log P(t,x,z) (no velocity) and log P(t,v,x,z) = log P(t,x,z) + log P(v|t,x), built from
+the stored factors.  Distributions without `v` never integrate the velocity law (its tails
+outside the cube's velocity range are not renormalised, exactly as in the reference).
+"""
+from abc import abstractmethod
+
+import numpy as np
+from scipy import special, stats
+
+from . import base
+from .. import engine
+
+
+def _log_diff_exp(log_hi, log_lo):
+    """log(exp(log_hi) - exp(log_lo)), elementwise."""
+    stacked = np.stack([log_hi, log_lo], axis=-1)
+    return special.logsumexp(stacked, axis=-1, b=[1.0, -1.0])
+
+
+class ParametricComponent(base.Component):
+    """Abstract parametric component; subclasses provide p(x|t), t_dep(x), mu_v and sig_v.
+
+    Args:
+        cube: a `popkinmocks_b200.ifu_cube.IFUCube`
+        center (x1, x2): centre of the component
+        rotation: anti-clockwise rotation of the component's axes (radians)
+    """
+
+    def __init__(self, cube=None, center=(0, 0), rotation=0.0):
+        self.cube = cube
+        self.center = center
+        self.rotation = rotation
+        dx1 = self.cube.xx - center[0]
+        dx2 = self.cube.yy - center[1]
+        c, s = np.cos(rotation), np.sin(rotation)
+        # coordinates in the component's own frame; the reference contracts the FIRST index of
+        # [[c, s], [-s, c]] with the position vector (parametric.py:43-49)
+        self.xxp = c * dx1 - s * dx2
+        self.yyp = s * dx1 + c * dx2
+        self.get_z_interpolation_grid()
+
+    # ------------------------------------------------------------------ star formation history
+    def get_beta_a_b_from_lmd_phi(self, lmd, phi):
+        """Beta shape parameters from total concentration `lmd` and mean `phi`."""
+        return lmd * phi, lmd * (1.0 - phi)
+
+    def set_p_t(self, lmd=None, phi=None, cdf_start_end=(0.05, 0.95)):
+        """Beta-distributed star formation history p(t) (parametric.py:89-144).
+
+        Also records the ages `t_start`, `t_end` between which the time-varying parameters of
+        the other factors are interpolated."""
+        a, b = self.get_beta_a_b_from_lmd_phi(lmd, phi)
+        if not (a > 1.0 or b > 1.0):
+            raise ValueError("SFH is bimodal - increase lmd?'")
+        t_edges = self.cube.ssps.par_edges[1]
+        sfh = stats.beta(a, b, loc=t_edges[0], scale=t_edges[-1] - t_edges[0])
+        t_start, t_end = sfh.ppf(cdf_start_end)
+        self.t_pars = dict(lmd=lmd, phi=phi, t_start=t_start, t_end=t_end, delta_t=t_end - t_start,
+                           idx_start_end=np.digitize([t_start, t_end], t_edges))
+        log_cdf = sfh.logcdf(t_edges)
+        log_P_t = _log_diff_exp(log_cdf[1:], log_cdf[:-1])
+        self.log_p_t = log_P_t - np.log(self.cube.construct_volume_element("t"))
+        self.p_t = np.exp(self.log_p_t)
+
+    def linear_interpolate_t(self, f_end, f_start):
+        """A parameter varying linearly in age between f_start (at t_start) ... note the
+        reference's argument order: value `f_end` applies before `t_start`, `f_start` after
+        `t_end` (parametric.py:68-87)."""
+        t = self.cube.ssps.par_cents[1]
+        slope = (f_start - f_end) / self.t_pars["delta_t"]
+        f = f_end + slope * (t - self.t_pars["t_start"])
+        f[t < self.t_pars["t_start"]] = f_end
+        f[t > self.t_pars["t_end"]] = f_start
+        return f
+
+    # ------------------------------------------------------------------ abstract factors
+    @abstractmethod
+    def set_p_x_t(self):
+        pass
+
+    @abstractmethod
+    def set_mu_v(self):
+        pass
+
+    @abstractmethod
+    def set_sig_v(self):
+        pass
+
+    @abstractmethod
+    def set_t_dep(self):
+        pass
+
+    # ------------------------------------------------------------------ chemical enrichment
+    def get_z_interpolation_grid(self, t_dep_lim=(0.1, 10.0), n_t_dep=1000, n_z=1000):
+        """Tabulate mean metallicity against age for a grid of depletion times.
+
+        Zhu, van de Venn, Leaman et al. 2020 (eqs 3-10): t(z) = t_H - t_dep z / (1 - a z^b);
+        inverted by interpolation onto the SSP ages (parametric.py:213-247)."""
+        self.ahat = 10.0 ** (-0.689)
+        self.bhat = 1.899 - 1.0
+        z_max = 0.9999 * self.ahat ** (-1.0 / self.bhat)
+        t_hubble = self.cube.ssps.par_edges[1][-1]
+        t_dep = np.logspace(np.log10(t_dep_lim[0]), np.log10(t_dep_lim[1]), n_t_dep)
+        z = np.linspace(z_max, 0.0, n_z)
+        t_of_z = t_hubble - t_dep[:, None] * z[None, :] / (1.0 - self.ahat * z[None, :] ** self.bhat)
+        self.t = t_of_z
+        t_ssps = self.cube.ssps.par_cents[1]
+        z_of_t = np.empty((n_t_dep, t_ssps.size))
+        for i in range(n_t_dep):
+            z_of_t[i] = np.interp(t_ssps, t_of_z[i], z)
+        self.z_t_interp_grid = dict(t=t_ssps, z=z_of_t, t_dep=t_dep)
+
+    def evaluate_chemical_enrichment_model_base(self, t_dep):
+        """log p(z|t,x) for a map of depletion times t_dep[x1,x2] (parametric.py:253-289).
+
+        Linear metallicity is Gaussian about the tabulated mean with variance a z^b, binned
+        onto the SSP metallicity edges and normalised over the grid."""
+        grid = self.z_t_interp_grid
+        nearest = np.argmin(np.abs(t_dep[:, :, None] - grid["t_dep"]), axis=-1)
+        z_mu = np.moveaxis(grid["z"][nearest], -1, 0)                     # [t, x1, x2]
+        z_sd = (self.ahat * z_mu ** self.bhat) ** 0.5
+        lin_z_edges = 10.0 ** self.cube.ssps.par_edges[0]
+        law = stats.norm(loc=z_mu, scale=z_sd)
+        log_cdf = law.logcdf(lin_z_edges[:, None, None, None])            # [z+1, t, x1, x2]
+        log_P = _log_diff_exp(log_cdf[1:], log_cdf[:-1])                  # [z, t, x1, x2]
+        log_dz = np.log(self.cube.construct_volume_element("z"))
+        log_norm = special.logsumexp(log_P.T + log_dz, -1).T
+        log_p_z_tx = log_P - log_norm
+        return log_p_z_tx, np.exp(log_p_z_tx)
+
+    def set_p_z_tx(self):
+        self.log_p_z_tx, self.p_z_tx = self.evaluate_chemical_enrichment_model_base(self.t_dep)
+
+    def evaluate_chemical_enrichment_model(self, t_dep):
+        """p(z|t) for one spatially constant depletion time."""
+        uniform = np.full((self.cube.nx, self.cube.ny), t_dep)
+        _, p_z_tx = self.evaluate_chemical_enrichment_model_base(uniform)
+        return p_z_tx[:, :, 0, 0]
+
+    # ------------------------------------------------------------------ building blocks
+    def _log_P_txz_mass(self):
+        """log P(t,x,z): volume-weighted, mass-weighted, shape [t, x1, x2, z]."""
+        cube = self.cube
+        log_P_t = self.log_p_t + np.log(cube.construct_volume_element("t"))
+        log_P_x_t = self.log_p_x_t + (np.log(cube.dx) + np.log(cube.dy))          # [x1, x2, t]
+        log_P_z_tx = (self.log_p_z_tx.T + np.log(cube.construct_volume_element("z"))).T  # [z,t,x1,x2]
+        log_P_tx = np.moveaxis(log_P_x_t + log_P_t, -1, 0)
+        return log_P_tx[..., None] + np.moveaxis(log_P_z_tx, 0, -1)
+
+    def _log_P_v_tx(self):
+        """log P(v-bin | t,x) from Gaussian cdf differences, shape [v, t, x1, x2]."""
+        v_edg = self.cube.v_edg[:, None, None, None]
+        law = stats.norm(loc=self.mu_v, scale=self.sig_v)
+        return _log_diff_exp(law.logcdf(v_edg[1:]), law.logcdf(v_edg[:-1]))
+
+    def _log_P_joint(self, with_v, light_weighted):
+        """log P over (t,x,z) or (t,v,x,z), light-weighted and renormalised if asked."""
+        log_P = self._log_P_txz_mass()
+        lw_axes = (slice(None), None, None, slice(None))
+        if with_v:
+            log_P = log_P[:, None] + np.moveaxis(self._log_P_v_tx(), 0, 1)[..., None]
+            lw_axes = (slice(None), None, None, None, slice(None))
+        if light_weighted:
+            log_P = log_P + np.log(self.cube.ssps.light_weights[lw_axes])
+            log_P = log_P - special.logsumexp(log_P)
+        return log_P
+
+    def _log_marginal(self, keep, density=True, light_weighted=False):
+        with_v = "v" in keep
+        log_P = self._log_P_joint(with_v, light_weighted)
+        axes = {"t": (0,), "v": (1,), "x": (2, 3), "z": (4,)} if with_v else \
+               {"t": (0,), "x": (1, 2), "z": (3,)}
+        drop = tuple(ax for name, axs in axes.items() if name not in keep for ax in axs)
+        if drop:
+            log_P = special.logsumexp(log_P, drop)
+        if density:
+            log_P = log_P - np.log(self.cube.construct_volume_element(keep))
+        return log_P
+
+    # hard-coded conditionals kept for API parity: mass-weighted they are the stored factors
+    def _get_log_p_x_t(self, density=True, light_weighted=False):
+        if light_weighted:
+            raise NotImplementedError  # falls back to joint - marginal in get_log_p
+        out = self.log_p_x_t.copy()
+        if not density:
+            out += np.log(self.cube.dx) + np.log(self.cube.dy)
+        return out
+
+    def _get_log_p_z_tx(self, density=True, light_weighted=False):
+        if light_weighted:
+            raise NotImplementedError
+        out = self.log_p_z_tx.copy()
+        if not density:
+            out = (out.T + np.log(self.cube.construct_volume_element("z"))).T
+        return out
+
+    def _get_log_p_v_tx(self, density=True, light_weighted=False):
+        if light_weighted:
+            raise NotImplementedError
+        out = self._log_P_v_tx()
+        if density:
+            out = (out.T - np.log(self.cube.construct_volume_element("v"))).T
+        return out
+
+    # ------------------------------------------------------------------ the hot path
+    def evaluate_ybar(self, batch="none", device=0):
+        """Datacube of a Gaussian-LOSVD component (parametric.py:335-407).
+
+        Y-hat[k,x] = sum_t exp(-i mu_v w_k - (sig_v w_k)^2/2) sum_z P(t,x,z) S-hat[k,z,t];
+        one inverse real FFT per pixel; all on the device.  `batch` is accepted for
+        compatibility (the device path tiles pixels internally)."""
+        if batch not in ("none", "column", "spaxel"):
+            raise ValueError("Unknown option for batch")
+        plan = engine.get_plan(self.cube, device=device)
+        P_txz = self.get_p("txz", density=False)
+        self.ybar = plan.ybar_gaussian(P_txz, self.mu_v, self.sig_v)
+
+    # ------------------------------------------------------------------ analytic velocity moments
+    # E and central moments of v given (t,x) are those of the Gaussian law and do not depend on
+    # z or on the weighting; every other conditioning set averages them over P(t,x | given)
+    # (parametric.py:757-1228).
+    _V_WEIGHTS = {"tx": None, "txz": None, "x": "t_x", "t": "x_t", "": "tx", "tz": "x_tz",
+                  "xz": "t_xz", "z": "tx_z"}
+
+    def _tx_weights(self, given, light_weighted):
+        """P(t,x | given) as an array broadcastable to [t, x1, x2, (z)] and the axes to sum."""
+        key = self._V_WEIGHTS[given]
+        if key is None:
+            return 1.0, ()
+        P = self.get_p(key if given else "tx", light_weighted=light_weighted, density=False)
+        if given == "":
+            return P, (0, 1, 2)
+        if given == "x":
+            return P, (0,)                                  # [t, x1, x2]
+        if given == "t":
+            return np.moveaxis(P, -1, 0), (1, 2)            # [x1,x2,t] -> [t,x1,x2]
+        if given == "tz":
+            return np.moveaxis(P, -2, 0), (1, 2)            # [x1,x2,t,z] -> [t,x1,x2,z]
+        if given == "xz":
+            return P, (0,)                                  # [t,x1,x2,z]
+        if given == "z":
+            return P, (0, 1, 2)                             # [t,x1,x2,z]
+        raise ValueError(given)
+
+    def _gauss_central_moment(self, k):
+        if k % 2:
+            return np.zeros_like(self.sig_v)
+        return self.sig_v ** k * base._double_factorial_odd(k - 1)
+
+    @staticmethod
+    def _align_to_tx(given, arr):
+        """Reshape an array laid out like the conditioners `given` to broadcast over [t,x1,x2,(z)]."""
+        arr = np.asarray(arr)
+        if given in ("", "tx", "txz"):
+            return arr
+        if given in ("x", "xz"):
+            return arr[None]
+        if given == "t":
+            return arr[:, None, None]
+        if given == "tz":
+            return arr[:, None, None, :]
+        if given == "z":
+            return arr[None, None, None, :]
+        raise ValueError(given)
+
+    def _mu_v_aligned(self, given):
+        mu_v = np.asarray(self.mu_v)
+        if "z" not in given:
+            return mu_v
+        mu_v = mu_v[..., None]
+        if given == "txz":
+            mu_v = np.broadcast_to(mu_v, mu_v.shape[:-1] + (self.cube.ssps.delta_z.size,))
+        return mu_v
+
+    def _mean_v(self, given, light_weighted=False):
+        W, axes = self._tx_weights(given, light_weighted)
+        out = self._mu_v_aligned(given) * W
+        return np.sum(out, axes) if axes else out
+
+    def _noncentral_moment_v(self, given, j, mu, light_weighted=False):
+        """E[(v - mu)^j | given] = sum_k C(j,k) E_tx[(mu_v - mu)^(j-k) m_k(sig_v)]."""
+        W, axes = self._tx_weights(given, light_weighted)
+        delta = self._mu_v_aligned(given) - self._align_to_tx(given, mu)
+        total = 0.0
+        for k in range(j + 1):
+            mk = self._gauss_central_moment(k)
+            if "z" in given:
+                mk = mk[..., None]
+            total = total + special.comb(j, k) * delta ** (j - k) * mk
+        total = total * W
+        return np.sum(total, axes) if axes else total
+
+    def get_mean_v_tx(self, light_weighted=False):
+        return self.mu_v
+
+    def get_central_moment_v_tx(self, j, light_weighted=False):
+        return self._gauss_central_moment(j)
+
+
+def _install_v_moment_methods():
+    def mean_factory(given):
+        def get_mean(self, light_weighted=False):
+            return self._mean_v(given, light_weighted=light_weighted)
+        return get_mean
+
+    def moment_factory(given):
+        def get_noncentral_moment(self, j, mu, light_weighted=False):
+            return self._noncentral_moment_v(given, j, mu, light_weighted=light_weighted)
+        return get_noncentral_moment
+
+    for given in ("x", "t", "", "txz", "tz", "xz", "z"):
+        suffix = "v" + ("_" + given if given else "")
+        setattr(ParametricComponent, "get_mean_" + suffix, mean_factory(given))
+        setattr(ParametricComponent, "get_noncentral_moment_" + suffix, moment_factory(given))
+    setattr(ParametricComponent, "get_noncentral_moment_v_tx", moment_factory("tx"))
+
+
+def _install_marginals():
+    def factory(keep):
+        def _get_log_p(self, density=True, light_weighted=False):
+            return self._log_marginal(keep, density=density, light_weighted=light_weighted)
+        _get_log_p.__name__ = "_get_log_p_" + keep
+        return _get_log_p
+
+    for keep in base._MARGINALS:
+        setattr(ParametricComponent, "_get_log_p_" + keep, factory(keep))
+
+
+_install_marginals()
+_install_v_moment_methods()
