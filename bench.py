@@ -9,10 +9,11 @@ full MILES_BASTI grid (nt=53, nz=12), nv=101, lambda 4700-6500 A -> n_fft=4907; 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
     python bench.py --impl reference [...]                        # the reference's CPU algorithm
 
-N > 1 (torchrun, one rank per GPU): weak scaling - every rank evaluates its own 201x201-pixel
-row block of a (201*N)x201 mosaic (pixels are independent) and the blocks are
-gathered on rank 0 over NCCL inside the timed region; `--scaling strong` shards ONE 201x201
-cube by x1 rows instead.
+N > 1 (torchrun, one rank per GPU): strong scaling of the named configuration - the x1 rows of
+ONE 201x201-pixel cube are sharded over the ranks (pixels are independent),
+every rank evaluates its block in sub-blocks that are shipped to rank 0 over NCCL while the next
+one is computed, and rank 0 assembles [n_fft, nx1, nx2]; all inside the timed region.
+`--scaling weak` evaluates a (201*N)x201 mosaic instead (201 rows per rank).
 
 The JSON line printed by rank 0 follows the driver contract: `value` = device-resident
 throughput, `e2e` = the same call through the C ABI with pinned HOST buffers (H2D of the
@@ -47,7 +48,8 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=201, help="pixels per side of one cube")
     ap.add_argument("--nv", type=int, default=101)
     ap.add_argument("--lmd", type=float, nargs=2, default=(4700.0, 6500.0))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--gather-tiles", type=int, default=4, help="sub-blocks per rank for the overlapped gather")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -72,7 +74,7 @@ def build_cube(args, nx1=None):
 def workload_config(args, cube):
     nz, nt = cube.ssps.par_dims
     return {
-        "workload": f"C4 synthetic density cube {args.nx}x{args.nx} px per GPU-block, full MILES_BASTI grid "
+        "workload": f"C4 synthetic density cube {args.nx}x{args.nx} px, full MILES_BASTI grid "
                     f"nt={nt} nz={nz}, nv={args.nv}, lmd {args.lmd[0]:.0f}-{args.lmd[1]:.0f} A, "
                     f"n_fft={cube.ssps.n_fft} (path B: Component.evaluate_ybar on log_p_tvxz)",
         "nx1": args.nx, "nx2": args.nx, "nv": args.nv, "nt": int(nt), "nz": int(nz),
@@ -286,14 +288,19 @@ def run_b200(args):
     nv, nx, n_fft = args.nv, args.nx, int(cube.ssps.n_fft)
     plan = engine.Plan(cube, device=local)
 
-    # ---- this rank's share
-    if args.scaling == "weak" or world == 1:
-        rows = nx                       # one whole nx x nx block per rank
-    else:
-        r0 = rank * nx // world
-        rows = (rank + 1) * nx // world - r0
+    # ---- this rank's share of the pixels
+    from popkinmocks_b200 import sharding
+    if world == 1:
+        nx1_total, r0, r1 = nx, 0, nx
+    elif args.scaling == "strong":            # ONE nx x nx cube, x1 rows sharded over the ranks
+        nx1_total = nx
+        r0, r1 = sharding.my_rows(nx, world, rank)
+    else:                                     # weak: a (world*nx) x nx mosaic, nx rows per rank
+        nx1_total = nx * world
+        r0, r1 = rank * nx, (rank + 1) * nx
+    rows = r1 - r0
     npix = rows * nx
-    total_pix = npix if world == 1 else (nx * nx * world if args.scaling == "weak" else nx * nx)
+    total_pix = nx1_total * nx
     voxels_per_step = total_pix * n_fft
 
     # ---- synthetic density (log p, as Component(cube, log_p_tvxz) holds it), generated on device
@@ -302,33 +309,29 @@ def run_b200(args):
     for t in range(nt):                 # slab-wise to keep the temporary small
         logp[t] = torch.rand((nv, rows, nx, nz), dtype=torch.float64, device=dev, generator=gen)
     dV = float(np.mean(cube.ssps.delta_t) * np.mean(cube.ssps.delta_z) * cube.dx * cube.dy * cube.ssps.dv)
-    logp.mul_(1.0 / (0.5 * logp.numel() * dV)).clamp_(min=1e-300).log_()
+    logp.mul_(1.0 / (0.5 * nt * nv * total_pix * nz * dV)).clamp_(min=1e-300).log_()
 
-    out = torch.empty((n_fft, rows, nx), dtype=torch.float64, device=dev)
-    gathered = None
-    pm = None
-    if world > 1:
-        pm = torch.empty((npix, n_fft), dtype=torch.float64, device=dev)
-        if rank == 0:
-            gathered = torch.empty((total_pix, n_fft), dtype=torch.float64, device=dev)
-            full = torch.empty((n_fft, total_pix), dtype=torch.float64, device=dev)
-        counts = [None] * world
-        dist.all_gather_object(counts, npix)
+    if world == 1:
+        out = torch.empty((n_fft, rows, nx), dtype=torch.float64, device=dev)
+        tg = None
+    else:
+        tg = sharding.TileGather(nx1_total, nx, n_fft, dev, dist=dist, ntile=args.gather_tiles)
+        out = torch.empty((n_fft, nx1_total, nx), dtype=torch.float64, device=dev) if rank == 0 else None
 
     def step():
         if world == 1:
             plan.ybar_density(logp, is_log=True, out=out)
             return
-        # rank-local rows -> pixel-major tile -> gather on rank 0 -> one transpose to [n_fft, x1, x2]
-        plan.ybar_density(logp, is_log=True, out=pm, layout=_lib.LAYOUT_PIXEL_MAJOR)
+        # sub-blocks of this rank's rows -> spaxel-major tiles, each shipped to rank 0 over NCCL
+        # while the next one is computed; rank 0 transposes once to [n_fft, x1, x2]
+        for t, (a, b, view) in enumerate(tg.my_tiles()):
+            if b > a:
+                plan.ybar_density(logp, is_log=True, rows=(a, b), out=view, layout=_lib.LAYOUT_PIXEL_MAJOR)
+            tg.post(t)
+        full = tg.finish()
         if rank == 0:
-            offs = np.concatenate(([0], np.cumsum(counts)))
-            parts = [gathered[offs[i]:offs[i + 1]] for i in range(world)]
-            dist.gather(pm, parts, dst=0)
-            _lib.check(_lib.load().pkm_transpose_to_cube(_lib.ptr(gathered), total_pix, n_fft,
-                                                         _lib.ptr(full), local, None))
-        else:
-            dist.gather(pm, None, dst=0)
+            _lib.check(_lib.load().pkm_transpose_to_cube(_lib.ptr(full), total_pix, n_fft,
+                                                         _lib.ptr(out), local, None))
 
     def barrier():
         torch.cuda.synchronize()
@@ -368,13 +371,20 @@ def run_b200(args):
     # ---- e2e: same call through the C ABI with pinned host buffers
     e2e = None
     windows = [(w0, w1)]
-    if not args.no_e2e:
+    host_bytes = world * (logp.numel() * 8 + n_fft * rows * nx * 8)
+    try:
+        import psutil
+        ram = psutil.virtual_memory().total
+    except Exception:  # noqa: BLE001
+        ram = 1 << 40
+    if not args.no_e2e and host_bytes > 0.6 * ram:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": f"skipped: pinned host buffers of all ranks ({host_bytes / 1e9:.0f} GB) exceed 60% of host RAM"}
+    elif not args.no_e2e:
         h_in = torch.empty(logp.shape, dtype=torch.float64, pin_memory=True)
         h_in.copy_(logp)
         h_out = torch.empty((n_fft, rows, nx), dtype=torch.float64, pin_memory=True)
         np_in, np_out = h_in.numpy(), h_out.numpy()
-        if world > 1:
-            del pm
         del logp
         torch.cuda.empty_cache()
 
@@ -406,7 +416,10 @@ def run_b200(args):
     if rank == 0:
         # ---- roofline of the dominant kernel (live CUDA-event times of this run)
         nfo, ntz, nfi = n_fft // 2 + 1, nt * nz, nv // 2 + 1
-        flops_px = {"contract": 24.0 * nfo * ntz, "coeff": 2.0 * nfi * nv * ntz}
+        # executed FP64 work per pixel: contraction = per (k, t, z) 6 FMA for the 3-weight spline
+        # form + 4 FMA complex MAC (20 flops) + 6 DADD per (t,z) shared by 10 frequencies;
+        # coefficient GEMM = nfi x nv real MACs per (t, z) column
+        flops_px = {"contract": 20.6 * nfo * ntz, "coeff": 2.0 * nfi * nv * ntz}
         tot_k = sum(m for m, _ in ktimes.values()) or 1.0
         kern = {k: {"ms_per_step": m / args.steps, "launches_per_step": c / args.steps, "share": m / tot_k}
                 for k, (m, c) in ktimes.items() if c}
@@ -432,7 +445,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, cube),
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof,

@@ -55,3 +55,86 @@ def pixel_major_to_cube(full, nx1, nx2):
     if hasattr(full, "numpy") or type(full).__module__.startswith("torch"):
         return full.t().contiguous().reshape(full.shape[1], nx1, nx2)
     return np.ascontiguousarray(full.T).reshape(full.shape[1], nx1, nx2)
+
+
+class TileGather:
+    """Gather of spaxel-major cube tiles onto rank 0, overlapped with the computation.
+
+    Each rank splits its x1-row block into `ntile` sub-blocks.  As soon as a sub-block has been
+    evaluated (`post`), it is sent to rank 0 on a side stream while the next one is computed;
+    rank 0 evaluates its own sub-blocks straight into the gathered buffer and receives the
+    others in the background.  Sends and receives of one round are issued as one NCCL group.
+    Works with gloo/CPU tensors too (no streams), which is how the CPU tests drive it.
+    """
+
+    def __init__(self, nx1, nx2, n, device, dist=None, ntile=4, dtype=None):
+        import torch
+        self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.nx1, self.nx2, self.n = nx1, nx2, n
+        self.device = torch.device(device)
+        dtype = dtype or torch.float64
+        self.bounds = row_partition(nx1, self.world)
+        self.ntile = max(1, int(ntile))
+        # global row boundaries of every rank's sub-blocks
+        self.tiles = []
+        for r in range(self.world):
+            r0, r1 = self.bounds[r], self.bounds[r + 1]
+            sub = row_partition(r1 - r0, self.ntile)
+            self.tiles.append([(r0 + sub[t], r0 + sub[t + 1]) for t in range(self.ntile)])
+        r0, r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        if self.rank == 0:
+            self.full = torch.empty((nx1 * nx2, n), dtype=dtype, device=self.device)
+            self.local = self.full[r0 * nx2:r1 * nx2]
+        else:
+            self.full = None
+            self.local = torch.empty(((r1 - r0) * nx2, n), dtype=dtype, device=self.device)
+        self.cuda = self.device.type == "cuda"
+        self.comm = torch.cuda.Stream(device=self.device) if (self.cuda and self.dist) else None
+        self.pending = []
+
+    def my_tiles(self):
+        """[(local_row_begin, local_row_end, out_view)] for this rank, in evaluation order."""
+        r0 = self.bounds[self.rank]
+        out = []
+        for a, b in self.tiles[self.rank]:
+            out.append((a - r0, b - r0, self.local[(a - r0) * self.nx2:(b - r0) * self.nx2]))
+        return out
+
+    def post(self, t):
+        """Sub-block `t` of this rank has been enqueued on the current stream: ship it."""
+        if self.dist is None:
+            return
+        import torch
+        ops = []
+        if self.rank == 0:
+            for r in range(1, self.world):
+                a, b = self.tiles[r][t]
+                if b > a:
+                    ops.append(self.dist.P2POp(self.dist.irecv, self.full[a * self.nx2:b * self.nx2], r))
+        else:
+            a, b = self.tiles[self.rank][t]
+            if b > a:
+                r0 = self.bounds[self.rank]
+                ops.append(self.dist.P2POp(self.dist.isend, self.local[(a - r0) * self.nx2:(b - r0) * self.nx2], 0))
+        if not ops:
+            return
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                self.pending += self.dist.batch_isend_irecv(ops)
+        else:
+            self.pending += self.dist.batch_isend_irecv(ops)
+
+    def finish(self):
+        """Wait for the transfers; returns the gathered [nx1*nx2, n] buffer on rank 0, else None."""
+        import torch
+        for req in self.pending:
+            req.wait()
+        self.pending = []
+        if self.cuda and self.comm is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+        return self.full

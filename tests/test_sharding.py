@@ -46,13 +46,24 @@ r0, r1 = sharding.my_rows(nx1, world, rank)
 pix = torch.arange(r0 * nx2, r1 * nx2, dtype=torch.float64)[:, None]
 tile = pix * 100.0 + torch.arange(n, dtype=torch.float64)[None, :]
 full = sharding.gather_pixel_major(tile, nx1, nx2, dist=dist, dst=0)
+want = (np.arange(nx1 * nx2)[None, :] * 100.0 + np.arange(n)[:, None]).reshape(n, nx1, nx2)
 if rank == 0:
     cube = sharding.pixel_major_to_cube(full, nx1, nx2).numpy()
-    want = (np.arange(nx1 * nx2)[None, :] * 100.0 + np.arange(n)[:, None]).reshape(n, nx1, nx2)
     assert np.array_equal(cube, want), "gathered cube is wrong"
     print("GATHER_OK")
 else:
     assert full is None
+# the overlapped tile gather used by bench.py (here without CUDA streams)
+tg = sharding.TileGather(nx1, nx2, n, "cpu", dist=dist, ntile=2)
+for t, (a, b, out) in enumerate(tg.my_tiles()):
+    g0 = (r0 + a) * nx2
+    out.copy_(torch.arange(g0, g0 + (b - a) * nx2, dtype=torch.float64)[:, None] * 100.0
+              + torch.arange(n, dtype=torch.float64)[None, :])
+    tg.post(t)
+full = tg.finish()
+if rank == 0:
+    assert np.array_equal(sharding.pixel_major_to_cube(full, nx1, nx2).numpy(), want)
+    print("TILE_GATHER_OK")
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -69,4 +80,4 @@ def test_two_rank_gloo_gather(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "GATHER_OK" in out.stdout
+    assert "GATHER_OK" in out.stdout and "TILE_GATHER_OK" in out.stdout
