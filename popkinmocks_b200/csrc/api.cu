@@ -127,6 +127,11 @@ static void plan_free(pkm_plan* pl) {
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz);
   collect_timers(pl);
+  for (int i = 0; i < 2; ++i)
+    for (cudaEvent_t e : {pl->ev_in[i], pl->ev_done[i], pl->ev_out[i], pl->ev_ready[i]})
+      if (e) cudaEventDestroy(e);
+  if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+  if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
   pl->coef.release(); pl->yhat.release(); pl->ypx.release(); pl->misc.release(); pl->small.release();
   for (int i = 0; i < 2; ++i) {
     pl->stage_in[i].release();
@@ -350,6 +355,19 @@ void emit_tile(pkm_plan* pl, const OutSpec& o, const double* ypx, int64_t pix_of
 
 }  // namespace
 
+// streams / events of the host-buffer pipeline (created on first use)
+static void pipe_init(pkm_plan* pl) {
+  if (pl->s_copy) return;
+  PKM_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+  PKM_CUDA(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+    PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_done[i], cudaEventDisableTiming));
+    PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
+    PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_ready[i], cudaEventDisableTiming));
+  }
+}
+
 // ----------------------------------------------------------------------------
 // density path
 // ----------------------------------------------------------------------------
@@ -375,39 +393,79 @@ extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is
     if (npix == 0) return;
     const int pxb = coeff_choose_pxb(pl);
 
+    // Host buffers are pipelined: H2D of tile i+1 (copy stream) and D2H of tile i-1 (output
+    // stream) overlap the kernels of tile i (caller's stream); two staging slots each way.
     size_t per_px = sizeof(double2) * (size_t)pl->ntz * pl->nfi + sizeof(double2) * pl->nfo + sizeof(double) * n;
-    if (in_host) per_px += sizeof(double) * (size_t)nt * nv * nz;
-    if (out_host && out_layout == PKM_LAYOUT_CUBE) per_px += sizeof(double) * n;
+    if (in_host) per_px += 2 * sizeof(double) * (size_t)nt * nv * nz;
+    if (out_host) per_px += 2 * sizeof(double) * n;
     int tile = pixel_tile(pl, npix, per_px);
+    if (in_host || out_host) tile = std::min<int64_t>(tile, ((npix + 7) / 8 + 31) & ~int64_t(31));
     tile = std::max((tile / 32) * 32, 32);  // the coefficient layout groups pixels by 32
     (void)pxb;
 
     pl->coef.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
     pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
     pl->ypx.reserve(sizeof(double) * (size_t)n * tile);
+    if (in_host || out_host) pipe_init(pl);
+    cudaStream_t s_in = pl->s_copy, s_out = pl->s_comp;
+    const bool pm = out_layout == PKM_LAYOUT_PIXEL_MAJOR;
     OutSpec o{ybar_out, out_host, out_layout, npix, n};
 
-    for (int64_t p0 = 0; p0 < npix; p0 += tile) {
+    int64_t it = 0;
+    for (int64_t p0 = 0; p0 < npix; p0 += tile, ++it) {
       const int np = (int)std::min<int64_t>(tile, npix - p0);
+      const int slot = (int)(it & 1);
       const double* src = dens;
       int64_t src_npix = npix_total, src_pix0 = pix_begin + p0;
       if (in_host) {
-        pl->stage_in[0].reserve(sizeof(double) * (size_t)nt * nv * nz * np);
-        PKM_CUDA(cudaMemcpy2DAsync(pl->stage_in[0].p, sizeof(double) * (size_t)np * nz,
+        pl->stage_in[slot].reserve(sizeof(double) * (size_t)nt * nv * nz * tile);
+        PKM_CUDA(cudaStreamWaitEvent(s_in, pl->ev_done[slot], 0));   // kernel 1 of tile it-2 is done with it
+        PKM_CUDA(cudaMemcpy2DAsync(pl->stage_in[slot].p, sizeof(double) * (size_t)np * nz,
                                    dens + (size_t)(pix_begin + p0) * nz,
                                    sizeof(double) * (size_t)npix_total * nz,
                                    sizeof(double) * (size_t)np * nz, (size_t)nt * nv,
-                                   cudaMemcpyHostToDevice, st));
-        src = pl->stage_in[0].as<double>();
+                                   cudaMemcpyHostToDevice, s_in));
+        PKM_CUDA(cudaEventRecord(pl->ev_in[slot], s_in));
+        PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_in[slot], 0));
+        src = pl->stage_in[slot].as<double>();
         src_npix = np;
         src_pix0 = 0;
       }
       launch_coeff(pl, src, is_log, src_npix, src_pix0, np, tile, pl->coef.as<double2>(), st);
+      if (in_host) PKM_CUDA(cudaEventRecord(pl->ev_done[slot], st));
       launch_contract(pl, pl->coef.as<double2>(), np, tile, pl->yhat.as<double2>(), st);
-      launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
-      emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);
+      if (!out_host) {
+        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
+        emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);
+        continue;
+      }
+      // host output: the staging slot must have been drained by the D2H of tile it-2
+      pl->stage_out[slot].reserve(sizeof(double) * (size_t)n * tile);
+      double* stage = pl->stage_out[slot].as<double>();
+      PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_out[slot], 0));
+      if (pm) {
+        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, stage, st);
+      } else {
+        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
+        KernelTimer tm(pl, PKM_K_TRANSPOSE, st);
+        launch_transpose(pl->ypx.as<double>(), np, n, stage, np, 0, st);
+        pl->launches++;
+      }
+      PKM_CUDA(cudaEventRecord(pl->ev_ready[slot], st));
+      PKM_CUDA(cudaStreamWaitEvent(s_out, pl->ev_ready[slot], 0));
+      if (pm)
+        PKM_CUDA(cudaMemcpyAsync(ybar_out + (size_t)p0 * n, stage, sizeof(double) * (size_t)n * np,
+                                 cudaMemcpyDeviceToHost, s_out));
+      else
+        PKM_CUDA(cudaMemcpy2DAsync(ybar_out + p0, sizeof(double) * npix, stage, sizeof(double) * np,
+                                   sizeof(double) * np, n, cudaMemcpyDeviceToHost, s_out));
+      PKM_CUDA(cudaEventRecord(pl->ev_out[slot], s_out));
     }
-    if (in_host || out_host) PKM_CUDA(cudaStreamSynchronize(st));
+    if (in_host || out_host) {
+      PKM_CUDA(cudaStreamSynchronize(st));
+      PKM_CUDA(cudaStreamSynchronize(s_out));
+      PKM_CUDA(cudaStreamSynchronize(s_in));
+    }
   });
 }
 

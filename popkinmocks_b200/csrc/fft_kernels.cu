@@ -16,6 +16,8 @@
 // Chirp phases are reduced exactly (j^2 mod 2n in integers) on the host.
 #include "pkm_internal.h"
 
+constexpr int CZT_THREADS = 1024;  // one CTA per SM holds the whole transform in smem: hide latency with warps
+
 namespace {
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -101,7 +103,7 @@ k_filter_spectrum(const double2* __restrict__ bfilt, double2* __restrict__ Bhat,
   for (int i = threadIdx.x; i < M; i += blockDim.x) Bhat[i] = s[i];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CZT_THREADS)
 k_irfft_czt(const double2* __restrict__ yhat, long long npix, int n, int nfo, int M, int logM,
             double scale, const double2* __restrict__ chi, const double* __restrict__ alpha,
             const double2* __restrict__ tw, const double2* __restrict__ Bhat,
@@ -228,7 +230,7 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
     scratch = pl->misc.as<double2>();
   }
   KernelTimer tm(pl, PKM_K_IRFFT, st);
-  k_irfft_czt<<<grid, 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_chi, pl->d_alpha,
+  k_irfft_czt<<<grid, c.M >= 4096 ? CZT_THREADS : 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_chi, pl->d_alpha,
                                        pl->d_twiddle, pl->d_Bhat, out, scratch);
   PKM_CUDA(cudaGetLastError());
   pl->launches++;

@@ -146,9 +146,11 @@ struct pkm_plan {
 
   // workspace
   DevBuf coef, yhat, ypx, stage_in[2], stage_out[2], misc, small;
+  // host-buffer pipeline: s_copy = H2D stream, s_comp = D2H stream; per staging slot:
+  // ev_in (H2D landed), ev_done (kernel 1 consumed it), ev_ready (output staged), ev_out (D2H done)
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
-              ev_out[2] = {nullptr, nullptr};
+              ev_out[2] = {nullptr, nullptr}, ev_ready[2] = {nullptr, nullptr};
 };
 
 // ----------------------------------------------------------------------------
