@@ -78,6 +78,7 @@ struct K1Geom {
   long long npix_total, pix0;
   int npix_tile, xpad, nv, nz, nfi, ne, no, pxb, nt, is_log, v0;
   int use_tma;  // 0 = plain loads, 1 = one 1-D bulk copy per velocity row, 2 = one 2-D tensor copy per tile
+  int ngroup;   // independent warp groups per CTA (1 or 2), each running its own tile pipeline
 };
 
 // velocity row holding rolled position +u / -u  (np.roll(p, nv - v0), base.py:843)
@@ -90,32 +91,48 @@ __device__ __forceinline__ int row_minus(int u, int v0, int nv) {
   return r < 0 ? r + nv : r;
 }
 
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores.  Lane l holds A[l/4][l%4], B[l%4][l/4]
+// and D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 template <int TM>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tmap, K1Geom g,
         const double* __restrict__ CRt, const double* __restrict__ CIt, double2* __restrict__ cT) {
   extern __shared__ __align__(128) double smem[];
-  constexpr int TMP = TM + (TM & 1);  // even row padding -> 16-byte aligned double2 loads
-  constexpr int NFIP = 8 * TMP;
+  constexpr int MB = TM;              // 8-row blocks of the output (MB * 8 >= nfi)
   const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, pxb = g.pxb;
+  const int nks = (ne + 3) >> 2;      // k-steps of 4 rolled velocities (real part; imaginary has no <= ne)
+  const int frag_elems = nks * MB * 32;  // one A operand in DMMA fragment order
   const int NC = pxb * nz;
   const int NCp = (NC + 15) & ~15;
   // one slab buffer holds the [nv][NCp] density slab and later the [nz][nfi][pxb] complex staging
   const int buf_elems = (max(nv * NCp, 2 * nz * nfi * pxb) + 15) & ~15;
-  double* As_r = smem;                                   // [ne][NFIP]
-  double* As_i = As_r + (size_t)ne * NFIP;               // [max(no,1)][NFIP]
-  double* Bbuf = As_i + (size_t)max(no, 1) * NFIP;       // [2][buf_elems]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Bbuf + 2 * (size_t)buf_elems);
+  double* As_r = smem;                                   // [nks][MB][32]  A fragments, real part
+  double* As_i = As_r + frag_elems;                      // [nks][MB][32]  imaginary part
+  double* Bbuf0 = As_i + frag_elems;                     // [ngroup][2][buf_elems]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Bbuf0 + 2 * (size_t)g.ngroup * buf_elems);
   const int v0 = g.v0;
   const int xmask = pxb - 1;                             // staging swizzle (pxb is a power of two)
-  const int tid = threadIdx.x;
+  // The CTA is split into `ngroup` warp groups that run the tile loop independently (own slab
+  // buffers, own mbarriers, own named barrier) and share only the A matrices: while one group
+  // is in its GEMM phase the other folds / stages / stores, which keeps the FP64 pipe busy.
+  const int GT = K1_THREADS / g.ngroup;                  // threads per group
+  const int grp = threadIdx.x / GT;
+  const int tid = threadIdx.x - grp * GT;                // thread index within the group
   const int warp = tid >> 5, lane = tid & 31;
-  const int rg = lane & 7, cg = lane >> 3;
+  double* Bbuf = Bbuf0 + (size_t)grp * 2 * buf_elems;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(GT) : "memory"); };
 
-  for (int i = tid; i < ne * NFIP; i += K1_THREADS) As_r[i] = CRt[i];
-  for (int i = tid; i < no * NFIP; i += K1_THREADS) As_i[i] = CIt[i];
-  for (int i = tid; i < 2 * buf_elems; i += K1_THREADS) Bbuf[i] = 0.0;
-  const unsigned bar0 = smem_u32(bars);
+  for (int i = threadIdx.x; i < frag_elems; i += K1_THREADS) {
+    As_r[i] = CRt[i];
+    As_i[i] = CIt[i];
+  }
+  for (int i = threadIdx.x; i < 2 * g.ngroup * buf_elems; i += K1_THREADS) Bbuf0[i] = 0.0;
+  const unsigned bar0 = smem_u32(bars) + 16u * grp;
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -157,7 +174,7 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
           bulk_g2s(smem_u32(dst + (size_t)v * NCp), src + (size_t)v * vstride, row_bytes, bar);
       }
     } else {
-      for (int i = tid; i < nv * NCp; i += K1_THREADS) {
+      for (int i = tid; i < nv * NCp; i += GT) {
         const int v = i / NCp, col = i - v * NCp;
         dst[i] = col < ncol_valid ? __ldg(src + (size_t)v * vstride + col) : 0.0;
       }
@@ -167,23 +184,24 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
 
   unsigned phases = 0u;      // bit b = parity the next TMA completion on buffer b will have
   bool cur_tma = false, next_tma = false;
-  long long tile = blockIdx.x;
+  const long long tstep = (long long)gridDim.x * g.ngroup;
+  long long tile = (long long)blockIdx.x * g.ngroup + grp;
   if (tile < ntile) cur_tma = load_tile(tile, 0);
-  for (int it = 0; tile < ntile; tile += gridDim.x, ++it, cur_tma = next_tma) {
+  for (int it = 0; tile < ntile; tile += tstep, ++it, cur_tma = next_tma) {
     const int b = it & 1;
     // the other buffer was released by the barrier that ended the previous iteration
-    if (tile + gridDim.x < ntile) next_tma = load_tile(tile + gridDim.x, b ^ 1);
+    if (tile + tstep < ntile) next_tma = load_tile(tile + tstep, b ^ 1);
     if (cur_tma) {
       mbar_wait(bar0 + 8u * b, (phases >> b) & 1u);
       phases ^= 1u << b;
     } else {
-      __syncthreads();
+      group_sync();
     }
     const int t = (int)(tile / nxb);
     const int xb = (int)(tile - (long long)t * nxb);
     double* Bs = Bbuf + (size_t)b * buf_elems;
     // phase 1 (self-paired rows carry weight 1/2 in CRt, so e = a + b unconditionally)
-    for (int i = tid; i < ne * (NCp >> 1); i += K1_THREADS) {
+    for (int i = tid; i < ne * (NCp >> 1); i += GT) {
       const int u = i / (NCp >> 1), c2 = i - u * (NCp >> 1);
       const int rp = row_plus(u, v0, nv), rm = row_minus(u, v0, nv);
       double2* pa = reinterpret_cast<double2*>(Bs + (size_t)rp * NCp) + c2;
@@ -196,65 +214,65 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
       *pa = make_double2(a.x + bb.x, a.y + bb.y);
       if (rp != rm) *pb = make_double2(a.x - bb.x, a.y - bb.y);
     }
-    __syncthreads();
-    // phase 2
+    group_sync();
+    // phase 2: FP64 tensor-core GEMM (DMMA m8n8k4).  One work item per warp = (16-column chunk,
+    // real | imaginary part): MB x 2 accumulator tiles of 8x8; per k-step of 4 rolled velocities
+    // a lane loads MB A-fragment doubles (pre-arranged, conflict-free) and 2 B-fragment doubles
+    // from the folded slab and issues 2*MB DMMAs - 0.6 shared-memory bytes per FMA instead of
+    // the 3.4 a register-tiled FMA loop needs (which made the phase shared-memory bound).
     // (the host picks PXB so that there is at most one item per warp: accumulators stay in
     // registers across the barrier that frees the slab for staging)
-    double acc[TM][4];
+    double acc[MB][2][2];
     const int item = warp;
     const int part = item & 1, chunk = item >> 1;
+    const int fr = lane >> 2, fk = lane & 3;      // fragment row / k index of this lane
     if (item < nitem) {
-      const double* A = (part ? As_i : As_r) + rg * 2;
+      const double* A = (part ? As_i : As_r) + lane;
       const int K = part ? no : ne;
-      const int col0 = chunk * 16 + cg * 4;
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 2
-      for (int u = 0; u < K; ++u) {
-        // E[u] lives in row +u, O[u] (u >= 1) in row -u of the folded slab
+      for (int mb = 0; mb < MB; ++mb) {
+        acc[mb][0][0] = acc[mb][0][1] = 0.0;
+        acc[mb][1][0] = acc[mb][1][1] = 0.0;
+      }
+      const double* Bcol = Bs + chunk * 16 + fr;
+      for (int ks = 0; ks < nks; ++ks) {
+        // E[u] lives in row +u, O[u] (u >= 1) in row -u of the folded slab; u >= K has zero A
+        const int u = min(ks * 4 + fk, K - 1);
         const int row = part ? row_minus(u + 1, v0, nv) : row_plus(u, v0, nv);
-        const double2* bp = reinterpret_cast<const double2*>(Bs + (size_t)row * NCp + col0);
-        const double2 b01 = bp[0], b23 = bp[1];
-        const double2* ap = reinterpret_cast<const double2*>(A + (size_t)u * NFIP);
-        double a[TMP];
+        const double b0 = Bcol[(size_t)row * NCp];
+        const double b1 = Bcol[(size_t)row * NCp + 8];
+        double a[MB];
 #pragma unroll
-        for (int i = 0; i < TMP / 2; ++i) {
-          double2 v2 = ap[i * 8];  // rows (2i, 2i+1) of the 8 row groups are 128 contiguous bytes
-          a[2 * i] = v2.x;
-          a[2 * i + 1] = v2.y;
-        }
+        for (int mb = 0; mb < MB; ++mb) a[mb] = A[(ks * MB + mb) * 32];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          acc[i][0] = fma(a[i], b01.x, acc[i][0]);
-          acc[i][1] = fma(a[i], b01.y, acc[i][1]);
-          acc[i][2] = fma(a[i], b23.x, acc[i][2]);
-          acc[i][3] = fma(a[i], b23.y, acc[i][3]);
+        for (int mb = 0; mb < MB; ++mb) {
+          dmma_m8n8k4(acc[mb][0][0], acc[mb][0][1], a[mb], b0);
+          dmma_m8n8k4(acc[mb][1][0], acc[mb][1][1], a[mb], b1);
         }
       }
     }
-    __syncthreads();  // every warp is done reading the slab: reuse it as the staging area
-    // phase 3: Cs[z][m][x] complex
+    group_sync();  // every warp of the group is done reading the slab: reuse it as the staging area
+    // phase 3: Cs[z][m][x] complex; lane holds C[row fr][cols 2 fk, 2 fk + 1] of every 8x8 tile
     double* Cs = Bs;
     if (item < nitem) {
-      const int col0 = chunk * 16 + cg * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = col0 + j;
-        if (col < NC) {
-          const int x = col / nz, z = col - x * nz;
+      for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-          for (int i = 0; i < TM; ++i) {
-            const int m = rg * TM + i;
-            if (m < nfi) Cs[(((size_t)z * nfi + m) * pxb + (x ^ ((m + (z >> 2)) & xmask))) * 2 + part] = acc[i][j];
+        for (int e = 0; e < 2; ++e) {
+          const int col = chunk * 16 + nb * 8 + 2 * fk + e;
+          if (col < NC) {
+            const int x = col / nz, z = col - x * nz;
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const int m = mb * 8 + fr;
+              if (m < nfi) Cs[(((size_t)z * nfi + m) * pxb + (x ^ ((m + (z >> 2)) & xmask))) * 2 + part] = acc[mb][nb][e];
+            }
           }
         }
-      }
     }
-    __syncthreads();
+    group_sync();
     // phase 4: cT[x/32][t*nz + z][m][x%32]
-    for (int i = tid; i < nz * nfi * pxb; i += K1_THREADS) {
+    for (int i = tid; i < nz * nfi * pxb; i += GT) {
       const int zm = i / pxb, xs = i - zm * pxb;
       const int z = zm / nfi, m = zm - z * nfi;
       const int x = xs ^ ((m + (z >> 2)) & xmask);
@@ -264,33 +282,31 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
     }
     // order this tile's generic-proxy accesses to the buffer before the TMA refill of it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    group_sync();
   }
 }
 
-// The GEMM phase reads rows (2*ip, 2*ip+1) of row group rg as the double2 at
-// As[u][ip*16 + rg*2]; the host stores row m = rg*TM + 2*ip + e at As[u][ip*16 + rg*2 + e].
-static void upload_padded_transposed(const std::vector<double>& C, int nfi, int K, int TM,
-                                     double** d_out) {
-  const int TMP = TM + (TM & 1), NFIP = 8 * TMP;
-  std::vector<double> h((size_t)std::max(K, 1) * NFIP, 0.0);
-  for (int u = 0; u < K; ++u)
-    for (int m = 0; m < nfi; ++m) {
-      int rg = m / TM, i = m % TM;
-      h[(size_t)u * NFIP + (i / 2) * 16 + rg * 2 + (i & 1)] = C[(size_t)m * K + u];
-    }
+// A operand in DMMA fragment order: element [ks][mb][lane] = C[m = mb*8 + lane/4][u = ks*4 + lane%4]
+// (zero outside the matrix), so a warp's fragment load is one contiguous 256-byte read.
+static void upload_fragments(const std::vector<double>& C, int nfi, int K, int MB, int nks, double** d_out) {
+  std::vector<double> h((size_t)nks * MB * 32, 0.0);
+  for (int ks = 0; ks < nks; ++ks)
+    for (int mb = 0; mb < MB; ++mb)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int m = mb * 8 + lane / 4, u = ks * 4 + lane % 4;
+        if (m < nfi && u < K) h[((size_t)ks * MB + mb) * 32 + lane] = C[(size_t)m * K + u];
+      }
   PKM_CUDA(cudaMalloc(d_out, h.size() * sizeof(double)));
   PKM_CUDA(cudaMemcpy(*d_out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
 }
 
 void density_tables_upload(pkm_plan* pl) {
-  // rows per thread: 8 row groups must cover nfi rows
-  pl->TM = (pl->nfi + 7) / 8;
+  pl->TM = (pl->nfi + 7) / 8;   // number of 8-row blocks
   PKM_REQUIRE(pl->TM <= 8, "nv=%d too large for the coefficient kernel (nfi=%d > 64)", pl->d.nv, pl->nfi);
-  const int TMP = pl->TM + (pl->TM & 1);
-  pl->nfiP = 8 * TMP;
-  upload_padded_transposed(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, &pl->d_CRt);
-  upload_padded_transposed(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, &pl->d_CIt);
+  const int nks = (pl->fold.ne + 3) / 4;
+  pl->nfiP = nks * pl->TM * 32;  // doubles per A operand
+  upload_fragments(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, nks, &pl->d_CRt);
+  upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt);
 }
 
 // [rows][cols] float64 matrix view of the density, box = box_rows x box_cols (tiled, no swizzle)
@@ -319,33 +335,42 @@ static bool encode_density_map(CUtensorMap* map, const double* base, int64_t col
   return r == CUDA_SUCCESS;
 }
 
-static size_t coeff_smem_bytes(const pkm_plan* pl, int pxb) {
+static size_t coeff_smem_bytes(const pkm_plan* pl, int pxb, int ngroup) {
   const int NC = pxb * pl->d.nz, NCp = (NC + 15) & ~15;
   const size_t buf_elems = (std::max<size_t>((size_t)pl->d.nv * NCp, (size_t)2 * pl->d.nz * pl->nfi * pxb) + 15) & ~size_t(15);
-  size_t dbl = (size_t)(pl->fold.ne + std::max(pl->fold.no, 1)) * pl->nfiP + 2 * buf_elems;
-  return dbl * sizeof(double) + 2 * sizeof(unsigned long long);
+  size_t dbl = (size_t)2 * pl->nfiP + 2 * ngroup * buf_elems;
+  return dbl * sizeof(double) + 2 * ngroup * sizeof(unsigned long long);
 }
 
-// pixels per tile: largest of {16, 8, 4, 2} whose two slab buffers fit shared memory and whose
-// GEMM items (2 per 16 columns) do not exceed one per warp
-int coeff_choose_pxb(const pkm_plan* pl) {
-  for (int pxb : {16, 8, 4, 2}) {
-    const int NCp = (pxb * pl->d.nz + 15) & ~15;
-    if ((NCp >> 4) * 2 > K1_WARPS) continue;
-    if (coeff_smem_bytes(pl, pxb) <= 227 * 1024) return pxb;
+// Tile shape: prefer two warp groups per CTA (6 warps each, pipelines overlap), then one group
+// of 12 warps; within each, the largest pixel block of {16, 8, 4, 2} whose slab buffers fit
+// shared memory and whose GEMM items (2 per 16 columns) do not exceed one per warp of a group.
+int coeff_choose_pxb(const pkm_plan* pl, int* ngroup_out) {
+  const char* force = getenv("PKM_COEFF_GROUPS");
+  for (int ngroup : {2, 1}) {
+    if (force && atoi(force) != ngroup) continue;
+    for (int pxb : {16, 8, 4, 2}) {
+      const int NCp = (pxb * pl->d.nz + 15) & ~15;
+      if ((NCp >> 4) * 2 > K1_WARPS / ngroup) continue;
+      if (coeff_smem_bytes(pl, pxb, ngroup) <= 227 * 1024) {
+        if (ngroup_out) *ngroup_out = ngroup;
+        return pxb;
+      }
+    }
   }
   PKM_THROW(PKM_ERR_INVALID, "coefficient kernel: nv=%d nz=%d does not fit shared memory", pl->d.nv, pl->d.nz);
 }
 
 template <int TM>
 static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
-                           int64_t pix0, int npix_tile, int xpad, int pxb, double2* cT,
+                           int64_t pix0, int npix_tile, int xpad, int pxb, int ngroup, double2* cT,
                            cudaStream_t st) {
-  size_t smem = coeff_smem_bytes(pl, pxb);
+  size_t smem = coeff_smem_bytes(pl, pxb, ngroup);
   PKM_CUDA(cudaFuncSetAttribute(k_coeff<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t ntile = (int64_t)((npix_tile + pxb - 1) / pxb) * pl->d.nt;
-  int grid = (int)std::min<int64_t>(ntile, pl->num_sms);
+  int grid = (int)std::min<int64_t>((ntile + ngroup - 1) / ngroup, pl->num_sms);
   K1Geom g;
+  g.ngroup = ngroup;
   g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile; g.xpad = xpad;
   g.nv = pl->d.nv; g.nz = pl->d.nz; g.nfi = pl->nfi; g.ne = pl->fold.ne; g.no = pl->fold.no;
   g.pxb = pxb; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
@@ -369,10 +394,11 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
 
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total, int64_t pix0,
                   int npix_tile, int xpad, double2* cT, cudaStream_t st) {
-  const int pxb = coeff_choose_pxb(pl);
+  int ngroup = 1;
+  const int pxb = coeff_choose_pxb(pl, &ngroup);
   PKM_REQUIRE(xpad % 32 == 0 && xpad >= npix_tile, "internal: xpad=%d not a multiple of 32", xpad);
   switch (pl->TM) {
-#define CASE(T) case T: launch_coeff_t<T>(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, pxb, cT, st); break;
+#define CASE(T) case T: launch_coeff_t<T>(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, pxb, ngroup, cT, st); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     default: PKM_THROW(PKM_ERR_INVALID, "unsupported TM=%d", pl->TM);

@@ -30,11 +30,11 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
 // forward DIF: natural order in, digit-permuted order out
-__device__ void fft_forward(double2* s, int M, int logM, const double2* __restrict__ tw) {
+__device__ void fft_forward(double2* s, int M, int logM, const double2* __restrict__ twp) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   int Nb = M;
   for (; Nb >= 4; Nb >>= 2) {
-    const int q = Nb >> 2, stride = M / Nb;
+    const int q = Nb >> 2;
     for (int i = tid; i < (M >> 2); i += nthr) {
       const int j = i & (q - 1);
       const int base = (i - j) * 4 + j;
@@ -42,10 +42,12 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
       double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
       double2 t3 = make_double2(bd.y, -bd.x);  // -i (b - d)
       double2 y0 = cadd(t0, t2), y1 = cadd(t1, t3), y2 = csub(t0, t2), y3 = csub(t1, t3);
+      // per-pass twiddle table: W^(m j stride) at twp[M - 4q + (m-1) q + j], contiguous in j
+      const double2* tp = twp + (M - 4 * q) + j;
       s[base] = y0;
-      s[base + q] = cmul(y1, __ldg(tw + j * stride));
-      s[base + 2 * q] = cmul(y2, __ldg(tw + 2 * j * stride));
-      s[base + 3 * q] = cmul(y3, __ldg(tw + 3 * j * stride));
+      s[base + q] = cmul(y1, __ldg(tp));
+      s[base + 2 * q] = cmul(y2, __ldg(tp + q));
+      s[base + 3 * q] = cmul(y3, __ldg(tp + 2 * q));
     }
     __syncthreads();
   }
@@ -60,7 +62,7 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
 }
 
 // exact inverse of fft_forward up to the factor M: permuted order in, natural order out
-__device__ void fft_inverse(double2* s, int M, int logM, const double2* __restrict__ tw) {
+__device__ void fft_inverse(double2* s, int M, int logM, const double2* __restrict__ twp) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   int Nb = 4;
   if (logM & 1) {
@@ -73,14 +75,15 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
     Nb = 8;
   }
   for (; Nb <= M; Nb <<= 2) {
-    const int q = Nb >> 2, stride = M / Nb;
+    const int q = Nb >> 2;
     for (int i = tid; i < (M >> 2); i += nthr) {
       const int j = i & (q - 1);
       const int base = (i - j) * 4 + j;
+      const double2* tp = twp + (M - 4 * q) + j;
       double2 y0 = s[base];
-      double2 y1 = cmulc(s[base + q], __ldg(tw + j * stride));
-      double2 y2 = cmulc(s[base + 2 * q], __ldg(tw + 2 * j * stride));
-      double2 y3 = cmulc(s[base + 3 * q], __ldg(tw + 3 * j * stride));
+      double2 y1 = cmulc(s[base + q], __ldg(tp));
+      double2 y2 = cmulc(s[base + 2 * q], __ldg(tp + q));
+      double2 y3 = cmulc(s[base + 3 * q], __ldg(tp + 2 * q));
       double2 u0 = cadd(y0, y2), u1 = csub(y0, y2), u2 = cadd(y1, y3), yd = csub(y1, y3);
       double2 u3 = make_double2(-yd.y, yd.x);  // +i (y1 - y3)
       s[base] = cadd(u0, u2);

@@ -183,7 +183,7 @@ void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const do
                         const double* d_log_lw, uint32_t keep_mask, int density, double* out,
                         cudaStream_t st);
 void density_tables_upload(pkm_plan* pl);
-int coeff_choose_pxb(const pkm_plan* pl);
+int coeff_choose_pxb(const pkm_plan* pl, int* ngroup_out = nullptr);
 void launch_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,
                     double* out, cudaStream_t st);
 void launch_max(const double* x, int64_t n, double* d_result, cudaStream_t st);

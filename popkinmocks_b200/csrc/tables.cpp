@@ -220,11 +220,20 @@ void build_czt_tables(int n, CztTables& out) {
   out.alpha.assign(out.nfo, 2.0);
   out.alpha[0] = 1.0;
   if (n % 2 == 0) out.alpha[out.nfo - 1] = 1.0;
-  out.twiddle.resize(size_t(2) * M);
-  for (int j = 0; j < M; ++j) {
-    long double ang = -2.0L * PI_L * (long double)j / (long double)M;
-    out.twiddle[2 * j] = (double)cosl(ang);
-    out.twiddle[2 * j + 1] = (double)sinl(ang);
+  // per-pass radix-4 twiddles, contiguous in the butterfly index j: the pass with quarter
+  // size q (block Nb = 4q, stride = M/Nb) reads W_M^(m j stride), m = 1..3, at
+  // [M - 4q + (m-1) q + j]; the passes q = M/4, M/16, ... fill [0, M - 4 q_min).
+  out.twiddle.assign(size_t(2) * M, 0.0);
+  for (int Nb = M; Nb >= 4; Nb >>= 2) {
+    const int q = Nb >> 2, stride = M / Nb;
+    for (int m = 1; m <= 3; ++m)
+      for (int j = 0; j < q; ++j) {
+        const long long idx = ((long long)m * j * stride) % M;
+        long double ang = -2.0L * PI_L * (long double)idx / (long double)M;
+        const size_t pos = size_t(M - 4 * q) + size_t(m - 1) * q + j;
+        out.twiddle[2 * pos] = (double)cosl(ang);
+        out.twiddle[2 * pos + 1] = (double)sinl(ang);
+      }
   }
   // z[m] = chi[m] * sum_k (a[k] chi[k]) conj(chi[m-k]),  m-k in [-(nfo-1), n-1]
   out.bfilt.assign(size_t(2) * M, 0.0);
