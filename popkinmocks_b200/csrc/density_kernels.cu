@@ -510,7 +510,9 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
       for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + q * 32);
       // B200's FP64 pipe needs >= 4 independent DFMAs per warp to reach its issue rate (8-cycle
       // latency, one warp instruction per ~2.2 cycles per scheduler): frequencies are processed
-      // in groups of K2_G with their chains interleaved.
+      // in groups of K2_G with their chains interleaved.  Measured ceiling: a DFMA with three
+      // fresh register operands costs 3 cycles of register-file bandwidth (25.5 TFLOP/s chip-wide
+      // vs 36.9 with an immediate operand, tools/dfma_rf.cu); this loop runs at ~85 % of that.
 #pragma unroll
       for (int h = 0; h < PKM_KT; h += K2_G) {
         double pr[K2_G], pi[K2_G];

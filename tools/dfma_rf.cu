@@ -1,0 +1,45 @@
+// Development probe: DFMA throughput with 1, 2, 3 distinct register source operands.
+#include <cstdio>
+#include <cuda_runtime.h>
+template <int MODE>
+__global__ void k(double* out, int iters, double a, double b) {
+  double x[8], y[8], z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x + i; y[i] = 1.0 + 1e-9 * (threadIdx.x + i); z[i] = 1e-9 * i * threadIdx.x; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 1) x[i] = fma(x[i], a, b);
+        if (MODE == 2) x[i] = fma(x[i], y[i], b);
+        if (MODE == 3) x[i] = fma(z[(i + u) & 7], y[i], x[i]);
+        if (MODE == 4) x[i] = fma(z[(i + u) & 7], y[(i + 2 * u + 1) & 7], x[i]);
+        if (MODE == 5) x[i] = fma(z[(i + u) & 7], y[u], x[i]);          // slot B shared by 8 consecutive
+        if (MODE == 6) x[i] = fma(z[(i + u) & 7], y[(i >> 1) + u], x[i]); // slot B shared by pairs
+      }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i] + y[i] + z[i];
+  if (s == 1.2345) out[0] = s;
+}
+template <int MODE>
+void run(int warps, int ctas) {
+  double* out; cudaMalloc(&out, 8);
+  int iters = 4000;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k<MODE><<<148 * ctas, warps * 32>>>(out, 10, 0.999, 1e-9);
+  cudaEventRecord(e0);
+  k<MODE><<<148 * ctas, warps * 32>>>(out, iters, 0.999, 1e-9);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double flops = 2.0 * 32 * 32.0 * iters * warps * ctas * 148;
+  printf("mode %d warps/SM=%2d: %.1f TF\n", MODE, warps * ctas, flops / ms / 1e9);
+  cudaFree(out);
+}
+int main() {
+  run<1>(4, 3); run<2>(4, 3); run<3>(4, 3); run<4>(4, 3);
+  run<1>(8, 4); run<2>(8, 4); run<3>(8, 4); run<4>(8, 4); run<5>(4, 3); run<6>(4, 3); run<5>(8, 4); run<6>(8, 4); run<5>(1, 1); run<3>(1, 1);
+  return 0;
+}
