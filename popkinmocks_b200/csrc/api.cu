@@ -197,21 +197,10 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
       pl->d_wseg_w = upload(pl->wsegs.w);
     }
 
-    // ---- gaussian path: FXw as [t][z][kpad]
-    const int kq = 16;
-    pl->kpadA = ((nfo + kq - 1) / kq) * kq;
+    // ---- gaussian path: FXw in tensor-core fragment order, omega buffer
+    gaussian_tables_upload(pl, FXw);
     {
-      std::vector<double> SA(size_t(2) * nt * nz * pl->kpadA, 0.0);
-      for (int k = 0; k < nfo; ++k)
-        for (int z = 0; z < nz; ++z)
-          for (int t = 0; t < nt; ++t) {
-            const double* s = FXw + size_t(2) * ((size_t(k) * nz + z) * nt + t);
-            double* o = SA.data() + size_t(2) * ((size_t(t) * nz + z) * pl->kpadA + k);
-            o[0] = s[0];
-            o[1] = s[1];
-          }
-      pl->d_SA = reinterpret_cast<double2*>(upload(SA));
-      std::vector<double> om(pl->kpadA, 0.0);
+      std::vector<double> om(nfo, 0.0);
       pl->d_omega = upload(om);
     }
 
@@ -497,6 +486,13 @@ extern "C" int32_t pkm_ybar_gaussian(pkm_plan* pl, const double* P_txz, const do
     // omega is tiny: stage it through the stream (ordered with earlier kernels using it)
     PKM_CUDA(cudaMemcpyAsync(pl->d_omega, omega, sizeof(double) * pl->nfo, cudaMemcpyDefault, st));
     PKM_CUDA(cudaStreamSynchronize(st));  // omega may be a pageable temporary of the caller
+    double omega_step4 = 0.0;             // frequency stride of one lane of the kernel: omega[4] - omega[0]
+    {
+      double o[5] = {0, 0, 0, 0, 0};
+      const int cnt = std::min(pl->nfo, 5);
+      PKM_CUDA(cudaMemcpy(o, pl->d_omega, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+      omega_step4 = cnt >= 2 ? 4.0 * (o[1] - o[0]) : 0.0;
+    }
 
     size_t per_px = sizeof(double2) * pl->nfo + sizeof(double) * n;
     if (in_host) per_px += sizeof(double) * (size_t)nt * (nz + 2);
@@ -539,7 +535,7 @@ extern "C" int32_t pkm_ybar_gaussian(pkm_plan* pl, const double* P_txz, const do
         ms[0] = ss[0] = np; ms[1] = ss[1] = 1; ms[2] = ss[2] = 0;
         k_nx2 = 1; k_npix_total = np; k_pix0 = 0;
       }
-      launch_gaussian(pl, dP, dmu, ms, dsg, ss, k_nx2, k_npix_total, k_pix0, np, tile,
+      launch_gaussian(pl, dP, dmu, ms, dsg, ss, k_nx2, k_npix_total, k_pix0, np, tile, omega_step4,
                       pl->yhat.as<double2>(), st);
       launch_irfft_czt(pl, pl->yhat.as<double2>(), np, 1.0, pl->ypx.as<double>(), st);
       emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);

@@ -1,90 +1,201 @@
 // Gaussian-LOSVD path (ParametricComponent.evaluate_ybar,
 // /root/reference/popkinmocks/components/parametric.py:355-373):
 //
-//   Y-hat[k,x] = sum_t exp(-i mu_v[t,x] w_k - (sig_v[t,x] w_k)^2 / 2) * sum_z P[t,x,z] * FXw[k,z,t]
+//   Y-hat[k,x] = sum_t E[k,t,x] * Q[k,t,x],   Q[k,t,x] = sum_z P[t,x,z] * FXw[k,z,t],
+//   E[k,t,x]   = exp(-i mu_v[t,x] w_k - (sig_v[t,x] w_k)^2 / 2),
 //
 // with w_k = linspace(0, pi, nfo)[k] / dv handed over by the host (the reference's own array; it
-// is NOT the true DFT frequency for odd n_fft).  Same thread mapping as the
-// density contraction: warp = 4 frequency groups x 8 pixels, thread = KT frequencies of one pixel,
-// FXw streamed from L2 in [t][z][k] order, accumulation over (t,z) in registers.  The inverse
-// FFT is shared with the density path (fft_kernels.cu).
+// is NOT the true DFT frequency for odd n_fft).
+//
+//   * Q is a small-K GEMM per age t ([pixels x nz] times [nz x (k, re|im)]): it runs on the FP64
+//     tensor cores (DMMA m8n8k4).  Warp = 8 pixels x 64 frequencies; a lane ends up with
+//     Q(re, im) for pixel lane/4 and frequencies lane%4 + 4j.  FXw is pre-arranged on the host in
+//     DMMA fragment order and staged per (frequency tile, age) by one TMA bulk copy, double
+//     buffered, shared by the 8 warps (8 pixel blocks) of the CTA.
+//   * E is evaluated exactly (sincos + 2 exp) once per (t, x, lane) and then advanced along the
+//     lane's frequencies (stride D = w_4) by recurrence: e_{j+1} = e_j r_j, r_{j+1} = r_j beta with
+//     r_0 = exp(-sig^2 D (w_k0 + D/2)) exp(-i mu D), beta = exp(-sig^2 D^2): 6 FP64 ops per
+//     frequency instead of ~80 for sincos + exp; 16 steps, so the round-off growth is ~1e-15.
+// The inverse FFT is shared with the density path (fft_kernels.cu).
+#include <cstdio>
+
 #include "pkm_internal.h"
 
-constexpr int GA_KT = 4;   // frequencies per thread
-constexpr int GA_GPW = 4;  // frequency groups per warp (x 8 pixels = 32 lanes)
+constexpr int GA_NB = 16;      // frequency blocks of 4 per warp (64 frequencies per CTA tile)
+constexpr int GA_WARPS = 8;    // pixel blocks of 8 per CTA
+constexpr int GA_KTILE = 4 * GA_NB;
 
-__global__ void __launch_bounds__(256, 2)
-k_gaussian(const double2* __restrict__ SA, const double* __restrict__ omega,
-           const double* __restrict__ P, const double* __restrict__ mu, long long mu_s0,
-           long long mu_s1, long long mu_s2, const double* __restrict__ sig, long long sg_s0,
-           long long sg_s1, long long sg_s2, long long nx2, long long npix_total, long long pix0,
-           int npix_tile, int nt, int nz, int kpad, int nunit, int nfo, int xpad,
-           double2* __restrict__ yhat) {
+namespace {
+
+__device__ __forceinline__ unsigned ga_smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void ga_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+struct GaGeom {
+  long long mu_s0, mu_s1, mu_s2, sg_s0, sg_s1, sg_s2, nx2, npix_total, pix0;
+  int npix_tile, nt, nz, nks, nfo;
+  double D;  // omega[4] - omega[0]: frequency stride of one lane
+};
+
+template <int NKS>
+__global__ void __launch_bounds__(GA_WARPS * 32, 2)
+k_gaussian(const double* __restrict__ Sg, const double* __restrict__ omega,
+           const double* __restrict__ P, const double* __restrict__ mu,
+           const double* __restrict__ sig, GaGeom g, double2* __restrict__ yhat) {
+  extern __shared__ __align__(128) double ga_smem[];
+  constexpr int STAGE = GA_NB * NKS * 32;                      // doubles per (tile, age) slab
+  double* sS = ga_smem;                                        // [2][STAGE]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sS + 2 * STAGE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * 8 + warp;
-  if (unit >= nunit) return;
-  const int px = lane & 7, gsub = lane >> 3;
-  const int x = blockIdx.y * 8 + px;
-  const bool live = x < npix_tile;
-  const long long xg = pix0 + (live ? x : 0);
-  const long long x1 = xg / nx2, x2 = xg - x1 * nx2;
-  const int k0 = (unit * GA_GPW + gsub) * GA_KT;
-  double om[GA_KT];
-#pragma unroll
-  for (int r = 0; r < GA_KT; ++r) om[r] = omega[k0 + r];  // padded with zeros
-  double2 acc[GA_KT];
-#pragma unroll
-  for (int r = 0; r < GA_KT; ++r) acc[r] = make_double2(0.0, 0.0);
+  const int fr = lane >> 2, fk = lane & 3;
+  const int kt = blockIdx.x;
+  const int x = (blockIdx.y * GA_WARPS + warp) * 8 + fr;       // pixel of this lane within the tile
+  const long long xg = g.pix0 + min(x, g.npix_tile - 1);       // lanes past the tile recompute the last pixel
+  const long long x1 = xg / g.nx2, x2 = xg - x1 * g.nx2;
+  const int k0 = kt * GA_KTILE + fk;
+  const double om0 = __ldg(omega + min(k0, g.nfo - 1));
+  const double D = g.D;
+  const unsigned bar0 = ga_smem_u32(bars);
+  constexpr unsigned BYTES = STAGE * sizeof(double);
+  const double* Sk = Sg + (size_t)kt * g.nt * STAGE;
 
-  for (int t = 0; t < nt; ++t) {
-    const double m = mu[t * mu_s0 + x1 * mu_s1 + x2 * mu_s2];
-    const double sg = sig[t * sg_s0 + x1 * sg_s1 + x2 * sg_s2];
-    double2 q[GA_KT];
-#pragma unroll
-    for (int r = 0; r < GA_KT; ++r) q[r] = make_double2(0.0, 0.0);
-    const double* pp = P + ((long long)t * npix_total + xg) * nz;
-    const double2* sp = SA + (size_t)t * nz * kpad + k0;
-    for (int z = 0; z < nz; ++z) {
-      const double pz = __ldg(pp + z);
-#pragma unroll
-      for (int r = 0; r < GA_KT; ++r) {
-        double2 s = __ldg(sp + r);
-        q[r].x = fma(pz, s.x, q[r].x);
-        q[r].y = fma(pz, s.y, q[r].y);
-      }
-      sp += kpad;
-    }
-#pragma unroll
-    for (int r = 0; r < GA_KT; ++r) {
-      const double so = sg * om[r];
-      const double g = exp(-0.5 * (so * so));
-      double sn, cs;
-      sincos(m * om[r], &sn, &cs);
-      const double er = g * cs, ei = -g * sn;
-      acc[r].x = fma(er, q[r].x, acc[r].x);
-      acc[r].x = fma(-ei, q[r].y, acc[r].x);
-      acc[r].y = fma(er, q[r].y, acc[r].y);
-      acc[r].y = fma(ei, q[r].x, acc[r].y);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < 2 && s < g.nt; ++s) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ga_smem_u32(sS + s * STAGE)), "l"(Sk + (size_t)s * STAGE), "r"(BYTES), "r"(bar0 + 8u * s) : "memory");
     }
   }
-  if (!live) {
+  __syncthreads();
+
+  double2 acc[GA_NB];
 #pragma unroll
-    for (int r = 0; r < GA_KT; ++r) acc[r] = make_double2(0.0, 0.0);
+  for (int nb = 0; nb < GA_NB; ++nb) acc[nb] = make_double2(0.0, 0.0);
+
+  for (int t = 0; t < g.nt; ++t) {
+    const int stage = t & 1;
+    const unsigned parity = (t >> 1) & 1;
+    // this lane's A fragments: P[t, x, z = ks*4 + fk]
+    double pf[NKS];
+    const double* pp = P + ((size_t)t * g.npix_total + xg) * g.nz;
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const int z = ks * 4 + fk;
+      pf[ks] = z < g.nz ? __ldg(pp + z) : 0.0;
+    }
+    const double m = __ldg(mu + t * g.mu_s0 + x1 * g.mu_s1 + x2 * g.mu_s2);
+    const double sg = __ldg(sig + t * g.sg_s0 + x1 * g.sg_s1 + x2 * g.sg_s2);
+    // exact E at the lane's first frequency, then the recurrence factors
+    double sn, cs;
+    sincos(m * om0, &sn, &cs);
+    const double so = sg * om0;
+    const double g0 = exp(-0.5 * (so * so));
+    double2 e = make_double2(g0 * cs, -g0 * sn);
+    sincos(m * D, &sn, &cs);
+    const double a0 = exp(-(sg * sg) * D * (om0 + 0.5 * D));
+    double2 r = make_double2(a0 * cs, -a0 * sn);
+    const double beta = exp(-(sg * sg) * (D * D));
+
+    {  // wait for this age's S slab
+      asm volatile(
+          "{\n.reg .pred p;\nGA_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra GA_DONE;\nbra GA_WAIT;\nGA_DONE:\n}\n" ::"r"(bar0 + 8u * stage), "r"(parity) : "memory");
+    }
+    const double* sb = sS + stage * STAGE + lane;
+#pragma unroll
+    for (int nb = 0; nb < GA_NB; ++nb) {
+      double qr = 0.0, qi = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) ga_dmma(qr, qi, pf[ks], sb[(nb * NKS + ks) * 32]);
+      acc[nb].x = fma(e.x, qr, acc[nb].x);
+      acc[nb].x = fma(-e.y, qi, acc[nb].x);
+      acc[nb].y = fma(e.x, qi, acc[nb].y);
+      acc[nb].y = fma(e.y, qr, acc[nb].y);
+      const double ex = e.x * r.x - e.y * r.y;
+      e.y = e.x * r.y + e.y * r.x;
+      e.x = ex;
+      r.x *= beta;
+      r.y *= beta;
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (threadIdx.x == 0 && t + 2 < g.nt) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * stage), "r"(BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ga_smem_u32(sS + stage * STAGE)), "l"(Sk + (size_t)(t + 2) * STAGE), "r"(BYTES), "r"(bar0 + 8u * stage) : "memory");
+    }
   }
+  if (x < g.npix_tile) {
+    double2* yo = yhat + (size_t)x * g.nfo;
 #pragma unroll
-  for (int r = 0; r < GA_KT; ++r)
-    if (k0 + r < nfo) yhat[(size_t)x * nfo + k0 + r] = acc[r];
+    for (int nb = 0; nb < GA_NB; ++nb) {
+      const int k = k0 + 4 * nb;
+      if (k < g.nfo) yo[k] = acc[nb];
+    }
+  }
+}
+
+}  // namespace
+
+// FXw in DMMA B-fragment order: [ktile][t][nb][ks][lane], lane holds S_ri[k][z] with
+// z = ks*4 + lane%4, column c = lane/4 -> k = ktile*64 + nb*4 + c/2, ri = c%2 (zero padded).
+void gaussian_tables_upload(pkm_plan* pl, const double* FXw) {
+  const int nt = pl->d.nt, nz = pl->d.nz, nfo = pl->nfo;
+  const int nks = (nz + 3) / 4;
+  PKM_REQUIRE(nks <= 8, "nz=%d > 32 unsupported by the Gaussian-path kernel", nz);
+  const int nkt = (nfo + GA_KTILE - 1) / GA_KTILE;
+  pl->ga_nks = nks;
+  pl->ga_nkt = nkt;
+  std::vector<double> h((size_t)nkt * nt * GA_NB * nks * 32, 0.0);
+  for (int kt = 0; kt < nkt; ++kt)
+    for (int t = 0; t < nt; ++t)
+      for (int nb = 0; nb < GA_NB; ++nb)
+        for (int ks = 0; ks < nks; ++ks)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int z = ks * 4 + lane % 4, c = lane / 4;
+            const int k = kt * GA_KTILE + nb * 4 + c / 2, ri = c % 2;
+            if (k < nfo && z < nz)
+              h[((((size_t)kt * nt + t) * GA_NB + nb) * nks + ks) * 32 + lane] =
+                  FXw[size_t(2) * ((size_t(k) * nz + z) * nt + t) + ri];
+          }
+  PKM_CUDA(cudaMalloc(&pl->d_SA, h.size() * sizeof(double)));
+  PKM_CUDA(cudaMemcpy(pl->d_SA, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+template <int NKS>
+static void launch_gaussian_t(pkm_plan* pl, const GaGeom& g, const double* P, const double* mu,
+                              const double* sig, double2* yhat, cudaStream_t st) {
+  const size_t smem = sizeof(double) * 2 * GA_NB * NKS * 32 + 2 * sizeof(unsigned long long);
+  PKM_CUDA(cudaFuncSetAttribute(k_gaussian<NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(pl->ga_nkt, (g.npix_tile + GA_WARPS * 8 - 1) / (GA_WARPS * 8));
+  KernelTimer tm(pl, PKM_K_GAUSSIAN, st);
+  k_gaussian<NKS><<<grid, GA_WARPS * 32, smem, st>>>(reinterpret_cast<const double*>(pl->d_SA), pl->d_omega, P, mu,
+                                                     sig, g, yhat);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches++;
 }
 
 void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
-                     int64_t pix0, int npix_tile, int xpad, double2* yhat, cudaStream_t st) {
-  const int nunit = pl->kpadA / (GA_GPW * GA_KT);
-  dim3 grid((nunit + 7) / 8, (npix_tile + 7) / 8);
-  KernelTimer tm(pl, PKM_K_GAUSSIAN, st);
-  k_gaussian<<<grid, 256, 0, st>>>(pl->d_SA, pl->d_omega, P_txz, mu, mu_st[0], mu_st[1], mu_st[2], sig,
-                                   sig_st[0], sig_st[1], sig_st[2], nx2, npix_total, pix0, npix_tile,
-                                   pl->d.nt, pl->d.nz, pl->kpadA, nunit, pl->nfo, xpad, yhat);
-  PKM_CUDA(cudaGetLastError());
-  pl->launches++;
+                     int64_t pix0, int npix_tile, int xpad, double omega_step4, double2* yhat,
+                     cudaStream_t st) {
+  (void)xpad;
+  GaGeom g;
+  g.mu_s0 = mu_st[0]; g.mu_s1 = mu_st[1]; g.mu_s2 = mu_st[2];
+  g.sg_s0 = sig_st[0]; g.sg_s1 = sig_st[1]; g.sg_s2 = sig_st[2];
+  g.nx2 = nx2; g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile;
+  g.nt = pl->d.nt; g.nz = pl->d.nz; g.nks = pl->ga_nks; g.nfo = pl->nfo; g.D = omega_step4;
+  switch (pl->ga_nks) {
+#define CASE(N) case N: launch_gaussian_t<N>(pl, g, P_txz, mu, sig, yhat, st); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default: PKM_THROW(PKM_ERR_INVALID, "unsupported nz=%d", pl->d.nz);
+  }
 }

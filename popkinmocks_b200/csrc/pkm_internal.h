@@ -127,9 +127,9 @@ struct pkm_plan {
   double* d_wseg_w = nullptr;   // [nwseg][KT][4]
 
   // gaussian path
-  int kpadA = 0;
-  double2* d_SA = nullptr;      // [nt][nz][kpadA]  FXw (unscaled), zero padded
-  double* d_omega = nullptr;    // [kpadA]
+  int ga_nks = 0, ga_nkt = 0;   // k-steps of 4 metallicities, frequency tiles of 64
+  double* d_SA = nullptr;       // FXw (unscaled) in DMMA fragment order [nkt][nt][16][nks][32]
+  double* d_omega = nullptr;    // [nfo] the reference's omega array (set per call)
 
   // inverse FFT
   CztTables czt;
@@ -165,7 +165,9 @@ void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, d
 // gaussian path -> Yhat[xpad][nfo]
 void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
-                     int64_t pix0, int npix_tile, int xpad, double2* yhat, cudaStream_t st);
+                     int64_t pix0, int npix_tile, int xpad, double omega_step4, double2* yhat,
+                     cudaStream_t st);
+void gaussian_tables_upload(pkm_plan* pl, const double* FXw);
 // inverse real FFT: Yhat[npix][nfo] -> out[npix][n] * scale
 void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double scale, double* out,
                       cudaStream_t st);
