@@ -432,7 +432,9 @@ def run_b200(args):
                     "peak_source": "pkm_fp64_fma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                     "flops_per_pixel": flops_px[dom],
                     "note": "P-hat is never materialised (SURVEY.md 8f rank 1): the contraction is "
-                            "FP64-pipe bound, not HBM bound; see roofline_hbm for the canonical byte figure"}
+                            "FP64-pipe bound, not HBM bound; see roofline_hbm for the canonical byte figure. "
+                            "peak is the 2-register-operand DFMA rate; DFMAs with 3 fresh register "
+                            "operands (this kernel's mix) measure 25.5 TFLOP/s (tools/dfma_rf.cu)"}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -123,3 +123,55 @@ def test_mixture_axpy(gpu_ok):
     g = load_golden("g1_conftest_full_nv41")
     out = engine.axpy_cubes([g["d1_ybar"], g["d2_ybar"], g["s1_ybar"]], g["mix_weights"])
     assert rel_err(out, g["mix_ybar"]) < 1e-15
+
+
+def test_headline_shape_properties(gpu_ok):
+    """Full MILES grid, nv=101 (n_fft=4907 = 7*701), 48x40 pixels = several pixel tiles and a
+    ragged last one.  The reference cannot run this size (25 MB/pixel); checked through
+    size-independent properties: spot pixels against the oracle's literal algorithm, linearity
+    in the density, and independence of the pixel tiling / row sharding."""
+    import torch
+    from oracle import restatement as R
+    import popkinmocks_b200 as pkm
+    ssps = pkm.milesSSPs()
+    nx1, nx2, nv = 48, 40, 101
+    cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx1, nx2=nx2, nv=nv, vrng=(-1000.0, 1000.0))
+    plan = pkm.engine.get_plan(cube)
+    nz, nt = ssps.par_dims
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    p1 = torch.rand((nt, nv, nx1, nx2, nz), dtype=torch.float64, device="cuda", generator=gen)
+    p2 = torch.rand((nt, nv, nx1, nx2, nz), dtype=torch.float64, device="cuda", generator=gen) ** 3
+    y1 = plan.ybar_density(p1, is_log=False)
+    y2 = plan.ybar_density(p2, is_log=False)
+    # (i) spot pixels vs the oracle (reference order: irfft per (t,z))
+    y1h = y1.cpu().numpy()
+    for (i, j) in [(0, 0), (17, 31), (47, 39), (23, 8)]:
+        sub = p1[:, :, i:i + 1, j:j + 1, :].cpu().numpy()
+        ref = R.ybar_density_literal(sub, cube.v_edg, ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv,
+                                     ssps.delta_t, ssps.delta_z, cube.dx, cube.dy)
+        assert rel_err(y1h[:, i, j], ref[:, 0, 0]) < TOL, (i, j)
+    # (ii) linearity
+    y12 = plan.ybar_density(0.25 * p1 + 3.0 * p2, is_log=False)
+    lin = 0.25 * y1 + 3.0 * y2
+    assert float((y12 - lin).abs().max() / lin.abs().max()) < 1e-12
+    # (iii) log input == linear input; tiling and row sharding do not change any value
+    ylog = plan.ybar_density(torch.log(p1), is_log=True)
+    assert float((ylog - y1).abs().max() / y1.abs().max()) < 1e-12
+    plan.set_workspace_limit(200 << 20)          # ~330-pixel tiles
+    try:
+        ytile = plan.ybar_density(p1, is_log=False)
+    finally:
+        plan.set_workspace_limit(0)
+    assert torch.equal(ytile, y1)
+    rows = plan.ybar_density(p1, is_log=False, rows=(11, 29))
+    assert torch.equal(rows, y1[:, 11:29])
+    # Gaussian path on the same cube: spot pixels vs the oracle
+    P = torch.rand((nt, nx1, nx2, nz), dtype=torch.float64, device="cuda", generator=gen)
+    P /= P.sum()
+    mu = 400.0 * (torch.rand((nt, nx1, nx2), dtype=torch.float64, device="cuda", generator=gen) - 0.5)
+    sg = 20.0 + 200.0 * torch.rand((nt, nx1, nx2), dtype=torch.float64, device="cuda", generator=gen)
+    ya = plan.ybar_gaussian(P, mu, sg).cpu().numpy()
+    for (i, j) in [(0, 0), (31, 17), (47, 39)]:
+        ref = R.ybar_gaussian(P[:, i:i + 1, j:j + 1].cpu().numpy(), mu[:, i:i + 1, j:j + 1].cpu().numpy(),
+                              sg[:, i:i + 1, j:j + 1].cpu().numpy(), ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv)
+        assert rel_err(ya[:, i, j], ref[:, 0, 0]) < TOL, (i, j)
