@@ -209,16 +209,18 @@ class Component(object):
         return self.get_excess_central_moment(which_dist, 4, light_weighted=light_weighted)
 
     # ------------------------------------------------------------------ the hot path
-    def evaluate_ybar(self, batch="none", device=0):
+    def evaluate_ybar(self, batch="none", device=0, dtype="float64"):
         """Evaluate the datacube  ybar(omega, x) = sum_{t,z} p(t,x,z) [S_tz * p(v|t,x,z)](omega).
 
         Stores `self.ybar` [n_fft, nx1, nx2] (float64 NumPy).  `batch` ('none', 'column',
         'spaxel') is accepted for compatibility: the device path tiles pixels internally so
-        all three give the same result (base.py:789-882)."""
+        all three give the same result (base.py:789-882).  `dtype="float32"` (extension) runs
+        the contraction in float32 arithmetic (~1e-7 relative; default float64 matches the
+        reference to 1e-10)."""
         if batch not in ("none", "column", "spaxel"):
             raise ValueError("Unknown option for batch")
         check_velocity_grid(self.cube)
-        plan = engine.get_plan(self.cube, device=device)
+        plan = engine.get_plan(self.cube, device=device, precision=dtype)
         # the reference evaluates get_p('tvxz') = exp(log p + log dV - log dV); exp is fused
         self.ybar = plan.ybar_density(self.log_p_tvxz, is_log=True)
 

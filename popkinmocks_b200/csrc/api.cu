@@ -122,7 +122,7 @@ static void plan_free(pkm_plan* pl) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_idx_plus); fr(pl->d_idx_minus); fr(pl->d_Sw);
+  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_idx_plus); fr(pl->d_idx_minus); fr(pl->d_Sw); fr(pl->d_Sw32);
   fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_omega);
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz);
@@ -149,7 +149,7 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
     PKM_REQUIRE(desc->nt >= 1 && desc->nz >= 1, "bad SSP grid %d x %d", desc->nt, desc->nz);
     PKM_REQUIRE(desc->n_fft >= 2, "n_fft=%d too small", desc->n_fft);
     PKM_REQUIRE(desc->nv >= 1, "nv=%d", desc->nv);
-    PKM_REQUIRE(desc->precision == 0, "precision=%d: only float64 arithmetic is built", desc->precision);
+    PKM_REQUIRE(desc->precision == 0 || desc->precision == 1, "precision=%d: must be 0 (float64) or 1 (float32)", desc->precision);
     int ndev = pkm_device_count();
     if (ndev <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
     PKM_REQUIRE(desc->device >= 0 && desc->device < ndev, "device %d out of range (%d visible)", desc->device, ndev);
@@ -193,6 +193,10 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
           }
       }
       pl->d_Sw = reinterpret_cast<double2*>(upload(Sw));
+      if (desc->precision == 1) {
+        std::vector<float> Sw32(Sw.begin(), Sw.end());
+        pl->d_Sw32 = reinterpret_cast<float2*>(upload(Sw32));
+      }
       pl->d_wseg = upload(pl->wsegs.seg);
       pl->d_wseg_w = upload(pl->wsegs.w);
     }

@@ -79,6 +79,7 @@ struct K1Geom {
   int npix_tile, xpad, nv, nz, nfi, ne, no, pxb, nt, is_log, v0;
   int use_tma;  // 0 = plain loads, 1 = one 1-D bulk copy per velocity row, 2 = one 2-D tensor copy per tile
   int ngroup;   // independent warp groups per CTA (1 or 2), each running its own tile pipeline
+  int out_f32;  // store the coefficients as float2 (float32 arithmetic mode of the contraction)
 };
 
 // velocity row holding rolled position +u / -u  (np.roll(p, nv - v0), base.py:843)
@@ -277,8 +278,10 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
       const int z = zm / nfi, m = zm - z * nfi;
       const int x = xs ^ ((m + (z >> 2)) & xmask);
       const double2 v = reinterpret_cast<const double2*>(Cs)[i];
-      const int xg = xb * pxb + x;  // pixel-group-major layout, see coef_index()
-      cT[(((size_t)(xg >> 5) * g.nt * nz + (size_t)t * nz + z) * nfi + m) * 32 + (xg & 31)] = v;
+      const int xg = xb * pxb + x;  // pixel-group-major layout cT[x/32][t*nz+z][m][x%32]
+      const size_t ci = (((size_t)(xg >> 5) * g.nt * nz + (size_t)t * nz + z) * nfi + m) * 32 + (xg & 31);
+      if (g.out_f32) reinterpret_cast<float2*>(cT)[ci] = make_float2((float)v.x, (float)v.y);
+      else cT[ci] = v;
     }
     // order this tile's generic-proxy accesses to the buffer before the TMA refill of it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -374,6 +377,7 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile; g.xpad = xpad;
   g.nv = pl->d.nv; g.nz = pl->d.nz; g.nfi = pl->nfi; g.ne = pl->fold.ne; g.no = pl->fold.no;
   g.pxb = pxb; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
+  g.out_f32 = pl->d.precision == 1;
   // 1-D bulk copies need 16-byte aligned row starts and sizes; the tensor map needs a 16-byte
   // aligned base and row pitch and writes a dense [nv][NC] box (so NC must equal the padded pitch)
   const int nz = pl->d.nz;
@@ -565,8 +569,134 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
   }
 }
 
+// ----------------------------------------------------------------------------
+// float32-arithmetic variant of the contraction (plan precision = 1): coefficients and S' are
+// float2, products and the spline run on the FP32 pipe; every staged chunk of 12 (t,z) steps is
+// accumulated in float32 and then folded into float64 accumulators, so the 636-term sum does
+// not lose accuracy to float32 accumulation.  Same work decomposition and TMA staging as above.
+// ----------------------------------------------------------------------------
+constexpr int K2F_CHUNK_ELEMS = PKM_TZC * PKM_KT;                       // float2 per staged chunk
+constexpr unsigned K2F_CHUNK_BYTES = K2F_CHUNK_ELEMS * sizeof(float2);   // 960
+
+__global__ void __launch_bounds__(K2_WARPS * 32, 3)
+k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
+               const int4* __restrict__ wsegs, const float2* __restrict__ cT,
+               double2* __restrict__ yhat, int nwseg, int ntz, int nchunk, int nfi, int np, int nfo,
+               long long nitems) {
+  __shared__ __align__(128) float2 sS[K2_WARPS][K2_STAGES][K2F_CHUNK_ELEMS];
+  __shared__ __align__(8) unsigned long long sBar[K2_WARPS][K2_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * K2_WARPS + warp;
+  if (item >= nitems) return;
+  const int pg = (int)(item / nwseg), ws = (int)(item - (long long)pg * nwseg);
+  const int4 sg = __ldg(wsegs + ws);
+  const int x = pg * 32 + lane;
+  const int xl = min(x, np - 1);
+
+  float w[PKM_KT][3];
+#pragma unroll
+  for (int r = 0; r < PKM_KT; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) w[r][q] = (float)__ldg(Ww + ((size_t)ws * PKM_KT + r) * 4 + q);
+  double2 acc[PKM_KT];
+#pragma unroll
+  for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
+
+  const float2* Sg = Sw + (size_t)ws * nchunk * K2F_CHUNK_ELEMS;
+  const unsigned bar0 = smem_u32(&sBar[warp][0]);
+  const unsigned buf0 = smem_u32(&sS[warp][0][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < K2_STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < K2_STAGES; ++s)
+      if (s < nchunk) {
+        mbar_expect_tx(bar0 + 8u * s, K2F_CHUNK_BYTES);
+        bulk_g2s(buf0 + K2F_CHUNK_BYTES * s, Sg + (size_t)s * K2F_CHUNK_ELEMS, K2F_CHUNK_BYTES, bar0 + 8u * s);
+      }
+  }
+  __syncwarp();
+
+  const size_t c_step = (size_t)nfi * 32;
+  const float2* cp = cT + (((size_t)pg * ntz) * nfi + sg.x) * 32 + (xl & 31);
+  float2 c[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) c[q] = __ldg(cp + q * 32);
+
+  int stage = 0;
+  unsigned parity = 0;
+  int tz = 0;
+  for (int ci = 0; ci < nchunk; ++ci) {
+    mbar_wait(bar0 + 8u * stage, parity);
+    const float2* sbuf = &sS[warp][stage][0];
+    const int nrow = min(PKM_TZC, ntz - ci * PKM_TZC);
+    float2 a32[PKM_KT];
+#pragma unroll
+    for (int r = 0; r < PKM_KT; ++r) a32[r] = make_float2(0.f, 0.f);
+    for (int j = 0; j < nrow; ++j, ++tz) {
+      const float2 c3 = c[3];
+      float2 d[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) d[q] = make_float2(c[q].x - c3.x, c[q].y - c3.y);
+      cp += (tz + 1 < ntz) ? c_step : 0;
+      if (tz + K2_PF < ntz)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)(K2_PF - 1) * c_step + (ws & 3) * 32));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[q] = __ldg(cp + q * 32);
+#pragma unroll
+      for (int r = 0; r < PKM_KT; ++r) {
+        const float2 s = sbuf[j * PKM_KT + r];
+        float pr = c3.x, pi = c3.y;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          pr = fmaf(w[r][q], d[q].x, pr);
+          pi = fmaf(w[r][q], d[q].y, pi);
+        }
+        a32[r].x = fmaf(s.x, pr, a32[r].x);
+        a32[r].x = fmaf(-s.y, pi, a32[r].x);
+        a32[r].y = fmaf(s.x, pi, a32[r].y);
+        a32[r].y = fmaf(s.y, pr, a32[r].y);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < PKM_KT; ++r) {
+      acc[r].x += (double)a32[r].x;
+      acc[r].y += (double)a32[r].y;
+    }
+    __syncwarp();
+    if (lane == 0 && ci + K2_STAGES < nchunk) {
+      mbar_expect_tx(bar0 + 8u * stage, K2F_CHUNK_BYTES);
+      bulk_g2s(buf0 + K2F_CHUNK_BYTES * stage, Sg + (size_t)(ci + K2_STAGES) * K2F_CHUNK_ELEMS, K2F_CHUNK_BYTES,
+               bar0 + 8u * stage);
+    }
+    if (++stage == K2_STAGES) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (x < np) {
+    double2* yo = yhat + (size_t)x * nfo + sg.y;
+#pragma unroll
+    for (int r = 0; r < PKM_KT; ++r)
+      if (r < sg.z) yo[r] = acc[r];
+  }
+}
+
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
                      cudaStream_t st) {
+  if (pl->d.precision == 1) {
+    const long long npg = (npix_tile + 31) / 32;
+    const long long nitems = npg * pl->wsegs.nwseg;
+    const unsigned grid = (unsigned)((nitems + K2_WARPS - 1) / K2_WARPS);
+    KernelTimer tm(pl, PKM_K_CONTRACT, st);
+    k_contract_f32<<<grid, K2_WARPS * 32, 0, st>>>(pl->d_Sw32, pl->d_wseg_w, reinterpret_cast<const int4*>(pl->d_wseg),
+                                                  reinterpret_cast<const float2*>(cT), yhat, pl->wsegs.nwseg,
+                                                  pl->ntz, pl->nchunk, pl->nfi, npix_tile, pl->nfo, nitems);
+    PKM_CUDA(cudaGetLastError());
+    pl->launches++;
+    return;
+  }
   const long long npg = (npix_tile + 31) / 32;
   const long long nitems = npg * pl->wsegs.nwseg;
   const unsigned grid = (unsigned)((nitems + K2_WARPS - 1) / K2_WARPS);

@@ -123,6 +123,7 @@ struct pkm_plan {
   int32_t* d_idx_plus = nullptr;
   int32_t* d_idx_minus = nullptr;
   double2* d_Sw = nullptr;      // [nwseg][nchunk*TZC][KT]  S-hat' = FXw*dz*dt, tz = t*nz+z, zero padded
+  float2* d_Sw32 = nullptr;     // float32 copy of d_Sw (precision = 1 only)
   int32_t* d_wseg = nullptr;    // [nwseg][4]
   double* d_wseg_w = nullptr;   // [nwseg][KT][4]
 

@@ -34,8 +34,11 @@ def find_v0_idx(cube):
 class Plan:
     """Device-resident constants of one cube on one GPU."""
 
-    def __init__(self, cube, device=0):
+    def __init__(self, cube, device=0, precision="float64"):
         _lib.require_gpu()
+        if precision not in ("float64", "float32"):
+            raise ValueError("precision must be 'float64' or 'float32'")
+        self.precision = precision
         ssps = cube.ssps
         nz, nt = ssps.par_dims
         self.nt, self.nz, self.nv = int(nt), int(nz), int(cube.nv)
@@ -43,7 +46,8 @@ class Plan:
         self.nfo = self.n_fft // 2 + 1
         self.device = int(device)
         desc = _lib.CubeDesc(nt=self.nt, nz=self.nz, nv=self.nv, n_fft=self.n_fft,
-                             v0_idx=find_v0_idx(cube), device=self.device, precision=0,
+                             v0_idx=find_v0_idx(cube), device=self.device,
+                             precision=1 if precision == "float32" else 0,
                              reserved=0, dv=float(ssps.dv), dx=float(cube.dx), dy=float(cube.dy))
         FXw = np.ascontiguousarray(ssps.FXw, dtype=np.complex128)
         if FXw.shape != (self.nfo, self.nz * self.nt):
@@ -198,12 +202,15 @@ class Plan:
         return out
 
 
-def get_plan(cube, device=0):
-    """The cube's plan for `device` (created on first use)."""
+def get_plan(cube, device=0, precision="float64"):
+    """The cube's plan for (`device`, `precision`), created on first use.
+
+    precision="float32" selects float32 arithmetic in the density-path contraction (inputs and
+    outputs stay float64; BASELINE.json tolerance 1e-5); everything else is always float64."""
     cache = cube.__dict__.setdefault("_pkm_plans", {})
-    key = int(device)
+    key = int(device) if precision == "float64" else (int(device), precision)
     if key not in cache:
-        cache[key] = Plan(cube, device=key)
+        cache[key] = Plan(cube, device=int(device), precision=precision)
     return cache[key]
 
 

@@ -175,3 +175,19 @@ def test_headline_shape_properties(gpu_ok):
         ref = R.ybar_gaussian(P[:, i:i + 1, j:j + 1].cpu().numpy(), mu[:, i:i + 1, j:j + 1].cpu().numpy(),
                               sg[:, i:i + 1, j:j + 1].cpu().numpy(), ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv)
         assert rel_err(ya[:, i, j], ref[:, 0, 0]) < TOL, (i, j)
+
+
+@pytest.mark.parametrize("name,tags", [("g1_conftest_full_nv41", ["b_"]), ("g2_rebin_nv21_prime", ["b_", "wn_"]),
+                                       ("g3_full_nv101_odd", ["wn_"])])
+def test_float32_option_within_1e5(gpu_ok, name, tags):
+    """Optional float32 arithmetic of the contraction: BASELINE.json tolerance 1e-5 max-norm."""
+    from popkinmocks_b200 import engine
+    g = load_golden(name)
+    plan32 = engine.get_plan(golden_cube(name), precision="float32")
+    plan64 = engine.get_plan(golden_cube(name))
+    assert plan32 is not plan64
+    for tag in tags:
+        y32 = plan32.ybar_density(g[tag + "log_p_tvxz"], is_log=True)
+        err = rel_err(y32, g[tag + "ybar"])
+        assert err < 1e-5, (name, tag, err)
+        assert err > 1e-12      # it really is the float32 path

@@ -46,3 +46,10 @@ print(f"density(log) : {ms:.2f} ms  {vox/ms*1e3:.3e} voxel/s", {k: round(v[0]/6,
 plan.set_profiling(True)
 ms = timeit(lambda: plan.ybar_gaussian(P, mu, sg))
 print(f"gaussian {nx}x{nx}: {ms:.2f} ms  {vox/ms*1e3:.3e} voxel/s", {k: round(v[0]/6, 3) for k, v in plan.kernel_times().items()})
+
+plan32 = engine.get_plan(cube, precision="float32")
+plan32.set_profiling(True)
+ms = timeit(lambda: plan32.ybar_density(p, is_log=False))
+y64 = plan.ybar_density(p, is_log=False); y32 = plan32.ybar_density(p, is_log=False)
+print(f"density fp32 {nx}x{nx}: {ms:.2f} ms  {vox/ms*1e3:.3e} voxel/s", {k: round(v[0]/6, 3) for k, v in plan32.kernel_times().items()},
+      "rel diff vs fp64", float((y32 - y64).abs().max() / y64.abs().max()))
