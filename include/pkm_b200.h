@@ -168,6 +168,16 @@ PKM_API int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t mod
 /* max over a device/host float64 buffer (NaN-propagating like numpy.max). */
 PKM_API int32_t pkm_max(const double* x, int64_t n, double* result_host, int32_t device, void* stream);
 
+/* 5-D particle histogram with numpy.histogramdd bin semantics (FromParticle,
+ * popkinmocks/components/particle.py:52-54): samples[a] (a = t, v, x1, x2, z; n values each, host
+ * or device, all on the same side), edges[a] host arrays of nbin[a]+1 ascending bin edges.
+ * out [nbin0][nbin1][nbin2][nbin3][nbin4] float64 (host or device) receives the counts, or the
+ * sums of `weights` (may be NULL).  Bin = searchsorted(edges, x, "right") - 1, x == last edge
+ * falls in the last bin, outside / NaN is dropped: indices are bit-exact w.r.t. NumPy. */
+PKM_API int32_t pkm_histogram5d(const double* const* samples, const double* weights, int64_t n,
+                                const double* const* edges, const int32_t* nbin, double* out,
+                                int32_t device, void* stream);
+
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA; best of `repeats`
  * timed launches of a register-resident DFMA chain on every SM).  The roofline denominator of
  * the FP64-pipe-bound kernels; MEASURED_PEAKS.json carries no FP64 figure. */

@@ -1,13 +1,30 @@
 """`FromParticle`: a component built by binning simulation particles onto the cube's grid.
 
 Behind the reference's API (/root/reference/popkinmocks/components/particle.py:5-56).  The
-5-D histogram uses `numpy.histogramdd` semantics exactly (right edge of the last bin
-inclusive, `density=True`, optional mass weights); a device histogram is the first "next" row
-of SURVEY.md section 8f.
+5-D histogram is counted on the device (pkm_histogram5d) with `numpy.histogramdd` bin
+semantics - searchsorted(side="right"), right edge of the last bin inclusive, outliers dropped -
+so bin indices are bit-exact; the `density=True` normalisation then applies NumPy's own
+sequence of operations to the counts on the host, which makes the unweighted result
+bit-identical to `np.histogramdd(..., density=True)`.
 """
 import numpy as np
 
 from . import base
+from .. import engine
+
+
+def density_from_counts(counts, edges):
+    """The `density=True` normalisation of numpy.histogramdd, operation for operation
+    (numpy/lib/_histograms_impl.py: total first, then one division per axis, then the total)."""
+    hist = counts
+    total = hist.sum()
+    ndim = hist.ndim
+    for axis, e in enumerate(edges):
+        shape = np.ones(ndim, int)
+        shape[axis] = hist.shape[axis]
+        hist = hist / np.diff(e).reshape(shape)
+    hist /= total
+    return hist
 
 
 class FromParticle(base.Component):
@@ -29,7 +46,9 @@ class FromParticle(base.Component):
         for name, data, e in zip(names, samples, edges):
             lines.append(f"   {name}\t: {int(np.sum(data < e[0]))}/{int(np.sum(data > e[-1]))}")
         print("\n".join(lines))
-        p_tvxz, _ = np.histogramdd(samples, bins=edges, density=True, weights=mass_weights)
+        counts = engine.histogram5d(samples, edges, weights=mass_weights)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            p_tvxz = density_from_counts(counts, edges)
         with np.errstate(divide="ignore"):
             log_p_tvxz = np.log(p_tvxz)
         super().__init__(cube=cube, log_p_tvxz=log_p_tvxz)

@@ -780,3 +780,59 @@ extern "C" int32_t pkm_fp64_fma_peak(int32_t device, int32_t repeats, double* tf
     *tflops_out = run_fma_probe(prop.multiProcessorCount, repeats);
   });
 }
+
+extern "C" int32_t pkm_histogram5d(const double* const* samples, const double* weights, int64_t n,
+                                   const double* const* edges, const int32_t* nbin, double* out,
+                                   int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(samples && edges && nbin && out && n >= 0, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaDeviceProp prop;
+    PKM_CUDA(cudaGetDeviceProperties(&prop, device));
+    int nb[5];
+    int64_t nbins = 1;
+    std::vector<double> h_edges;
+    for (int a = 0; a < 5; ++a) {
+      PKM_REQUIRE(nbin[a] >= 1 && samples[a] && edges[a], "bad axis %d", a);
+      nb[a] = nbin[a];
+      nbins *= nbin[a];
+      h_edges.insert(h_edges.end(), edges[a], edges[a] + nbin[a] + 1);   // edges are host arrays
+    }
+    PKM_REQUIRE(h_edges.size() * sizeof(double) <= 40 * 1024, "too many bin edges");
+    const bool host = !pkm_is_device_pointer(samples[0]);
+    for (int a = 1; a < 5; ++a)
+      PKM_REQUIRE(host == !pkm_is_device_pointer(samples[a]), "all sample arrays must be on the same side");
+    if (weights) PKM_REQUIRE(host == !pkm_is_device_pointer(weights), "weights must be on the same side as the samples");
+    const bool out_host = !pkm_is_device_pointer(out);
+    DevBuf buf, obuf, ebuf;
+    ebuf.reserve(sizeof(double) * h_edges.size());
+    PKM_CUDA(cudaMemcpyAsync(ebuf.p, h_edges.data(), sizeof(double) * h_edges.size(), cudaMemcpyHostToDevice, st));
+    const double* d_s[5];
+    const double* d_w = weights;
+    if (host) {
+      buf.reserve(sizeof(double) * (size_t)std::max<int64_t>(n, 1) * 6);
+      double* base = buf.as<double>();
+      for (int a = 0; a < 5; ++a) {
+        PKM_CUDA(cudaMemcpyAsync(base + (size_t)a * n, samples[a], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        d_s[a] = base + (size_t)a * n;
+      }
+      if (weights) {
+        PKM_CUDA(cudaMemcpyAsync(base + (size_t)5 * n, weights, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        d_w = base + (size_t)5 * n;
+      }
+    } else {
+      for (int a = 0; a < 5; ++a) d_s[a] = samples[a];
+    }
+    double* d_out = out;
+    if (out_host) {
+      obuf.reserve(sizeof(double) * nbins);
+      d_out = obuf.as<double>();
+    }
+    launch_hist5d(d_s, d_w, n, ebuf.as<double>(), nb, d_out, prop.multiProcessorCount, st);
+    if (out_host) PKM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * nbins, cudaMemcpyDeviceToHost, st));
+    PKM_CUDA(cudaStreamSynchronize(st));
+    buf.release(); obuf.release(); ebuf.release();
+  });
+}

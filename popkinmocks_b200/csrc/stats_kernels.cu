@@ -390,6 +390,91 @@ void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t 
 }
 
 // ----------------------------------------------------------------------------
+// 5-D particle histogram with numpy.histogramdd bin semantics (FromParticle,
+// /root/reference/popkinmocks/components/particle.py:52-54): per axis the bin is
+// searchsorted(edges, x, side="right") - 1, a sample equal to the last edge belongs to the last
+// bin, anything outside (or NaN) is dropped.  Comparisons are the same float64 comparisons NumPy
+// makes, so bin indices are bit-exact.  Unweighted counts use 64-bit integer atomics (exact);
+// weighted sums use float64 atomics (order of additions differs from NumPy's bincount).
+// ----------------------------------------------------------------------------
+namespace {
+struct HistGeom {
+  int n[5];
+  int off[5];   // offset of each axis' edges in the shared edge table
+};
+
+__device__ __forceinline__ int bin_of(const double* e, int nbin, double x) {
+  // number of edges <= x, minus one (side="right"); x == last edge -> last bin
+  if (!(x >= e[0]) || !(x <= e[nbin])) return -1;   // also rejects NaN
+  if (x == e[nbin]) return nbin - 1;
+  int lo = 0, hi = nbin;                             // invariant: e[lo] <= x < e[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (e[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_hist5d(const double* __restrict__ s0, const double* __restrict__ s1, const double* __restrict__ s2,
+         const double* __restrict__ s3, const double* __restrict__ s4, const double* __restrict__ wts,
+         long long n, const double* __restrict__ edges, HistGeom g, int nedge_total,
+         unsigned long long* __restrict__ counts, double* __restrict__ sums) {
+  extern __shared__ double s_edges[];
+  for (int i = threadIdx.x; i < nedge_total; i += blockDim.x) s_edges[i] = edges[i];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double xs[5] = {s0[i], s1[i], s2[i], s3[i], s4[i]};
+    long long flat = 0;
+    bool inside = true;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const int b = bin_of(s_edges + g.off[a], g.n[a], xs[a]);
+      inside = inside && b >= 0;
+      flat = flat * g.n[a] + (b >= 0 ? b : 0);
+    }
+    if (!inside) continue;
+    if (wts) atomicAdd(sums + flat, wts[i]);
+    else atomicAdd(counts + flat, 1ull);
+  }
+}
+
+__global__ void k_u64_to_f64(const unsigned long long* __restrict__ in, double* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+}  // namespace
+
+// out (device, nbins doubles) receives counts or weighted sums; samples/weights/edges on device
+void launch_hist5d(const double* const samples[5], const double* weights, int64_t n, const double* d_edges,
+                   const int nbin[5], double* out, int num_sms, cudaStream_t st) {
+  HistGeom g;
+  int off = 0;
+  long long nbins = 1;
+  for (int a = 0; a < 5; ++a) {
+    g.n[a] = nbin[a];
+    g.off[a] = off;
+    off += nbin[a] + 1;
+    nbins *= nbin[a];
+  }
+  PKM_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * nbins, st));
+  if (n > 0) {
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms * 16);
+    // unweighted: count in place as u64 (same size as the float64 output), convert afterwards
+    k_hist5d<<<grid, 256, sizeof(double) * off, st>>>(samples[0], samples[1], samples[2], samples[3], samples[4],
+                                                     weights, n, d_edges, g, off,
+                                                     reinterpret_cast<unsigned long long*>(out), out);
+    PKM_CUDA(cudaGetLastError());
+  }
+  if (!weights) {
+    const int grid = (int)std::min<int64_t>((nbins + 255) / 256, (int64_t)num_sms * 16);
+    k_u64_to_f64<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(out), out, nbins);
+    PKM_CUDA(cudaGetLastError());
+  }
+}
+
+// ----------------------------------------------------------------------------
 // FP64 FMA throughput probe (roofline denominator of the FP64-pipe-bound kernels; the
 // driver-written MEASURED_PEAKS.json has no FP64 figure).  8 independent DFMA chains per
 // thread, 256 threads x 8 CTAs per SM.

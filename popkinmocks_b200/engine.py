@@ -272,3 +272,25 @@ def fp64_fma_peak(device=0, repeats=5):
     out = C.c_double(0.0)
     _lib.check(_lib.load().pkm_fp64_fma_peak(int(device), int(repeats), C.byref(out)))
     return out.value
+
+
+def histogram5d(samples, edges, weights=None, device=0):
+    """Counts (or weighted sums) of particles on a 5-D grid with numpy.histogramdd bin semantics.
+
+    samples: 5 arrays (t, v, x1, x2, z); edges: 5 ascending edge arrays.  Returns a float64
+    array [nt, nv, nx1, nx2, nz] (host).  Bin indices are bit-exact w.r.t. NumPy."""
+    _lib.require_gpu()
+    samples = [_lib.as_f64(s).ravel() for s in samples]
+    n = samples[0].size
+    if any(s.size != n for s in samples):
+        raise ValueError("sample arrays must have equal length")
+    edges = [_lib.as_f64(e) for e in edges]
+    nbin = (C.c_int32 * 5)(*[e.size - 1 for e in edges])
+    out = np.empty(tuple(e.size - 1 for e in edges), dtype=np.float64)
+    sp = (C.c_void_p * 5)(*[_lib.ptr(s) for s in samples])
+    ep = (C.c_void_p * 5)(*[_lib.ptr(e) for e in edges])
+    w = None if weights is None else _lib.as_f64(weights).ravel()
+    if w is not None and w.size != n:
+        raise ValueError("weights must have one entry per particle")
+    _lib.check(_lib.load().pkm_histogram5d(sp, _lib.ptr(w), n, ep, nbin, _lib.ptr(out), int(device), None))
+    return out

@@ -219,3 +219,46 @@ def test_shot_noise_is_noisier_than_constant_snr(galaxy):
     eps_shot = pkm.noise.ShotNoise(galaxy).get_noisy_data(snr=100) - galaxy.ybar
     eps_const = pkm.noise.ConstantSNR(galaxy).get_noisy_data(snr=100) - galaxy.ybar
     assert np.median(np.abs(eps_shot)) > np.median(np.abs(eps_const))
+
+
+def test_from_particle_histogram_is_bit_identical_to_numpy(gpu_ok):
+    """Device 5-D histogram vs np.histogramdd: bit-exact binning, incl. samples on bin edges, on the
+    outer edges, outliers and NaN (BASELINE.json: 'bit-exact for indexing and binning')."""
+    cube = golden_cube("g2_rebin_nv21_prime")
+    names = ("t", "v", "x1", "x2", "z")
+    edges = [cube.get_variable_edges(k) for k in names]
+    rng = np.random.default_rng(5)
+    n = 200000
+    t = rng.uniform(-0.5, 14.5, n)
+    v = rng.normal(0.0, 400.0, n)
+    x1, x2 = rng.uniform(-1.1, 1.1, n), rng.uniform(-1.0, 1.0, n)
+    z = rng.uniform(-2.6, 0.5, n)
+    # adversarial values: exactly on inner / first / last edges
+    for arr, e in zip((t, v, x1, x2, z), edges):
+        arr[:e.size] = e
+        arr[e.size:2 * e.size] = np.nextafter(e, np.inf)
+        arr[2 * e.size:3 * e.size] = np.nextafter(e, -np.inf)
+    v[-3:] = [np.nan, np.inf, -np.inf]
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        comp = pkm.components.FromParticle(cube, t, v, x1, x2, z)
+    assert "particles out of bounds" in out.getvalue()
+    ok = np.isfinite(v)
+    ref, _ = np.histogramdd([a[ok] for a in (t, v, x1, x2, z)], bins=edges, density=True)
+    with np.errstate(divide="ignore"):
+        assert np.array_equal(comp.log_p_tvxz, np.log(ref))
+    counts = pkm.engine.histogram5d([t, v, x1, x2, z], edges)
+    cref, _ = np.histogramdd([a[ok] for a in (t, v, x1, x2, z)], bins=edges)
+    assert np.array_equal(counts, cref)
+    # weighted: same bins, sums equal up to the order of additions
+    w = rng.random(n)
+    sums = pkm.engine.histogram5d([t, v, x1, x2, z], edges, weights=w)
+    wref, _ = np.histogramdd([a[ok] for a in (t, v, x1, x2, z)], bins=edges, weights=w[ok])
+    assert np.allclose(sums, wref, rtol=1e-13, atol=0)
+    assert np.array_equal(sums == 0, wref == 0)
+    # the reference's own check: p(t,z) of the component equals the 2-D histogram
+    tz, _, _ = np.histogram2d(t[ok], z[ok], bins=[edges[0], edges[4]], density=True)
+    inside = np.ones(n, dtype=bool)
+    for arr, e in zip((t, v, x1, x2, z), edges):
+        inside &= (arr >= e[0]) & (arr <= e[-1])
+    tz_in, _, _ = np.histogram2d(t[inside], z[inside], bins=[edges[0], edges[4]], density=True)
+    assert np.allclose(comp.get_p("tz"), tz_in, rtol=1e-10)

@@ -147,24 +147,6 @@ def test_constructor_and_argument_errors_match_reference():
         pkm.components.Component(cube=bad, log_p_tvxz=np.zeros(shape)).evaluate_ybar()
 
 
-def test_from_particle_histogram_matches_numpy():
-    cube = golden_cube("g2_rebin_nv21_prime")
-    rng = np.random.default_rng(5)
-    n = 20000
-    t = rng.uniform(0.0, 14.0, n)
-    v = rng.normal(0.0, 300.0, n)
-    x1, x2 = rng.uniform(-1.1, 1.1, n), rng.uniform(-1.0, 1.0, n)
-    z = rng.uniform(-2.5, 0.5, n)
-    import contextlib, io
-    with contextlib.redirect_stdout(io.StringIO()) as out:
-        comp = pkm.components.FromParticle(cube, t, v, x1, x2, z)
-    assert "particles out of bounds" in out.getvalue()
-    ref, _ = np.histogramdd([t, v, x1, x2, z], bins=[cube.get_variable_edges(k) for k in ("t", "v", "x1", "x2", "z")],
-                            density=True)
-    with np.errstate(divide="ignore"):
-        assert np.array_equal(comp.log_p_tvxz, np.log(ref))
-
-
 def test_plans_are_not_pickled():
     import dill
     cube = build_cube("g4_even_nv40")
