@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the brief timings of the other hot-path rows")
     ap.add_argument("--cpu-procs", type=int, default=0, help="host processes of the CPU legs (0 = all cores, max 64)")
     ap.add_argument("--cpu-px", type=int, default=2, help="pixels per CPU task")
     return ap.parse_args()
@@ -368,6 +369,46 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = voxels_per_step / (ms_step * 1e-3)
 
+    # ---- the other rows of the hot-path table, timed briefly on the same cube (N=1 only; reported
+    # under "other_paths", not part of `value`)
+    other = None
+    if world == 1 and not args.no_other:
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a0 = torch.cuda.Event(enable_timing=True)
+            a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps
+        other = {}
+        P = torch.rand((nt, rows, nx, nz), dtype=torch.float64, device=dev, generator=gen)
+        P /= P.sum()
+        mu_v = 400.0 * (torch.rand((nt, rows, nx), dtype=torch.float64, device=dev, generator=gen) - 0.5)
+        sig_v = 20.0 + 200.0 * torch.rand((nt, rows, nx), dtype=torch.float64, device=dev, generator=gen)
+        ms = timed(lambda: plan.ybar_gaussian(P, mu_v, sig_v, out=out))
+        other["gaussian_path_A"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
+                                    "ref": "ParametricComponent.evaluate_ybar parametric.py:335-407"}
+        del P, mu_v, sig_v
+        plan32 = engine.Plan(cube, device=local, precision="float32")
+        ms = timed(lambda: plan32.ybar_density(logp, is_log=True, out=out))
+        other["density_path_B_float32"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
+                                           "note": "optional float32 contraction, tolerance 1e-5"}
+        plan32.close()
+        del plan32
+        log_dv = np.log(np.diff(cube.v_edg))
+        ms = timed(lambda: plan.reduce_logp(logp, log_dv, "vx", False))
+        other["log_marginal_vx"] = {"ms": ms, "GB_per_s": 2 * logp.numel() * 8 / (ms * 1e-3) / 1e9,
+                                    "note": "pkm_reduce_logp: two streaming passes over the 5-D array",
+                                    "ref": "Component._get_log_p_vx base.py:1062-1079"}
+        ms = timed(lambda: engine.noise(out, 100.0, 0, seed=1, want_sigma=False))
+        other["shot_noise"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
+                               "ref": "ShotNoise.get_noisy_data noise.py:16-71"}
+        torch.cuda.empty_cache()
+
     # ---- e2e: same call through the C ABI with pinned host buffers
     e2e = None
     windows = [(w0, w1)]
@@ -457,7 +498,7 @@ def run_b200(args):
                              "compulsory": {"bytes_per_voxel": b_min, "achieved": b_min * per_gpu / 1e9,
                                             "frac": b_min * per_gpu / 1e9 / hbm_peak},
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
-            "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+            "kernels": kern, "other_paths": other, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

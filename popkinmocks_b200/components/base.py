@@ -113,13 +113,38 @@ class Component(object):
             out = out - np.log(self.cube.construct_volume_element(which_dist))
         return out
 
+    # device-resident copy of log_p_tvxz, shared by evaluate_ybar / get_p / moments so that a
+    # sequence of calls uploads the 5-D array once (the reference re-derives it per call)
+    _DEVICE_CACHE_LIMIT = 64 << 30
+
+    def _device_log_p(self, device=0):
+        cached = self.__dict__.get("_pkm_dev")
+        src = self.log_p_tvxz
+        if cached is not None and cached[0] is src and cached[1] == device:
+            return cached[2]
+        if engine._is_cuda_tensor(src):
+            return src
+        engine._lib.require_gpu()
+        if src.nbytes > self._DEVICE_CACHE_LIMIT:
+            return src                       # too large to keep resident: stream it per call
+        import torch
+        dev = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64)).to(f"cuda:{device}")
+        self.__dict__["_pkm_dev"] = (src, device, dev)
+        return dev
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_pkm_dev", None)          # never pickle device handles (dill_dump must keep working)
+        return state
+
     def _log_marginal(self, keep, density=True, light_weighted=False):
         """log-marginal over the axes not in `keep`, on the GPU (pkm_reduce_logp)."""
         cube = self.cube
         plan = engine.get_plan(cube)
         log_dv = np.log(cube.v_edg[1:] - cube.v_edg[:-1])
         lw = cube.ssps.light_weights if light_weighted else None
-        return plan.reduce_logp(self.log_p_tvxz, log_dv, keep, density, light_weights=lw)
+        out = plan.reduce_logp(self._device_log_p(), log_dv, keep, density, light_weights=lw)
+        return out.cpu().numpy() if engine._is_torch(out) else out
 
     # ------------------------------------------------------------------ moments
     def _moment_axis(self, which_dist):
@@ -222,7 +247,8 @@ class Component(object):
         check_velocity_grid(self.cube)
         plan = engine.get_plan(self.cube, device=device, precision=dtype)
         # the reference evaluates get_p('tvxz') = exp(log p + log dV - log dV); exp is fused
-        self.ybar = plan.ybar_density(self.log_p_tvxz, is_log=True)
+        out = plan.ybar_density(self._device_log_p(device), is_log=True)
+        self.ybar = out.cpu().numpy() if engine._is_torch(out) else out
 
     # ------------------------------------------------------------------ persistence
     def dill_dump(self, fname, direc=None):
