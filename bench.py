@@ -11,8 +11,9 @@ full MILES_BASTI grid (nt=53, nz=12), nv=101, lambda 4700-6500 A -> n_fft=4907; 
 
 N > 1 (torchrun, one rank per GPU): strong scaling of the named configuration - the x1 rows of
 ONE 201x201-pixel cube are sharded over the ranks (pixels are independent),
-every rank evaluates its block in sub-blocks that are shipped to rank 0 over NCCL while the next
-one is computed, and rank 0 assembles [n_fft, nx1, nx2]; all inside the timed region.
+every rank evaluates its block and its last kernel (the transpose to the reference layout) stores
+the rows straight into rank 0's cube through NVLink peer memory (CUDA IPC), followed by one small
+NCCL all-reduce as the barrier; all inside the timed region (`--gather nccl`: NCCL send/recv).
 `--scaling weak` evaluates a (201*N)x201 mosaic instead (201 rows per rank).
 
 The JSON line printed by rank 0 follows the driver contract: `value` = device-resident
@@ -49,7 +50,9 @@ def parse_args():
     ap.add_argument("--nv", type=int, default=101)
     ap.add_argument("--lmd", type=float, nargs=2, default=(4700.0, 6500.0))
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
-    ap.add_argument("--gather-tiles", type=int, default=4, help="sub-blocks per rank for the overlapped gather")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: assemble the cube on rank 0 by peer-memory stores from the transpose kernel, or by NCCL send/recv")
+    ap.add_argument("--gather-tiles", type=int, default=1, help="sub-blocks per rank for the NCCL gather")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -315,6 +318,12 @@ def run_b200(args):
     if world == 1:
         out = torch.empty((n_fft, rows, nx), dtype=torch.float64, device=dev)
         tg = None
+    elif args.gather == "peer":
+        # rank 0 owns the cube; every rank's final transpose kernel stores its rows into it over NVLink
+        pc = sharding.PeerCube(n_fft, nx1_total, nx, dev, dist)
+        out = pc.cube
+        tg = None
+        flag = torch.zeros(1, device=dev)
     else:
         tg = sharding.TileGather(nx1_total, nx, n_fft, dev, dist=dist, ntile=args.gather_tiles)
         out = torch.empty((n_fft, nx1_total, nx), dtype=torch.float64, device=dev) if rank == 0 else None
@@ -322,6 +331,10 @@ def run_b200(args):
     def step():
         if world == 1:
             plan.ybar_density(logp, is_log=True, out=out)
+            return
+        if args.gather == "peer":
+            pc.evaluate_rows(plan, logp, 0, rows, cube_row0=r0)
+            dist.all_reduce(flag)      # stream-ordered barrier: all peer stores precede rank 0's next use
             return
         # sub-blocks of this rank's rows -> spaxel-major tiles, each shipped to rank 0 over NCCL
         # while the next one is computed; rank 0 transposes once to [n_fft, x1, x2]
@@ -361,7 +374,7 @@ def run_b200(args):
     ms_total = e0.elapsed_time(e1)
     ktimes = plan.kernel_times()
     plan.set_profiling(False)
-    launches = plan.launches - l0 + (args.steps if world > 1 and rank == 0 else 0)
+    launches = plan.launches - l0 + (args.steps if world > 1 and rank == 0 and args.gather == "nccl" else 0)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -502,6 +515,11 @@ def run_b200(args):
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        if args.gather == "peer":
+            torch.cuda.synchronize()
+            out = None
+            pc.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -112,6 +112,23 @@ PKM_API int32_t pkm_ybar_density(pkm_plan* plan, const double* dens, int32_t is_
                          int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
                          int32_t out_layout, void* stream);
 
+/* Multi-GPU variant of pkm_ybar_density: rows [row_begin,row_end) are written straight into a
+ * LARGER cube [n_fft][cube_nx1][nx2] at row offset cube_row0.  `cube` is device memory of this GPU
+ * or of a PEER GPU (a pointer obtained with pkm_ipc_open): the final transpose kernel stores over
+ * NVLink, so the cube of a sharded evaluation is assembled on rank 0 without a separate gather
+ * (each rank then needs one barrier before rank 0 reads the cube). */
+PKM_API int32_t pkm_ybar_density_into_cube(pkm_plan* plan, const double* dens, int32_t is_log,
+                                           int32_t nx1, int32_t nx2, int32_t row_begin,
+                                           int32_t row_end, double* cube, int32_t cube_nx1,
+                                           int32_t cube_row0, void* stream);
+/* CUDA IPC plumbing for the peer-memory cube (one process per GPU): export a 64-byte handle of a
+ * device allocation's BASE address, open it in another process, close it. */
+PKM_API int32_t pkm_device_alloc(int32_t device, int64_t bytes, void** ptr_out); /* plain cudaMalloc: IPC-exportable */
+PKM_API int32_t pkm_device_free(void* ptr);
+PKM_API int32_t pkm_ipc_export(const void* dev_ptr, uint8_t* handle64);
+PKM_API int32_t pkm_ipc_open(const uint8_t* handle64, int32_t device, void** ptr_out);
+PKM_API int32_t pkm_ipc_close(void* ptr);
+
 /* Gaussian-LOSVD path.  P_txz [nt][nx1][nx2][nz] (volume-weighted probabilities),
  * mu_v / sig_v addressed as base[t*s[0] + x1*s[1] + x2*s[2]] with ELEMENT strides
  * (0 strides allow numpy broadcast views, stream.py:126); omega [n_fft/2+1] is the

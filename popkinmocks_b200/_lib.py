@@ -53,6 +53,12 @@ SIGNATURES = {
     "pkm_plan_set_profiling": (_I32, [_P, _I32]),
     "pkm_plan_kernel_times": (_I32, [_P, _P, _P]),
     "pkm_ybar_density": (_I32, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P]),
+    "pkm_ybar_density_into_cube": (_I32, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P]),
+    "pkm_device_alloc": (_I32, [_I32, _I64, C.POINTER(_P)]),
+    "pkm_device_free": (_I32, [_P]),
+    "pkm_ipc_export": (_I32, [_P, _P]),
+    "pkm_ipc_open": (_I32, [_P, _I32, C.POINTER(_P)]),
+    "pkm_ipc_close": (_I32, [_P]),
     "pkm_ybar_gaussian": (_I32, [_P, _P, _P, C.POINTER(_I64), _P, C.POINTER(_I64), _P, _I32, _I32,
                                  _I32, _I32, _P, _I32, _P]),
     "pkm_axpy_cubes": (_I32, [_I32, C.POINTER(_P), _P, _I64, _P, _I32, _P]),

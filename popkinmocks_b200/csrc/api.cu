@@ -364,9 +364,11 @@ static void pipe_init(pkm_plan* pl) {
 // ----------------------------------------------------------------------------
 // density path
 // ----------------------------------------------------------------------------
-extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
-                                    int32_t nx2, int32_t row_begin, int32_t row_end,
-                                    double* ybar_out, int32_t out_layout, void* stream) {
+// cube_npix > 0: cube layout written into a larger cube [n_fft][cube_npix] at pixel offset
+// cube_pix0 (local or peer device memory); otherwise the output covers exactly the rows asked for.
+static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
+                            int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
+                            int32_t out_layout, int64_t cube_npix, int64_t cube_pix0, void* stream) {
   return guarded([&] {
     PKM_REQUIRE(pl && dens && ybar_out, "null argument");
     PKM_REQUIRE(nx1 >= 1 && nx2 >= 1 && row_begin >= 0 && row_end <= nx1 && row_begin <= row_end,
@@ -403,6 +405,12 @@ extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is
     cudaStream_t s_in = pl->s_copy, s_out = pl->s_comp;
     const bool pm = out_layout == PKM_LAYOUT_PIXEL_MAJOR;
     OutSpec o{ybar_out, out_host, out_layout, npix, n};
+    if (cube_npix > 0) {
+      PKM_REQUIRE(!out_host && !pm && cube_pix0 >= 0 && cube_pix0 + npix <= cube_npix,
+                  "embedded cube output needs a device buffer, cube layout and a valid offset");
+      o.npix_out = cube_npix;
+      o.out = ybar_out + cube_pix0;
+    }
 
     int64_t it = 0;
     for (int64_t p0 = 0; p0 < npix; p0 += tile, ++it) {
@@ -460,6 +468,61 @@ extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is
       PKM_CUDA(cudaStreamSynchronize(s_in));
     }
   });
+}
+
+extern "C" int32_t pkm_ybar_density(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
+                                    int32_t nx2, int32_t row_begin, int32_t row_end,
+                                    double* ybar_out, int32_t out_layout, void* stream) {
+  return density_impl(pl, dens, is_log, nx1, nx2, row_begin, row_end, ybar_out, out_layout, 0, 0, stream);
+}
+
+extern "C" int32_t pkm_ybar_density_into_cube(pkm_plan* pl, const double* dens, int32_t is_log,
+                                              int32_t nx1, int32_t nx2, int32_t row_begin,
+                                              int32_t row_end, double* cube, int32_t cube_nx1,
+                                              int32_t cube_row0, void* stream) {
+  if (cube_nx1 < 1 || cube_row0 < 0) {
+    pkm_set_error("bad cube geometry");
+    return PKM_ERR_INVALID;
+  }
+  return density_impl(pl, dens, is_log, nx1, nx2, row_begin, row_end, cube, PKM_LAYOUT_CUBE,
+                      (int64_t)cube_nx1 * nx2, (int64_t)cube_row0 * nx2, stream);
+}
+
+extern "C" int32_t pkm_device_alloc(int32_t device, int64_t bytes, void** ptr_out) {
+  return guarded([&] {
+    PKM_REQUIRE(ptr_out && bytes > 0, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible");
+    use_device(device);
+    PKM_CUDA(cudaMalloc(ptr_out, (size_t)bytes));
+  });
+}
+
+extern "C" int32_t pkm_device_free(void* ptr) {
+  return guarded([&] { PKM_CUDA(cudaFree(ptr)); });
+}
+
+extern "C" int32_t pkm_ipc_export(const void* dev_ptr, uint8_t* handle64) {
+  return guarded([&] {
+    PKM_REQUIRE(dev_ptr && handle64, "null argument");
+    cudaIpcMemHandle_t h;
+    PKM_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+  });
+}
+
+extern "C" int32_t pkm_ipc_open(const uint8_t* handle64, int32_t device, void** ptr_out) {
+  return guarded([&] {
+    PKM_REQUIRE(handle64 && ptr_out, "null argument");
+    use_device(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PKM_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+
+extern "C" int32_t pkm_ipc_close(void* ptr) {
+  return guarded([&] { PKM_CUDA(cudaIpcCloseMemHandle(ptr)); });
 }
 
 // ----------------------------------------------------------------------------

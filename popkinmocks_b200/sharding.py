@@ -138,3 +138,68 @@ class TileGather:
         if self.cuda and self.comm is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.comm)
         return self.full
+
+
+class PeerCube:
+    """The full cube [n_fft, nx1, nx2] on rank 0, written by every rank through peer memory.
+
+    Rank 0 allocates the cube and shares it over CUDA IPC; every other rank maps it and lets
+    the LAST kernel of its evaluation (the pixel-major -> cube transpose) store its rows straight
+    into rank 0's memory over NVLink (pkm_ybar_density_into_cube).  There is no gather step and
+    no extra pass over the cube on rank 0; one barrier per evaluation orders the peer stores
+    before rank 0 reads.  CUDA only (NCCL for the handle broadcast / barrier)."""
+
+    def __init__(self, n_fft, nx1, nx2, device, dist):
+        import ctypes as C
+        import torch
+        from . import _lib
+        self.dist, self.nx1, self.nx2, self.n_fft = dist, nx1, nx2, n_fft
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device(device)
+        self._peer_base = None
+        self._own_base = None
+        if self.rank == 0:
+            # a plain cudaMalloc allocation (torch's caching allocator sub-allocates and cannot be
+            # exported portably), viewed as a torch tensor through __cuda_array_interface__
+            base = C.c_void_p()
+            nbytes = n_fft * nx1 * nx2 * 8
+            _lib.check(_lib.load().pkm_device_alloc(self.device.index or 0, nbytes, C.byref(base)))
+            self._own_base = base
+            handle = (C.c_uint8 * 64)()
+            _lib.check(_lib.load().pkm_ipc_export(base, handle))
+
+            class _View:
+                __cuda_array_interface__ = {"shape": (n_fft, nx1, nx2), "typestr": "<f8",
+                                            "data": (base.value, False), "version": 3, "strides": None}
+            self.cube = torch.as_tensor(_View(), device=self.device)
+            payload = [bytes(handle), 0]
+            self.ptr = base.value
+        else:
+            self.cube = None
+            payload = [None, None]
+        dist.broadcast_object_list(payload, src=0)
+        if self.rank != 0:
+            handle = (C.c_uint8 * 64).from_buffer_copy(payload[0])
+            base = C.c_void_p()
+            _lib.check(_lib.load().pkm_ipc_open(handle, self.device.index or 0, C.byref(base)))
+            self._peer_base = base
+            self.ptr = base.value + payload[1]
+
+    def evaluate_rows(self, plan, dens, row_begin, row_end, cube_row0, is_log=True):
+        """Rows [row_begin,row_end) of this rank's density block -> rank 0's cube at `cube_row0`."""
+        import ctypes as C
+        from . import _lib
+        nx1_local = int(dens.shape[2])
+        _lib.check(_lib.load().pkm_ybar_density_into_cube(
+            plan._h, _lib.ptr(dens), int(bool(is_log)), nx1_local, self.nx2, int(row_begin), int(row_end),
+            C.c_void_p(self.ptr), self.nx1, int(cube_row0), None))
+
+    def close(self):
+        from . import _lib
+        if self._peer_base is not None:
+            _lib.load().pkm_ipc_close(self._peer_base)
+            self._peer_base = None
+        if self._own_base is not None:
+            self.cube = None
+            _lib.load().pkm_device_free(self._own_base)
+            self._own_base = None

@@ -191,3 +191,25 @@ def test_float32_option_within_1e5(gpu_ok, name, tags):
         err = rel_err(y32, g[tag + "ybar"])
         assert err < 1e-5, (name, tag, err)
         assert err > 1e-12      # it really is the float32 path
+
+
+def test_output_embedded_in_a_larger_cube(gpu_ok):
+    """pkm_ybar_density_into_cube: rows written at an offset of a larger [n_fft, nx1, nx2] buffer
+    (the multi-GPU path stores into rank 0's cube this way, through a peer pointer)."""
+    import ctypes as C
+    import torch
+    from popkinmocks_b200 import _lib
+    g = load_golden("g2_rebin_nv21_prime")
+    plan = _plan("g2_rebin_nv21_prime")
+    ref = g["wn_ybar"]                                   # [n_fft, 4, 5]
+    d = torch.from_numpy(g["wn_log_p_tvxz"]).cuda()
+    big = torch.full((plan.n_fft, 9, 5), -1.0, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().pkm_ybar_density_into_cube(plan._h, _lib.ptr(d), 1, 4, 5, 1, 4, _lib.ptr(big), 9, 5, None))
+    torch.cuda.synchronize()
+    out = big.cpu().numpy()
+    assert rel_err(out[:, 5:8], ref[:, 1:4]) < TOL
+    assert np.all(out[:, :5] == -1.0) and np.all(out[:, 8:] == -1.0)
+    # IPC handle round trip of a raw allocation (same process: export only)
+    h = (C.c_uint8 * 64)()
+    base = torch.empty(1 << 21, dtype=torch.uint8, device="cuda")
+    assert _lib.load().pkm_ipc_export(_lib.ptr(base), h) == 0 and any(h)
