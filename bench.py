@@ -294,39 +294,45 @@ def run_b200(args):
 
     # ---- this rank's share of the pixels
     from popkinmocks_b200 import sharding
+    # Pixels are independent, so the cube is sharded at PIXEL granularity (contiguous ranges of the
+    # flattened (x1, x2) index, sizes differing by at most one pixel): locally the range is handled
+    # as an (npix x 1) image, globally it is a contiguous slab of the cube's pixel axis.
     if world == 1:
-        nx1_total, r0, r1 = nx, 0, nx
-    elif args.scaling == "strong":            # ONE nx x nx cube, x1 rows sharded over the ranks
-        nx1_total = nx
-        r0, r1 = sharding.my_rows(nx, world, rank)
-    else:                                     # weak: a (world*nx) x nx mosaic, nx rows per rank
-        nx1_total = nx * world
-        r0, r1 = rank * nx, (rank + 1) * nx
-    rows = r1 - r0
-    npix = rows * nx
-    total_pix = nx1_total * nx
+        total_pix, r0, r1 = nx * nx, 0, nx * nx
+    elif args.scaling == "strong":            # ONE nx x nx cube sharded over the ranks
+        total_pix = nx * nx
+        r0, r1 = sharding.my_rows(total_pix, world, rank)
+    else:                                     # weak: a (world*nx) x nx mosaic, nx*nx pixels per rank
+        total_pix = nx * nx * world
+        r0, r1 = rank * nx * nx, (rank + 1) * nx * nx
+    if world == 1:
+        rows, nxl = nx, nx                    # keep the natural (nx, nx) image on one GPU
+    else:
+        rows, nxl = r1 - r0, 1
+    npix = rows * nxl
+    nx1_total = total_pix if world > 1 else nx
     voxels_per_step = total_pix * n_fft
 
     # ---- synthetic density (log p, as Component(cube, log_p_tvxz) holds it), generated on device
     gen = torch.Generator(device=dev).manual_seed(20241019 + rank)
-    logp = torch.empty((nt, nv, rows, nx, nz), dtype=torch.float64, device=dev)
+    logp = torch.empty((nt, nv, rows, nxl, nz), dtype=torch.float64, device=dev)
     for t in range(nt):                 # slab-wise to keep the temporary small
-        logp[t] = torch.rand((nv, rows, nx, nz), dtype=torch.float64, device=dev, generator=gen)
+        logp[t] = torch.rand((nv, rows, nxl, nz), dtype=torch.float64, device=dev, generator=gen)
     dV = float(np.mean(cube.ssps.delta_t) * np.mean(cube.ssps.delta_z) * cube.dx * cube.dy * cube.ssps.dv)
     logp.mul_(1.0 / (0.5 * nt * nv * total_pix * nz * dV)).clamp_(min=1e-300).log_()
 
     if world == 1:
-        out = torch.empty((n_fft, rows, nx), dtype=torch.float64, device=dev)
+        out = torch.empty((n_fft, rows, nxl), dtype=torch.float64, device=dev)
         tg = None
     elif args.gather == "peer":
         # rank 0 owns the cube; every rank's final transpose kernel stores its rows into it over NVLink
-        pc = sharding.PeerCube(n_fft, nx1_total, nx, dev, dist)
+        pc = sharding.PeerCube(n_fft, nx1_total, nxl, dev, dist)
         out = pc.cube
         tg = None
         flag = torch.zeros(1, device=dev)
     else:
-        tg = sharding.TileGather(nx1_total, nx, n_fft, dev, dist=dist, ntile=args.gather_tiles)
-        out = torch.empty((n_fft, nx1_total, nx), dtype=torch.float64, device=dev) if rank == 0 else None
+        tg = sharding.TileGather(nx1_total, nxl, n_fft, dev, dist=dist, ntile=args.gather_tiles)
+        out = torch.empty((n_fft, nx1_total, nxl), dtype=torch.float64, device=dev) if rank == 0 else None
 
     def step():
         if world == 1:
@@ -334,7 +340,8 @@ def run_b200(args):
             return
         if args.gather == "peer":
             pc.evaluate_rows(plan, logp, 0, rows, cube_row0=r0)
-            dist.all_reduce(flag)      # stream-ordered barrier: all peer stores precede rank 0's next use
+            if not os.environ.get("PKM_BENCH_NO_BARRIER"):
+                dist.all_reduce(flag)  # stream-ordered barrier: all peer stores precede rank 0's next use
             return
         # sub-blocks of this rank's rows -> spaxel-major tiles, each shipped to rank 0 over NCCL
         # while the next one is computed; rank 0 transposes once to [n_fft, x1, x2]
@@ -398,10 +405,10 @@ def run_b200(args):
             torch.cuda.synchronize()
             return a0.elapsed_time(a1) / reps
         other = {}
-        P = torch.rand((nt, rows, nx, nz), dtype=torch.float64, device=dev, generator=gen)
+        P = torch.rand((nt, rows, nxl, nz), dtype=torch.float64, device=dev, generator=gen)
         P /= P.sum()
-        mu_v = 400.0 * (torch.rand((nt, rows, nx), dtype=torch.float64, device=dev, generator=gen) - 0.5)
-        sig_v = 20.0 + 200.0 * torch.rand((nt, rows, nx), dtype=torch.float64, device=dev, generator=gen)
+        mu_v = 400.0 * (torch.rand((nt, rows, nxl), dtype=torch.float64, device=dev, generator=gen) - 0.5)
+        sig_v = 20.0 + 200.0 * torch.rand((nt, rows, nxl), dtype=torch.float64, device=dev, generator=gen)
         ms = timed(lambda: plan.ybar_gaussian(P, mu_v, sig_v, out=out))
         other["gaussian_path_A"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
                                     "ref": "ParametricComponent.evaluate_ybar parametric.py:335-407"}
@@ -425,7 +432,7 @@ def run_b200(args):
     # ---- e2e: same call through the C ABI with pinned host buffers
     e2e = None
     windows = [(w0, w1)]
-    host_bytes = world * (logp.numel() * 8 + n_fft * rows * nx * 8)
+    host_bytes = world * (logp.numel() * 8 + n_fft * rows * nxl * 8)
     try:
         import psutil
         ram = psutil.virtual_memory().total
@@ -437,7 +444,7 @@ def run_b200(args):
     elif not args.no_e2e:
         h_in = torch.empty(logp.shape, dtype=torch.float64, pin_memory=True)
         h_in.copy_(logp)
-        h_out = torch.empty((n_fft, rows, nx), dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty((n_fft, rows, nxl), dtype=torch.float64, pin_memory=True)
         np_in, np_out = h_in.numpy(), h_out.numpy()
         del logp
         torch.cuda.empty_cache()

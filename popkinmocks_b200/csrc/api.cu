@@ -395,13 +395,17 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
     if (out_host) per_px += 2 * sizeof(double) * n;
     int tile = pixel_tile(pl, npix, per_px);
     if (in_host || out_host) tile = std::min<int64_t>(tile, ((npix + 7) / 8 + 31) & ~int64_t(31));
+    // embedded (possibly peer-memory) cube: the transposes run on a side stream and overlap the
+    // next tile's kernels, so the NVLink stores of all ranks do not pile up at the end
+    const bool side_transpose = cube_npix > 0;
+    if (side_transpose) tile = std::min<int64_t>(tile, ((npix + 3) / 4 + 31) & ~int64_t(31));
     tile = std::max((tile / 32) * 32, 32);  // the coefficient layout groups pixels by 32
     (void)pxb;
 
     pl->coef.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
     pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
     pl->ypx.reserve(sizeof(double) * (size_t)n * tile);
-    if (in_host || out_host) pipe_init(pl);
+    if (in_host || out_host || side_transpose) pipe_init(pl);
     cudaStream_t s_in = pl->s_copy, s_out = pl->s_comp;
     const bool pm = out_layout == PKM_LAYOUT_PIXEL_MAJOR;
     OutSpec o{ybar_out, out_host, out_layout, npix, n};
@@ -435,6 +439,18 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
       launch_coeff(pl, src, is_log, src_npix, src_pix0, np, tile, pl->coef.as<double2>(), st);
       if (in_host) PKM_CUDA(cudaEventRecord(pl->ev_done[slot], st));
       launch_contract(pl, pl->coef.as<double2>(), np, tile, pl->yhat.as<double2>(), st);
+      if (side_transpose) {
+        // two pixel-major buffers (stage_out doubles as the second one)
+        pl->stage_out[slot].reserve(sizeof(double) * (size_t)n * tile);
+        double* ypx = pl->stage_out[slot].as<double>();
+        PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_out[slot], 0));      // transpose of tile it-2 has drained it
+        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, ypx, st);
+        PKM_CUDA(cudaEventRecord(pl->ev_ready[slot], st));
+        PKM_CUDA(cudaStreamWaitEvent(s_out, pl->ev_ready[slot], 0));
+        emit_tile(pl, o, ypx, p0, np, 0, s_out);
+        PKM_CUDA(cudaEventRecord(pl->ev_out[slot], s_out));
+        continue;
+      }
       if (!out_host) {
         launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
         emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);
@@ -461,6 +477,11 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
         PKM_CUDA(cudaMemcpy2DAsync(ybar_out + p0, sizeof(double) * npix, stage, sizeof(double) * np,
                                    sizeof(double) * np, n, cudaMemcpyDeviceToHost, s_out));
       PKM_CUDA(cudaEventRecord(pl->ev_out[slot], s_out));
+    }
+    if (side_transpose) {
+      // stream semantics for the caller: everything is complete once `st` reaches this point
+      PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_out[0], 0));
+      PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_out[1], 0));
     }
     if (in_host || out_host) {
       PKM_CUDA(cudaStreamSynchronize(st));
