@@ -29,40 +29,74 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
-// forward DIF: natural order in, digit-permuted order out
-__device__ void fft_forward(double2* s, int M, int logM, const double2* __restrict__ twp) {
+// forward DIF: natural order in, digit-permuted order out.
+// `in(idx)` supplies the inputs of the FIRST pass (so the caller's load / pre-multiply pass is
+// fused into it); if `post` is non-null every output of the LAST pass is multiplied by
+// post[idx] (the filter spectrum of the chirp-z convolution).
+struct SmemInput {
+  const double2* s;
+  __device__ __forceinline__ double2 operator()(int i) const { return s[i]; }
+};
+
+template <class In>
+__device__ void fft_forward(double2* s, int M, int logM, const double2* __restrict__ twp, In in,
+                            const double2* __restrict__ post) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   int Nb = M;
   for (; Nb >= 4; Nb >>= 2) {
     const int q = Nb >> 2;
+    const bool first = Nb == M;
+    const bool last = post != nullptr && q == 1;
     for (int i = tid; i < (M >> 2); i += nthr) {
       const int j = i & (q - 1);
       const int base = (i - j) * 4 + j;
-      double2 a = s[base], b = s[base + q], c = s[base + 2 * q], d = s[base + 3 * q];
+      double2 a, b, c, d;
+      if (first) {
+        a = in(base); b = in(base + q); c = in(base + 2 * q); d = in(base + 3 * q);
+      } else {
+        a = s[base]; b = s[base + q]; c = s[base + 2 * q]; d = s[base + 3 * q];
+      }
       double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
       double2 t3 = make_double2(bd.y, -bd.x);  // -i (b - d)
       double2 y0 = cadd(t0, t2), y1 = cadd(t1, t3), y2 = csub(t0, t2), y3 = csub(t1, t3);
       // per-pass twiddle table: W^(m j stride) at twp[M - 4q + (m-1) q + j], contiguous in j
       const double2* tp = twp + (M - 4 * q) + j;
+      y1 = cmul(y1, __ldg(tp));
+      y2 = cmul(y2, __ldg(tp + q));
+      y3 = cmul(y3, __ldg(tp + 2 * q));
+      if (last) {
+        y0 = cmul(y0, __ldg(post + base));
+        y1 = cmul(y1, __ldg(post + base + 1));
+        y2 = cmul(y2, __ldg(post + base + 2));
+        y3 = cmul(y3, __ldg(post + base + 3));
+      }
       s[base] = y0;
-      s[base + q] = cmul(y1, __ldg(tp));
-      s[base + 2 * q] = cmul(y2, __ldg(tp + q));
-      s[base + 3 * q] = cmul(y3, __ldg(tp + 2 * q));
+      s[base + q] = y1;
+      s[base + 2 * q] = y2;
+      s[base + 3 * q] = y3;
     }
     __syncthreads();
   }
   if (Nb == 2) {
     for (int i = tid; i < (M >> 1); i += nthr) {
       double2 a = s[2 * i], b = s[2 * i + 1];
-      s[2 * i] = cadd(a, b);
-      s[2 * i + 1] = csub(a, b);
+      double2 y0 = cadd(a, b), y1 = csub(a, b);
+      if (post) {
+        y0 = cmul(y0, __ldg(post + 2 * i));
+        y1 = cmul(y1, __ldg(post + 2 * i + 1));
+      }
+      s[2 * i] = y0;
+      s[2 * i + 1] = y1;
     }
     __syncthreads();
   }
 }
 
-// exact inverse of fft_forward up to the factor M: permuted order in, natural order out
-__device__ void fft_inverse(double2* s, int M, int logM, const double2* __restrict__ twp) {
+// exact inverse of fft_forward up to the factor M: permuted order in, natural order out.
+// The outputs of the LAST pass go to `out(idx, value)` instead of shared memory (fuses the
+// caller's post-multiply / store pass).
+template <class Out>
+__device__ void fft_inverse(double2* s, int M, int logM, const double2* __restrict__ twp, Out out) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   int Nb = 4;
   if (logM & 1) {
@@ -76,6 +110,7 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
   }
   for (; Nb <= M; Nb <<= 2) {
     const int q = Nb >> 2;
+    const bool last = Nb == M;
     for (int i = tid; i < (M >> 2); i += nthr) {
       const int j = i & (q - 1);
       const int base = (i - j) * 4 + j;
@@ -86,10 +121,17 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
       double2 y3 = cmulc(s[base + 3 * q], __ldg(tp + 2 * q));
       double2 u0 = cadd(y0, y2), u1 = csub(y0, y2), u2 = cadd(y1, y3), yd = csub(y1, y3);
       double2 u3 = make_double2(-yd.y, yd.x);  // +i (y1 - y3)
-      s[base] = cadd(u0, u2);
-      s[base + q] = cadd(u1, u3);
-      s[base + 2 * q] = csub(u0, u2);
-      s[base + 3 * q] = csub(u1, u3);
+      if (last) {
+        out(base, cadd(u0, u2));
+        out(base + q, cadd(u1, u3));
+        out(base + 2 * q, csub(u0, u2));
+        out(base + 3 * q, csub(u1, u3));
+      } else {
+        s[base] = cadd(u0, u2);
+        s[base + q] = cadd(u1, u3);
+        s[base + 2 * q] = csub(u0, u2);
+        s[base + 3 * q] = csub(u1, u3);
+      }
     }
     __syncthreads();
   }
@@ -102,9 +144,36 @@ k_filter_spectrum(const double2* __restrict__ bfilt, double2* __restrict__ Bhat,
   double2* s = scratch ? scratch : sbuf;
   for (int i = threadIdx.x; i < M; i += blockDim.x) s[i] = bfilt[i];
   __syncthreads();
-  fft_forward(s, M, logM, tw);
+  fft_forward(s, M, logM, tw, SmemInput{s}, nullptr);
   for (int i = threadIdx.x; i < M; i += blockDim.x) Bhat[i] = s[i];
 }
+
+// chirp-z input: alpha_k Yhat[k] chi[k] for k < nfo, zero above (numpy c2r semantics for DC/Nyquist)
+struct CztInput {
+  const double2* yin;
+  const double2* chi;
+  const double* alpha;
+  int nfo;
+  __device__ __forceinline__ double2 operator()(int k) const {
+    if (k >= nfo) return make_double2(0.0, 0.0);
+    double2 a = yin[k];
+    const double al = __ldg(alpha + k);
+    if (al == 1.0) a.y = 0.0;  // DC / Nyquist: imaginary part ignored
+    a.x *= al;
+    a.y *= al;
+    return cmul(a, __ldg(chi + k));
+  }
+};
+// chirp-z output: y[m] = Re(chi[m] z[m]) * scale for m < n
+struct CztOutput {
+  double* yo;
+  const double2* chi;
+  int n;
+  double scale;
+  __device__ __forceinline__ void operator()(int m, double2 v) const {
+    if (m < n) yo[m] = cmul(__ldg(chi + m), v).x * scale;
+  }
+};
 
 __global__ void __launch_bounds__(CZT_THREADS)
 k_irfft_czt(const double2* __restrict__ yhat, long long npix, int n, int nfo, int M, int logM,
@@ -113,32 +182,11 @@ k_irfft_czt(const double2* __restrict__ yhat, long long npix, int n, int nfo, in
             double* __restrict__ out, double2* scratch) {
   extern __shared__ double2 sbuf[];
   double2* s = scratch ? scratch + (size_t)blockIdx.x * M : sbuf;
-  const int tid = threadIdx.x, nthr = blockDim.x;
   for (long long x = blockIdx.x; x < npix; x += gridDim.x) {
-    const double2* yin = yhat + (size_t)x * nfo;
-    for (int k = tid; k < M; k += nthr) {
-      double2 v = make_double2(0.0, 0.0);
-      if (k < nfo) {
-        double2 a = yin[k];
-        const double al = alpha[k];
-        if (al == 1.0) a.y = 0.0;  // DC / Nyquist: imaginary part ignored (numpy c2r)
-        a.x *= al;
-        a.y *= al;
-        v = cmul(a, __ldg(chi + k));
-      }
-      s[k] = v;
-    }
-    __syncthreads();
-    fft_forward(s, M, logM, tw);
-    for (int i = tid; i < M; i += nthr) s[i] = cmul(s[i], __ldg(Bhat + i));
-    __syncthreads();
-    fft_inverse(s, M, logM, tw);
-    double* yo = out + (size_t)x * n;
-    for (int m = tid; m < n; m += nthr) {
-      double2 v = cmul(__ldg(chi + m), s[m]);
-      yo[m] = v.x * scale;
-    }
-    __syncthreads();
+    // load + chirp pre-multiply fused into the first forward pass, the filter multiply into the
+    // last forward pass, the chirp post-multiply + store into the last inverse pass
+    fft_forward(s, M, logM, tw, CztInput{yhat + (size_t)x * nfo, chi, alpha, nfo}, Bhat);
+    fft_inverse(s, M, logM, tw, CztOutput{out + (size_t)x * n, chi, n, scale});
   }
 }
 
