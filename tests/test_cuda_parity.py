@@ -213,3 +213,35 @@ def test_output_embedded_in_a_larger_cube(gpu_ok):
     h = (C.c_uint8 * 64)()
     base = torch.empty(1 << 21, dtype=torch.uint8, device="cuda")
     assert _lib.load().pkm_ipc_export(_lib.ptr(base), h) == 0 and any(h)
+
+
+@pytest.mark.parametrize("ssp_kw,nv,nx", [
+    (dict(lmd_min=3540.5, lmd_max=7409.6), 101, (2, 3)),   # full-resolution MILES range: n_fft = 11179 = 7*1597, M = 32768 (global-scratch FFT)
+    (dict(age_rebin=8, z_rebin=4), 7, (3, 3)),             # smallest velocity grid the cubic spline admits (nfi = 4)
+    (dict(age_rebin=8, z_rebin=12), 127, (1, 5)),          # largest supported nv (nfi = 64), a single metallicity bin
+    (dict(age_rebin=53, z_rebin=3), 33, (1, 1)),           # one age bin, one pixel
+])
+def test_edge_configurations_against_oracle(gpu_ok, ssp_kw, nv, nx):
+    """Shapes the golden files do not cover, checked against the oracle (which
+    tests/test_oracle.py pins to the reference)."""
+    from oracle import restatement as R
+    import popkinmocks_b200 as pkm
+    ssps = pkm.milesSSPs(**ssp_kw)
+    cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx[0], nx2=nx[1], nv=nv, vrng=(-1000.0, 1000.0))
+    plan = pkm.engine.get_plan(cube)
+    nz, nt = ssps.par_dims
+    rng = np.random.default_rng(nv)
+    p = rng.random(cube.get_distribution_shape("tvxz"))
+    p /= np.sum(p * cube.construct_volume_element("tvxz"))
+    y = plan.ybar_density(np.log(p), is_log=True)
+    ref = R.ybar_density_literal(p, cube.v_edg, ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv, ssps.delta_t,
+                                 ssps.delta_z, cube.dx, cube.dy, pixel_block=1)
+    assert y.shape == ref.shape == (ssps.n_fft, nx[0], nx[1])
+    assert rel_err(y, ref) < TOL, (ssps.n_fft, rel_err(y, ref))
+    P = rng.random((nt, nx[0], nx[1], nz))
+    P /= P.sum()
+    mu = 500.0 * (rng.random((nt, nx[0], nx[1])) - 0.5)
+    sg = 15.0 + 250.0 * rng.random((nt, nx[0], nx[1]))
+    ya = plan.ybar_gaussian(P, mu, sg)
+    ra = R.ybar_gaussian(P, mu, sg, ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv)
+    assert rel_err(ya, ra) < TOL, (ssps.n_fft, rel_err(ya, ra))

@@ -11,7 +11,8 @@ from popkinmocks_b200 import engine
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 nv = int(sys.argv[2]) if len(sys.argv) > 2 else 101
-ssps = pkm.milesSSPs()
+lmd = (float(sys.argv[3]), float(sys.argv[4])) if len(sys.argv) > 4 else (4700.0, 6500.0)
+ssps = pkm.milesSSPs(lmd_min=lmd[0], lmd_max=lmd[1])
 cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx, nx2=nx, nv=nv, vrng=(-1000.0, 1000.0))
 plan = engine.get_plan(cube)
 print("n_fft", plan.n_fft, "fp64 peak TF", engine.fp64_fma_peak())
