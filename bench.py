@@ -427,6 +427,20 @@ def run_b200(args):
         ms = timed(lambda: engine.noise(out, 100.0, 0, seed=1, want_sigma=False))
         other["shot_noise"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
                                "ref": "ShotNoise.get_noisy_data noise.py:16-71"}
+        # the same cube over the full MILES wavelength range (3540-7410 A): n_fft = 11179 = 7*1597,
+        # 2.3x more voxels per pixel; the inverse FFT no longer fits shared memory (M = 32768)
+        import popkinmocks_b200 as pkm
+        ssps_full = pkm.milesSSPs(lmd_min=3540.5, lmd_max=7409.6)
+        cube_full = pkm.ifu_cube.IFUCube(ssps=ssps_full, nx1=nx, nx2=nx, nv=nv, x1rng=(-1.0, 1.0), x2rng=(-1.0, 1.0),
+                                         vrng=(-1000.0, 1000.0))
+        plan_full = engine.Plan(cube_full, device=local)
+        out_full = torch.empty((plan_full.n_fft, rows, nxl), dtype=torch.float64, device=dev)
+        ms = timed(lambda: plan_full.ybar_density(logp, is_log=True, out=out_full), reps=2)
+        other["density_path_B_full_wavelength_range"] = {
+            "voxel_per_s": total_pix * plan_full.n_fft / (ms * 1e-3), "ms": ms, "n_fft": plan_full.n_fft,
+            "note": "milesSSPs(lmd_min=3540.5, lmd_max=7409.6): the 'full-resolution MILES' variant of SURVEY.md 8d C4"}
+        plan_full.close()
+        del plan_full, out_full
         torch.cuda.empty_cache()
 
     # ---- e2e: same call through the C ABI with pinned host buffers

@@ -190,6 +190,115 @@ k_irfft_czt(const double2* __restrict__ yhat, long long npix, int n, int nfo, in
   }
 }
 
+// ----------------------------------------------------------------------------
+// four-step variant for M = R * C > shared memory (C = 4096 in smem, R <= 16 rows in a CTA-private,
+// L2-resident global scratch g[R][C]):
+//   forward: column DFTs of length R (direct, R^2 complex MACs per column) with the twiddle
+//            W_M^(n2 k1), then R shared-memory transforms of length C (output row k1 holds the
+//            frequencies k1 + R k2 in the digit-permuted order of fft_forward);
+//   inverse: the exact reverse.  4 passes over the scratch instead of ~2 log4(M).
+// ----------------------------------------------------------------------------
+struct RowInput {
+  const double2* row;
+  __device__ __forceinline__ double2 operator()(int i) const { return row[i]; }
+};
+struct RowOutput {
+  double2* row;
+  __device__ __forceinline__ void operator()(int i, double2 v) const { row[i] = v; }
+};
+
+template <int R, class In>
+__device__ void fft4_forward(double2* g, double2* s, int C, int logC, const double2* __restrict__ tw,
+                             In in, const double2* __restrict__ post) {
+  constexpr int CZT4_MAXR = R;
+  const double2* twM = tw + C;       // W_M^(n2)
+  const double2* twR = tw + 2 * C;   // W_R^(j)
+  for (int n2 = threadIdx.x; n2 < C; n2 += blockDim.x) {
+    double2 x[CZT4_MAXR];
+#pragma unroll
+    for (int n1 = 0; n1 < CZT4_MAXR; ++n1)
+      if (n1 < R) x[n1] = in(n1 * C + n2);
+    const double2 w1 = __ldg(twM + n2);
+    double2 wk = make_double2(1.0, 0.0);            // W_M^(n2 k1)
+    for (int k1 = 0; k1 < R; ++k1) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int n1 = 0; n1 < CZT4_MAXR; ++n1)
+        if (n1 < R) {
+          const double2 w = __ldg(twR + ((n1 * k1) & (R - 1)));
+          acc.x = fma(x[n1].x, w.x, fma(-x[n1].y, w.y, acc.x));
+          acc.y = fma(x[n1].x, w.y, fma(x[n1].y, w.x, acc.y));
+        }
+      g[(size_t)k1 * C + n2] = cmul(acc, wk);
+      wk = cmul(wk, w1);
+    }
+  }
+  __syncthreads();
+  for (int k1 = 0; k1 < R; ++k1) {
+    fft_forward(s, C, logC, tw, RowInput{g + (size_t)k1 * C}, post ? post + (size_t)k1 * C : nullptr);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) g[(size_t)k1 * C + i] = s[i];
+    __syncthreads();
+  }
+}
+
+template <int R, class Out>
+__device__ void fft4_inverse(double2* g, double2* s, int C, int logC, const double2* __restrict__ tw,
+                             Out out) {
+  constexpr int CZT4_MAXR = R;
+  const double2* twM = tw + C;
+  const double2* twR = tw + 2 * C;
+  for (int k1 = 0; k1 < R; ++k1) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s[i] = g[(size_t)k1 * C + i];
+    __syncthreads();
+    fft_inverse(s, C, logC, tw, RowOutput{g + (size_t)k1 * C});
+  }
+  for (int n2 = threadIdx.x; n2 < C; n2 += blockDim.x) {
+    double2 y[CZT4_MAXR];
+    const double2 w1 = __ldg(twM + n2);
+    double2 wk = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int k1 = 0; k1 < CZT4_MAXR; ++k1)
+      if (k1 < R) {
+        y[k1] = cmulc(g[(size_t)k1 * C + n2], wk);   // undo W_M^(n2 k1)
+        wk = cmul(wk, w1);
+      }
+    for (int n1 = 0; n1 < R; ++n1) {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int k1 = 0; k1 < CZT4_MAXR; ++k1)
+        if (k1 < R) {
+          const double2 w = __ldg(twR + ((n1 * k1) & (R - 1)));   // conjugate applied below
+          acc.x = fma(y[k1].x, w.x, fma(y[k1].y, w.y, acc.x));
+          acc.y = fma(y[k1].y, w.x, fma(-y[k1].x, w.y, acc.y));
+        }
+      out(n1 * C + n2, acc);
+    }
+  }
+  __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(512)
+k_filter_spectrum4(const double2* __restrict__ bfilt, double2* __restrict__ Bhat, int C, int logC,
+                   const double2* __restrict__ tw) {
+  extern __shared__ double2 sbuf[];
+  fft4_forward<R>(Bhat, sbuf, C, logC, tw, RowInput{bfilt}, nullptr);   // Bhat doubles as the scratch
+}
+
+template <int R>
+__global__ void __launch_bounds__(256, 2)
+k_irfft_czt4(const double2* __restrict__ yhat, long long npix, int n, int nfo, int C, int logC,
+             double scale, const double2* __restrict__ chi, const double* __restrict__ alpha,
+             const double2* __restrict__ tw, const double2* __restrict__ Bhat,
+             double* __restrict__ out, double2* scratch) {
+  extern __shared__ double2 sbuf[];
+  double2* g = scratch + (size_t)blockIdx.x * R * C;
+  for (long long x = blockIdx.x; x < npix; x += gridDim.x) {
+    fft4_forward<R>(g, sbuf, C, logC, tw, CztInput{yhat + (size_t)x * nfo, chi, alpha, nfo}, Bhat);
+    fft4_inverse<R>(g, sbuf, C, logC, tw, CztOutput{out + (size_t)x * n, chi, n, scale});
+  }
+}
+
 // O(n * nfo) reference transform with exact integer phase reduction (tests only)
 __global__ void __launch_bounds__(256)
 k_irfft_naive(const double2* __restrict__ yhat, int n, int nfo, double scale,
@@ -240,26 +349,46 @@ __global__ void k_axpy(int n_cmps, const double* const* __restrict__ ptrs,
 
 }  // namespace
 
-static constexpr int CZT_SMEM_MAX_M = 8192;
+template <int R>
+static void filter4_t(pkm_plan* pl, const double2* d_b) {
+  const CztTables& c = pl->czt;
+  const size_t smem = sizeof(double2) * c.C;
+  PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_filter_spectrum4<R><<<1, 512, smem>>>(d_b, pl->d_Bhat, c.C, c.logC, pl->d_twiddle);
+}
 
 void czt_prepare_filter(pkm_plan* pl) {
   const CztTables& c = pl->czt;
   double2* d_b = nullptr;
   PKM_CUDA(cudaMalloc(&d_b, sizeof(double2) * c.M));
   PKM_CUDA(cudaMemcpy(d_b, c.bfilt.data(), sizeof(double2) * c.M, cudaMemcpyHostToDevice));
-  size_t smem = 0;
-  double2* scratch = nullptr;
-  if (c.M <= CZT_SMEM_MAX_M) {
-    smem = sizeof(double2) * c.M;
+  if (c.R == 1) {
+    const size_t smem = sizeof(double2) * c.M;
     PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_filter_spectrum<<<1, 256, smem>>>(d_b, pl->d_Bhat, c.M, c.logM, pl->d_twiddle, nullptr);
   } else {
-    PKM_CUDA(cudaMalloc(&scratch, sizeof(double2) * c.M));
+    switch (c.R) {
+      case 2: filter4_t<2>(pl, d_b); break;
+      case 4: filter4_t<4>(pl, d_b); break;
+      case 8: filter4_t<8>(pl, d_b); break;
+      case 16: filter4_t<16>(pl, d_b); break;
+      default: PKM_THROW(PKM_ERR_INVALID, "n_fft=%d too long for the inverse FFT (M=%d)", c.n, c.M);
+    }
   }
-  k_filter_spectrum<<<1, 256, smem>>>(d_b, pl->d_Bhat, c.M, c.logM, pl->d_twiddle, scratch);
   PKM_CUDA(cudaGetLastError());
   PKM_CUDA(cudaDeviceSynchronize());
   cudaFree(d_b);
-  if (scratch) cudaFree(scratch);
+}
+
+template <int R>
+static void irfft4_t(pkm_plan* pl, const double2* yhat, int64_t npix, double s, double* out, cudaStream_t st) {
+  const CztTables& c = pl->czt;
+  const size_t smem = sizeof(double2) * c.C;
+  PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * 2);
+  pl->misc.reserve(sizeof(double2) * (size_t)c.M * grid);
+  k_irfft_czt4<R><<<grid, 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.C, c.logC, s, pl->d_chi, pl->d_alpha,
+                                          pl->d_twiddle, pl->d_Bhat, out, pl->misc.as<double2>());
 }
 
 void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double scale, double* out,
@@ -267,22 +396,23 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
   if (npix <= 0) return;
   const CztTables& c = pl->czt;
   const double s = scale / ((double)c.M * (double)c.n);
-  size_t smem = 0;
-  double2* scratch = nullptr;
-  int grid;
-  if (c.M <= CZT_SMEM_MAX_M) {
-    smem = sizeof(double2) * c.M;
-    PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
-    grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
-  } else {
-    grid = (int)std::min<int64_t>(npix, pl->num_sms);
-    pl->misc.reserve(sizeof(double2) * (size_t)c.M * grid);
-    scratch = pl->misc.as<double2>();
-  }
   KernelTimer tm(pl, PKM_K_IRFFT, st);
-  k_irfft_czt<<<grid, c.M >= 4096 ? CZT_THREADS : 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_chi, pl->d_alpha,
-                                       pl->d_twiddle, pl->d_Bhat, out, scratch);
+  if (c.R == 1) {
+    const size_t smem = sizeof(double2) * c.M;
+    PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+    const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
+    k_irfft_czt<<<grid, c.M >= 4096 ? CZT_THREADS : 256, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_chi,
+                                                                    pl->d_alpha, pl->d_twiddle, pl->d_Bhat, out, nullptr);
+  } else {
+    switch (c.R) {
+      case 2: irfft4_t<2>(pl, yhat, npix, s, out, st); break;
+      case 4: irfft4_t<4>(pl, yhat, npix, s, out, st); break;
+      case 8: irfft4_t<8>(pl, yhat, npix, s, out, st); break;
+      case 16: irfft4_t<16>(pl, yhat, npix, s, out, st); break;
+      default: PKM_THROW(PKM_ERR_INVALID, "n_fft=%d too long for the inverse FFT (M=%d)", c.n, c.M);
+    }
+  }
   PKM_CUDA(cudaGetLastError());
   pl->launches++;
 }

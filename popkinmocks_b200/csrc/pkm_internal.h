@@ -84,6 +84,7 @@ void build_wseg_tables(const SplineTables& sp, WsegTables& out);
 // chirp-z tables for the arbitrary-length inverse real FFT
 struct CztTables {
   int n = 0, nfo = 0, M = 0, logM = 0;
+  int R = 1, C = 0, logC = 0;  // four-step split M = R * C used when M does not fit shared memory
   std::vector<double> chi;     // [n] complex: exp(+i*pi*j^2/n)
   std::vector<double> alpha;   // [nfo] weights 1,2,...,2,(1 if n even)
   std::vector<double> twiddle; // [M] complex: exp(-2*pi*i*j/M)

@@ -220,20 +220,39 @@ void build_czt_tables(int n, CztTables& out) {
   out.alpha.assign(out.nfo, 2.0);
   out.alpha[0] = 1.0;
   if (n % 2 == 0) out.alpha[out.nfo - 1] = 1.0;
-  // per-pass radix-4 twiddles, contiguous in the butterfly index j: the pass with quarter
-  // size q (block Nb = 4q, stride = M/Nb) reads W_M^(m j stride), m = 1..3, at
-  // [M - 4q + (m-1) q + j]; the passes q = M/4, M/16, ... fill [0, M - 4 q_min).
-  out.twiddle.assign(size_t(2) * M, 0.0);
-  for (int Nb = M; Nb >= 4; Nb >>= 2) {
-    const int q = Nb >> 2, stride = M / Nb;
+  // Transforms that fit shared memory (M <= 8192) run in one piece (R = 1, C = M); larger ones
+  // use the four-step split M = R * C with C = 4096: R-point DFTs down the columns, twiddles
+  // W_M^(n2 k1), then R shared-memory transforms of length C.
+  out.C = M <= 8192 ? M : 4096;
+  out.R = M / out.C;
+  out.logC = 0;
+  while ((1 << out.logC) < out.C) ++out.logC;
+  const int C = out.C, R = out.R;
+  // layout: [0, C) per-pass radix-4 twiddles of the length-C transform, contiguous in the
+  // butterfly index j: the pass with quarter size q (block Nb = 4q, stride = C/Nb) reads
+  // W_C^(m j stride), m = 1..3, at [C - 4q + (m-1) q + j];  [C, 2C) W_M^(n2), n2 < C;
+  // [2C, 2C + R) W_R^(j).
+  out.twiddle.assign(size_t(2) * (2 * size_t(C) + R), 0.0);
+  for (int Nb = C; Nb >= 4; Nb >>= 2) {
+    const int q = Nb >> 2, stride = C / Nb;
     for (int m = 1; m <= 3; ++m)
       for (int j = 0; j < q; ++j) {
-        const long long idx = ((long long)m * j * stride) % M;
-        long double ang = -2.0L * PI_L * (long double)idx / (long double)M;
-        const size_t pos = size_t(M - 4 * q) + size_t(m - 1) * q + j;
+        const long long idx = ((long long)m * j * stride) % C;
+        long double ang = -2.0L * PI_L * (long double)idx / (long double)C;
+        const size_t pos = size_t(C - 4 * q) + size_t(m - 1) * q + j;
         out.twiddle[2 * pos] = (double)cosl(ang);
         out.twiddle[2 * pos + 1] = (double)sinl(ang);
       }
+  }
+  for (int j = 0; j < C; ++j) {
+    long double ang = -2.0L * PI_L * (long double)j / (long double)M;
+    out.twiddle[2 * (size_t(C) + j)] = (double)cosl(ang);
+    out.twiddle[2 * (size_t(C) + j) + 1] = (double)sinl(ang);
+  }
+  for (int j = 0; j < R; ++j) {
+    long double ang = -2.0L * PI_L * (long double)j / (long double)R;
+    out.twiddle[2 * (2 * size_t(C) + j)] = (double)cosl(ang);
+    out.twiddle[2 * (2 * size_t(C) + j) + 1] = (double)sinl(ang);
   }
   // z[m] = chi[m] * sum_k (a[k] chi[k]) conj(chi[m-k]),  m-k in [-(nfo-1), n-1]
   out.bfilt.assign(size_t(2) * M, 0.0);
