@@ -382,7 +382,15 @@ def run_b200(args):
     ktimes = plan.kernel_times()
     plan.set_profiling(False)
     launches = plan.launches - l0 + (args.steps if world > 1 and rank == 0 and args.gather == "nccl" else 0)
+    per_rank = None
     if world > 1:
+        # diagnostics: every rank's own step time and kernel sum (the headline uses the MAX)
+        mine = torch.tensor([ms_total / args.steps, sum(m for m, _ in ktimes.values()) / args.steps],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"step_ms": [round(float(a[0]), 3) for a in allr],
+                    "kernel_sum_ms": [round(float(a[1]), 3) for a in allr]}
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
@@ -532,7 +540,7 @@ def run_b200(args):
                              "compulsory": {"bytes_per_voxel": b_min, "achieved": b_min * per_gpu / 1e9,
                                             "frac": b_min * per_gpu / 1e9 / hbm_peak},
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
-            "kernels": kern, "other_paths": other, "cpu_baseline": cpu, "clocks": clocks,
+            "kernels": kern, "per_rank": per_rank, "other_paths": other, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -114,9 +114,10 @@ PKM_API int32_t pkm_ybar_density(pkm_plan* plan, const double* dens, int32_t is_
 
 /* Multi-GPU variant of pkm_ybar_density: rows [row_begin,row_end) are written straight into a
  * LARGER cube [n_fft][cube_nx1][nx2] at row offset cube_row0.  `cube` is device memory of this GPU
- * or of a PEER GPU (a pointer obtained with pkm_ipc_open): the final transpose kernel stores over
- * NVLink, so the cube of a sharded evaluation is assembled on rank 0 without a separate gather
- * (each rank then needs one barrier before rank 0 reads the cube). */
+ * or of a PEER GPU (a pointer obtained with pkm_ipc_open): every pixel tile is transposed locally
+ * and moved into the cube by one strided 2-D copy-engine transfer over NVLink on a side stream,
+ * overlapped with the next tile's kernels, so the cube of a sharded evaluation is assembled on
+ * rank 0 without a separate gather pass (each rank needs one barrier before rank 0 reads). */
 PKM_API int32_t pkm_ybar_density_into_cube(pkm_plan* plan, const double* dens, int32_t is_log,
                                            int32_t nx1, int32_t nx2, int32_t row_begin,
                                            int32_t row_end, double* cube, int32_t cube_nx1,

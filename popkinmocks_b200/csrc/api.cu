@@ -136,6 +136,7 @@ static void plan_free(pkm_plan* pl) {
   for (int i = 0; i < 2; ++i) {
     pl->stage_in[i].release();
     pl->stage_out[i].release();
+    pl->cube_stage[i].release();
   }
   delete pl;
 }
@@ -447,7 +448,18 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
         launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, ypx, st);
         PKM_CUDA(cudaEventRecord(pl->ev_ready[slot], st));
         PKM_CUDA(cudaStreamWaitEvent(s_out, pl->ev_ready[slot], 0));
-        emit_tile(pl, o, ypx, p0, np, 0, s_out);
+        // transpose locally, then let a copy engine move the [n][np] block into the (possibly
+        // remote) cube as one strided 2-D copy: DMA bursts use NVLink far better than the
+        // 256-byte stores of a kernel writing to a peer, and cost no SM time
+        pl->cube_stage[slot].reserve(sizeof(double) * (size_t)n * tile);
+        double* cs = pl->cube_stage[slot].as<double>();
+        {
+          KernelTimer tm(pl, PKM_K_TRANSPOSE, s_out);
+          launch_transpose(ypx, np, n, cs, np, 0, s_out);
+        }
+        pl->launches++;
+        PKM_CUDA(cudaMemcpy2DAsync(o.out + p0, sizeof(double) * (size_t)o.npix_out, cs, sizeof(double) * (size_t)np,
+                                   sizeof(double) * (size_t)np, (size_t)n, cudaMemcpyDefault, s_out));
         PKM_CUDA(cudaEventRecord(pl->ev_out[slot], s_out));
         continue;
       }

@@ -147,7 +147,7 @@ struct pkm_plan {
   std::vector<double> h_delta_t, h_delta_z;
 
   // workspace
-  DevBuf coef, yhat, ypx, stage_in[2], stage_out[2], misc, small;
+  DevBuf coef, yhat, ypx, stage_in[2], stage_out[2], cube_stage[2], misc, small;
   // host-buffer pipeline: s_copy = H2D stream, s_comp = D2H stream; per staging slot:
   // ev_in (H2D landed), ev_done (kernel 1 consumed it), ev_ready (output staged), ev_out (D2H done)
   cudaStream_t s_copy = nullptr, s_comp = nullptr;

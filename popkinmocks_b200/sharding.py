@@ -143,11 +143,11 @@ class TileGather:
 class PeerCube:
     """The full cube [n_fft, nx1, nx2] on rank 0, written by every rank through peer memory.
 
-    Rank 0 allocates the cube and shares it over CUDA IPC; every other rank maps it and lets
-    the LAST kernel of its evaluation (the pixel-major -> cube transpose) store its rows straight
-    into rank 0's memory over NVLink (pkm_ybar_density_into_cube).  There is no gather step and
-    no extra pass over the cube on rank 0; one barrier per evaluation orders the peer stores
-    before rank 0 reads.  CUDA only (NCCL for the handle broadcast / barrier)."""
+    Rank 0 allocates the cube and shares it over CUDA IPC; every other rank maps it and moves
+    each finished pixel tile (transposed locally) into rank 0's memory with one strided 2-D
+    copy-engine transfer over NVLink, overlapped with the next tile's kernels
+    (pkm_ybar_density_into_cube).  There is no gather pass on rank 0; one barrier per evaluation
+    orders the peer writes before rank 0 reads.  CUDA only (NCCL for the handle broadcast / barrier)."""
 
     def __init__(self, n_fft, nx1, nx2, device, dist):
         import ctypes as C
