@@ -1,6 +1,10 @@
 """Turn an .ncu-rep (ncu --set full) into a markdown summary and per-kernel DRAM traffic JSON.
 
-usage: python tools/ncu_summarise.py <report.ncu-rep> <out.md> [<traffic.json> <npix_per_step>]
+usage: python tools/ncu_summarise.py <report.ncu-rep> <out.md> [<traffic.json> <npix_per_step> [<px_captured_launch> <launches_per_step> [note...]]]
+
+If the captured launches cover <px_captured_launch> pixels each but the step's launches average
+npix_per_step / launches_per_step pixels, the per-launch traffic is scaled by that ratio (traffic
+is proportional to the pixels of a launch).
 """
 import csv
 import io
@@ -34,7 +38,7 @@ def main():
     traffic = {}
     with open(out_md, "w") as f:
         f.write(f"# ncu --set full --clock-control none summary of `{rep.split('/')[-1]}`\n\n")
-        f.write(" ".join(sys.argv[5:]) + "\n\n" if len(sys.argv) > 5 else "")
+        f.write(" ".join(sys.argv[7:]) + "\n\n" if len(sys.argv) > 7 else "")
         for name, rs in per_kernel.items():
             f.write(f"## {name} ({len(rs)} launches captured)\n\n| metric | " + " | ".join(f"launch {i}" for i in range(len(rs))) + " | unit |\n")
             f.write("|---|" + "---|" * (len(rs) + 1) + "\n")
@@ -49,12 +53,16 @@ def main():
             f.write(f"\nDRAM traffic (read+write) per launch, mean of the captured launches: {tot / len(rs) / 1e9:.3f} GB\n\n")
     if len(sys.argv) > 4:
         npix = int(sys.argv[4])
+        scale = 1.0
+        if len(sys.argv) > 6:
+            scale = (npix / float(sys.argv[6])) / float(sys.argv[5])
         short = {"k_contract": "contract", "k_coeff<7>": "coeff", "k_irfft_czt": "irfft"}
         out = {}
         for name, t in traffic.items():
             for key, s in short.items():
                 if name.startswith(key.split("<")[0]):
-                    out[s] = {"npix": npix, "dram_bytes_per_launch": t["dram_bytes_per_launch"],
+                    out[s] = {"npix": npix, "dram_bytes_per_launch": t["dram_bytes_per_launch"] * scale,
+                              "dram_bytes_per_captured_launch": t["dram_bytes_per_launch"],
                               "launches_captured": t["launches"], "source": rep.split("/")[-1]}
         json.dump(out, open(sys.argv[3], "w"), indent=1)
     print(json.dumps(traffic, indent=1))
