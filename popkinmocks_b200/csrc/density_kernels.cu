@@ -428,7 +428,7 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 constexpr int K2_WARPS = 4;
 constexpr int K2_STAGES = 3;
 constexpr int K2_CTAS_PER_SM = 3;
-constexpr int K2_PF = 6;       // L2 prefetch distance of the coefficient rows in (t,z) steps
+constexpr int K2_PF = 12;      // L2 prefetch distance of the coefficient rows in (t,z) steps
 constexpr int K2_G = 2;        // frequencies whose FMA chains are interleaved (PKM_KT % K2_G == 0)
 constexpr int K2_CHUNK_ELEMS = PKM_TZC * PKM_KT;                      // double2 per staged chunk
 constexpr unsigned K2_CHUNK_BYTES = K2_CHUNK_ELEMS * sizeof(double2);  // 1920
@@ -508,8 +508,11 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
       cp += (tz + 1 < ntz) ? c_step : 0;  // branch-free: the last step re-reads its own rows
       // the coefficient tile streams from HBM: each warp pulls one of the span's 4 rows a few
       // steps ahead into L2 (the ~5 warps of a span cover all four), hiding the DRAM latency
-      if (tz + K2_PF < ntz)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)(K2_PF - 1) * c_step + (ws & 3) * 32));
+      if (tz + K2_PF < ntz) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)(K2_PF - 1) * c_step + q * 32));
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + q * 32);
       // B200's FP64 pipe needs >= 4 independent DFMAs per warp to reach its issue rate (8-cycle

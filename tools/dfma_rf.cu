@@ -1,8 +1,10 @@
 // Development probe: DFMA throughput with 1, 2, 3 distinct register source operands.
 #include <cstdio>
 #include <cuda_runtime.h>
+__constant__ double cw[64];
+struct WP { double w[1024]; };
 template <int MODE>
-__global__ void k(double* out, int iters, double a, double b) {
+__global__ void k(double* out, int iters, double a, double b, const __grid_constant__ WP wp, int woff) {
   double x[8], y[8], z[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x + i; y[i] = 1.0 + 1e-9 * (threadIdx.x + i); z[i] = 1e-9 * i * threadIdx.x; }
@@ -15,6 +17,8 @@ __global__ void k(double* out, int iters, double a, double b) {
         if (MODE == 2) x[i] = fma(x[i], y[i], b);
         if (MODE == 3) x[i] = fma(z[(i + u) & 7], y[i], x[i]);
         if (MODE == 4) x[i] = fma(z[(i + u) & 7], y[(i + 2 * u + 1) & 7], x[i]);
+        if (MODE == 7) x[i] = fma(z[(i + u) & 7], cw[i + 8 * u], x[i]);           // constant-bank weight, 2 vector regs
+        if (MODE == 8) x[i] = fma(z[(i + u) & 7], wp.w[woff + i + 8 * u], x[i]);  // kernel-param weight, uniform dynamic offset
         if (MODE == 5) x[i] = fma(z[(i + u) & 7], y[u], x[i]);          // slot B shared by 8 consecutive
         if (MODE == 6) x[i] = fma(z[(i + u) & 7], y[(i >> 1) + u], x[i]); // slot B shared by pairs
       }
@@ -29,9 +33,10 @@ void run(int warps, int ctas) {
   double* out; cudaMalloc(&out, 8);
   int iters = 4000;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<MODE><<<148 * ctas, warps * 32>>>(out, 10, 0.999, 1e-9);
+  WP wp; for (int i = 0; i < 1024; ++i) wp.w[i] = 1.0 + 1e-9 * i;
+  k<MODE><<<148 * ctas, warps * 32>>>(out, 10, 0.999, 1e-9, wp, 100);
   cudaEventRecord(e0);
-  k<MODE><<<148 * ctas, warps * 32>>>(out, iters, 0.999, 1e-9);
+  k<MODE><<<148 * ctas, warps * 32>>>(out, iters, 0.999, 1e-9, wp, 100);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   double flops = 2.0 * 32 * 32.0 * iters * warps * ctas * 148;
@@ -40,6 +45,6 @@ void run(int warps, int ctas) {
 }
 int main() {
   run<1>(4, 3); run<2>(4, 3); run<3>(4, 3); run<4>(4, 3);
-  run<1>(8, 4); run<2>(8, 4); run<3>(8, 4); run<4>(8, 4); run<5>(4, 3); run<6>(4, 3); run<5>(8, 4); run<6>(8, 4); run<5>(1, 1); run<3>(1, 1);
+  run<1>(8, 4); run<2>(8, 4); run<3>(8, 4); run<4>(8, 4); run<5>(4, 3); run<6>(4, 3); run<5>(8, 4); run<6>(8, 4); run<5>(1, 1); run<3>(1, 1); run<7>(4, 3); run<8>(4, 3); run<7>(1, 12); run<8>(1, 12);
   return 0;
 }
