@@ -245,3 +245,47 @@ def test_edge_configurations_against_oracle(gpu_ok, ssp_kw, nv, nx):
     ya = plan.ybar_gaussian(P, mu, sg)
     ra = R.ybar_gaussian(P, mu, sg, ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv)
     assert rel_err(ya, ra) < TOL, (ssps.n_fft, rel_err(ya, ra))
+
+
+def test_full_size_201_cube_properties(gpu_ok):
+    """BASELINE.json's headline size: 201x201 pixels, full grid, nv=101 (20.8 GB density, generated on
+    the device).  Size-independent checks: spot pixels against the oracle, a checksum of checksums
+    (the pixel-sum of the cube equals the cube of the pixel-summed density, by linearity), and the
+    cube assembled from 8 pixel shards is identical to the single-call cube."""
+    import torch
+    from oracle import restatement as R
+    import popkinmocks_b200 as pkm
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~45 GB of free device memory")
+    ssps = pkm.milesSSPs()
+    nx, nv = 201, 101
+    cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx, nx2=nx, nv=nv, vrng=(-1000.0, 1000.0))
+    plan = pkm.engine.get_plan(cube)
+    nz, nt = ssps.par_dims
+    gen = torch.Generator(device="cuda").manual_seed(201)
+    p = torch.empty((nt, nv, nx, nx, nz), dtype=torch.float64, device="cuda")
+    for t in range(nt):
+        p[t] = torch.rand((nv, nx, nx, nz), dtype=torch.float64, device="cuda", generator=gen)
+    y = plan.ybar_density(p, is_log=False)
+    assert tuple(y.shape) == (ssps.n_fft, nx, nx)
+    for (i, j) in [(0, 0), (200, 200), (100, 57), (13, 188)]:
+        sub = p[:, :, i:i + 1, j:j + 1, :].cpu().numpy()
+        ref = R.ybar_density_literal(sub, cube.v_edg, ssps.FXw, ssps.par_dims, ssps.n_fft, ssps.dv,
+                                     ssps.delta_t, ssps.delta_z, cube.dx, cube.dy)
+        assert rel_err(y[:, i, j].cpu().numpy(), ref[:, 0, 0]) < TOL, (i, j)
+    # checksum of checksums
+    psum = p.sum(dim=(2, 3), keepdim=True)
+    ysum = plan.ybar_density(psum, is_log=False)[:, 0, 0]
+    tot = y.sum(dim=(1, 2))
+    assert float((tot - ysum).abs().max() / ysum.abs().max()) < 1e-11
+    # 8 contiguous pixel shards written into one cube (the multi-GPU decomposition on one device)
+    from popkinmocks_b200 import _lib, sharding
+    flat = p.reshape(nt, nv, nx * nx, 1, nz)
+    big = torch.zeros((ssps.n_fft, nx * nx, 1), dtype=torch.float64, device="cuda")
+    bounds = sharding.row_partition(nx * nx, 8)
+    for r in range(8):
+        _lib.check(_lib.load().pkm_ybar_density_into_cube(plan._h, _lib.ptr(flat), 0, nx * nx, 1, bounds[r], bounds[r + 1],
+                                                          _lib.ptr(big), nx * nx, bounds[r], None))
+    torch.cuda.synchronize()
+    assert torch.equal(big.reshape(ssps.n_fft, nx, nx), y)
