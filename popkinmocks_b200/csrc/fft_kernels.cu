@@ -16,7 +16,7 @@
 // Chirp phases are reduced exactly (j^2 mod 2n in integers) on the host.
 #include "pkm_internal.h"
 
-constexpr int CZT_THREADS = 1024;  // one CTA per SM holds the whole transform in smem: hide latency with warps
+constexpr int CZT_THREADS = 512;   // M/16 radix-16 work items for M = 8192; 128 registers per thread
 
 namespace {
 
@@ -38,14 +38,111 @@ struct SmemInput {
   __device__ __forceinline__ double2 operator()(int i) const { return s[i]; }
 };
 
+// 4-point DIF butterfly (forward) and its inverse, twiddles applied by the caller
+__device__ __forceinline__ void bfly4_fwd(double2& a, double2& b, double2& c, double2& d) {
+  const double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
+  const double2 t3 = make_double2(bd.y, -bd.x);  // -i (b - d)
+  a = cadd(t0, t2);
+  b = cadd(t1, t3);
+  c = csub(t0, t2);
+  d = csub(t1, t3);
+}
+__device__ __forceinline__ void bfly4_inv(double2& y0, double2& y1, double2& y2, double2& y3) {
+  const double2 u0 = cadd(y0, y2), u1 = csub(y0, y2), u2 = cadd(y1, y3), yd = csub(y1, y3);
+  const double2 u3 = make_double2(-yd.y, yd.x);  // +i (y1 - y3)
+  y0 = cadd(u0, u2);
+  y1 = cadd(u1, u3);
+  y2 = csub(u0, u2);
+  y3 = csub(u1, u3);
+}
+
+// Twiddles of one radix-16 step from the single table entry u = W_M^(j M/Nb):
+//   level 1 (block Nb, position j + b Nb/16):  W^(m (j + b Nb/16) M/Nb) = u^m * W16^(m b)
+//   level 2 (block Nb/4, position j):          W^(n j 4M/Nb)            = (u^4)^n
+struct Tw16 {
+  double2 u[3];   // u, u^2, u^3
+  double2 v[3];   // u^4, u^8, u^12
+  __device__ __forceinline__ void init(double2 w) {
+    u[0] = w;
+    u[1] = cmul(w, w);
+    u[2] = cmul(u[1], w);
+    v[0] = cmul(u[1], u[1]);
+    v[1] = cmul(v[0], v[0]);
+    v[2] = cmul(v[1], v[0]);
+  }
+  // u^m * exp(-2 pi i m b / 16), m in 1..3, b in 0..3 (compile-time after unrolling)
+  __device__ __forceinline__ double2 level1(int m, int b) const {
+    const double C1 = 0.92387953251128674, S1 = 0.38268343236508977, C2 = 0.70710678118654752;
+    const int k = m * b;  // 0,1,2,3,4,6,9
+    const double2 w = u[m - 1];
+    switch (k) {
+      case 0: return w;
+      case 1: return cmul(w, make_double2(C1, -S1));
+      case 2: return cmul(w, make_double2(C2, -C2));
+      case 3: return cmul(w, make_double2(S1, -C1));
+      case 4: return make_double2(w.y, -w.x);                 // * (-i)
+      case 6: return cmul(w, make_double2(-C2, -C2));
+      default: return cmul(w, make_double2(-C1, S1));         // k = 9
+    }
+  }
+};
+
+// Radix-4 passes are executed two at a time in registers (a radix-16 step: 16 loads, two levels
+// of butterflies, 16 stores) - the arithmetic is exactly that of two consecutive radix-4 passes,
+// with half the shared-memory traffic and barriers.  Per-pass twiddle tables: the pass with
+// quarter size q reads W^(m j stride), m = 1..3, at twp[M - 4q + (m-1) q + j], contiguous in j.
 template <class In>
 __device__ void fft_forward(double2* s, int M, int logM, const double2* __restrict__ twp, In in,
                             const double2* __restrict__ post) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   int Nb = M;
-  for (; Nb >= 4; Nb >>= 2) {
+  bool first = true;
+  for (; Nb >= 16; Nb >>= 4, first = false) {
+    const int q = Nb >> 2, qq = Nb >> 4;
+    const bool last = post != nullptr && qq == 1;
+    for (int i = tid; i < (M >> 4); i += nthr) {
+      const int j = i & (qq - 1);
+      const int base = (i - j) * 16 + j;
+      double2 x[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int idx = base + a * q + b * qq;
+          x[a][b] = first ? in(idx) : s[idx];
+        }
+      // All 15 twiddles of the step derive from ONE table entry u = W^(j stride): level 1 needs
+      // u^m W16^(m b), level 2 (u^4)^n.  (The 128 KB table does not fit next to the 128 KB
+      // transform in L1/shared memory; loading every twiddle made the kernel L2-bound.)
+      Tw16 tw;
+      tw.init(__ldg(twp + (M - 4 * q) + j));
+      // level 1: blocks of Nb, butterflies over a, position in the quarter = j + b qq
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        bfly4_fwd(x[0][b], x[1][b], x[2][b], x[3][b]);
+        x[1][b] = cmul(x[1][b], tw.level1(1, b));
+        x[2][b] = cmul(x[2][b], tw.level1(2, b));
+        x[3][b] = cmul(x[3][b], tw.level1(3, b));
+      }
+      // level 2: blocks of Nb/4 (one per a), butterflies over b, position j
+      const double2 w1 = tw.v[0], w2 = tw.v[1], w3 = tw.v[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        bfly4_fwd(x[a][0], x[a][1], x[a][2], x[a][3]);
+        x[a][1] = cmul(x[a][1], w1);
+        x[a][2] = cmul(x[a][2], w2);
+        x[a][3] = cmul(x[a][3], w3);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int idx = base + a * q + b * qq;
+          s[idx] = last ? cmul(x[a][b], __ldg(post + idx)) : x[a][b];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (; Nb >= 4; Nb >>= 2, first = false) {
     const int q = Nb >> 2;
-    const bool first = Nb == M;
     const bool last = post != nullptr && q == 1;
     for (int i = tid; i < (M >> 2); i += nthr) {
       const int j = i & (q - 1);
@@ -56,30 +153,27 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
       } else {
         a = s[base]; b = s[base + q]; c = s[base + 2 * q]; d = s[base + 3 * q];
       }
-      double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), bd = csub(b, d);
-      double2 t3 = make_double2(bd.y, -bd.x);  // -i (b - d)
-      double2 y0 = cadd(t0, t2), y1 = cadd(t1, t3), y2 = csub(t0, t2), y3 = csub(t1, t3);
-      // per-pass twiddle table: W^(m j stride) at twp[M - 4q + (m-1) q + j], contiguous in j
+      bfly4_fwd(a, b, c, d);
       const double2* tp = twp + (M - 4 * q) + j;
-      y1 = cmul(y1, __ldg(tp));
-      y2 = cmul(y2, __ldg(tp + q));
-      y3 = cmul(y3, __ldg(tp + 2 * q));
+      b = cmul(b, __ldg(tp));
+      c = cmul(c, __ldg(tp + q));
+      d = cmul(d, __ldg(tp + 2 * q));
       if (last) {
-        y0 = cmul(y0, __ldg(post + base));
-        y1 = cmul(y1, __ldg(post + base + 1));
-        y2 = cmul(y2, __ldg(post + base + 2));
-        y3 = cmul(y3, __ldg(post + base + 3));
+        a = cmul(a, __ldg(post + base));
+        b = cmul(b, __ldg(post + base + 1));
+        c = cmul(c, __ldg(post + base + 2));
+        d = cmul(d, __ldg(post + base + 3));
       }
-      s[base] = y0;
-      s[base + q] = y1;
-      s[base + 2 * q] = y2;
-      s[base + 3 * q] = y3;
+      s[base] = a;
+      s[base + q] = b;
+      s[base + 2 * q] = c;
+      s[base + 3 * q] = d;
     }
     __syncthreads();
   }
   if (Nb == 2) {
     for (int i = tid; i < (M >> 1); i += nthr) {
-      double2 a = s[2 * i], b = s[2 * i + 1];
+      double2 a = first ? in(2 * i) : s[2 * i], b = first ? in(2 * i + 1) : s[2 * i + 1];
       double2 y0 = cadd(a, b), y1 = csub(a, b);
       if (post) {
         y0 = cmul(y0, __ldg(post + 2 * i));
@@ -98,18 +192,19 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
 template <class Out>
 __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restrict__ twp, Out out) {
   const int tid = threadIdx.x, nthr = blockDim.x;
-  int Nb = 4;
+  int D = 1;  // size of the blocks already transformed
   if (logM & 1) {
+    const bool last = M == 2;
     for (int i = tid; i < (M >> 1); i += nthr) {
-      double2 a = s[2 * i], b = s[2 * i + 1];
-      s[2 * i] = cadd(a, b);
-      s[2 * i + 1] = csub(a, b);
+      const double2 a = s[2 * i], b = s[2 * i + 1];
+      if (last) { out(2 * i, cadd(a, b)); out(2 * i + 1, csub(a, b)); }
+      else { s[2 * i] = cadd(a, b); s[2 * i + 1] = csub(a, b); }
     }
     __syncthreads();
-    Nb = 8;
+    D = 2;
   }
-  for (; Nb <= M; Nb <<= 2) {
-    const int q = Nb >> 2;
+  if ((logM & 3) >= 2) {  // one single radix-4 pass mirrors the forward transform's remainder
+    const int q = D, Nb = 4 * D;
     const bool last = Nb == M;
     for (int i = tid; i < (M >> 2); i += nthr) {
       const int j = i & (q - 1);
@@ -119,18 +214,47 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
       double2 y1 = cmulc(s[base + q], __ldg(tp));
       double2 y2 = cmulc(s[base + 2 * q], __ldg(tp + q));
       double2 y3 = cmulc(s[base + 3 * q], __ldg(tp + 2 * q));
-      double2 u0 = cadd(y0, y2), u1 = csub(y0, y2), u2 = cadd(y1, y3), yd = csub(y1, y3);
-      double2 u3 = make_double2(-yd.y, yd.x);  // +i (y1 - y3)
+      bfly4_inv(y0, y1, y2, y3);
       if (last) {
-        out(base, cadd(u0, u2));
-        out(base + q, cadd(u1, u3));
-        out(base + 2 * q, csub(u0, u2));
-        out(base + 3 * q, csub(u1, u3));
+        out(base, y0); out(base + q, y1); out(base + 2 * q, y2); out(base + 3 * q, y3);
       } else {
-        s[base] = cadd(u0, u2);
-        s[base + q] = cadd(u1, u3);
-        s[base + 2 * q] = csub(u0, u2);
-        s[base + 3 * q] = csub(u1, u3);
+        s[base] = y0; s[base + q] = y1; s[base + 2 * q] = y2; s[base + 3 * q] = y3;
+      }
+    }
+    __syncthreads();
+    D = Nb;
+  }
+  for (; D < M; D <<= 4) {  // fused pairs: blocks of D -> 4D -> 16D
+    const int qq = D, q = 4 * D;
+    const bool last = 16 * D == M;
+    for (int i = tid; i < (M >> 4); i += nthr) {
+      const int j = i & (qq - 1);
+      const int base = (i - j) * 16 + j;
+      double2 x[4][4];
+      Tw16 tw;
+      tw.init(__ldg(twp + (M - 4 * q) + j));
+      const double2 w1 = tw.v[0], w2 = tw.v[1], w3 = tw.v[2];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int ib = base + a * q;
+        x[a][0] = s[ib];
+        x[a][1] = cmulc(s[ib + qq], w1);
+        x[a][2] = cmulc(s[ib + 2 * qq], w2);
+        x[a][3] = cmulc(s[ib + 3 * qq], w3);
+        bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        x[1][b] = cmulc(x[1][b], tw.level1(1, b));
+        x[2][b] = cmulc(x[2][b], tw.level1(2, b));
+        x[3][b] = cmulc(x[3][b], tw.level1(3, b));
+        bfly4_inv(x[0][b], x[1][b], x[2][b], x[3][b]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int idx = base + a * q + b * qq;
+          if (last) out(idx, x[a][b]);
+          else s[idx] = x[a][b];
+        }
       }
     }
     __syncthreads();
