@@ -139,8 +139,10 @@ class ParametricComponent(base.Component):
         z_mu = np.moveaxis(grid["z"][nearest], -1, 0)                     # [t, x1, x2]
         z_sd = (self.ahat * z_mu ** self.bhat) ** 0.5
         lin_z_edges = 10.0 ** self.cube.ssps.par_edges[0]
-        law = stats.norm(loc=z_mu, scale=z_sd)
-        log_cdf = law.logcdf(lin_z_edges[:, None, None, None])            # [z+1, t, x1, x2]
+        # = stats.norm(z_mu, z_sd).logcdf(edges): the same log_ndtr call without the frozen-
+        # distribution overhead (bit-identical, ~2x faster on these [z+1, t, x1, x2] arrays)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            log_cdf = special.log_ndtr((lin_z_edges[:, None, None, None] - z_mu) / z_sd)
         log_P = _log_diff_exp(log_cdf[1:], log_cdf[:-1])                  # [z, t, x1, x2]
         log_dz = np.log(self.cube.construct_volume_element("z"))
         log_norm = special.logsumexp(log_P.T + log_dz, -1).T
@@ -169,8 +171,9 @@ class ParametricComponent(base.Component):
     def _log_P_v_tx(self):
         """log P(v-bin | t,x) from Gaussian cdf differences, shape [v, t, x1, x2]."""
         v_edg = self.cube.v_edg[:, None, None, None]
-        law = stats.norm(loc=self.mu_v, scale=self.sig_v)
-        return _log_diff_exp(law.logcdf(v_edg[1:]), law.logcdf(v_edg[:-1]))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            log_cdf = special.log_ndtr((v_edg - self.mu_v) / self.sig_v)   # == stats.norm.logcdf
+        return _log_diff_exp(log_cdf[1:], log_cdf[:-1])
 
     def _log_P_joint(self, with_v, light_weighted):
         """log P over (t,x,z) or (t,v,x,z), light-weighted and renormalised if asked."""
