@@ -321,16 +321,28 @@ def run_b200(args):
     dV = float(np.mean(cube.ssps.delta_t) * np.mean(cube.ssps.delta_z) * cube.dx * cube.dy * cube.ssps.dv)
     logp.mul_(1.0 / (0.5 * nt * nv * total_pix * nz * dV)).clamp_(min=1e-300).log_()
 
+    gather_note = None
     if world == 1:
         out = torch.empty((n_fft, rows, nxl), dtype=torch.float64, device=dev)
         tg = None
-    elif args.gather == "peer":
-        # rank 0 owns the cube; every rank's final transpose kernel stores its rows into it over NVLink
-        pc = sharding.PeerCube(n_fft, nx1_total, nxl, dev, dist)
-        out = pc.cube
-        tg = None
-        flag = torch.zeros(1, device=dev)
     else:
+        if args.gather == "peer":
+            # rank 0 owns the cube; every rank moves its finished tiles into it over NVLink (CUDA IPC).
+            # If peer mapping is not available on this box, all ranks fall back to the NCCL gather.
+            ok = torch.ones(1, device=dev)
+            try:
+                pc = sharding.PeerCube(n_fft, nx1_total, nxl, dev, dist)
+            except Exception as exc:  # noqa: BLE001
+                ok.zero_()
+                gather_note = f"peer-memory cube unavailable ({type(exc).__name__}); used the NCCL gather"
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 0.5:
+                args.gather = "nccl"
+        if args.gather == "peer":
+            out = pc.cube
+            tg = None
+            flag = torch.zeros(1, device=dev)
+    if world > 1 and args.gather == "nccl":
         tg = sharding.TileGather(nx1_total, nxl, n_fft, dev, dist=dist, ntile=args.gather_tiles)
         out = torch.empty((n_fft, nx1_total, nxl), dtype=torch.float64, device=dev) if rank == 0 else None
 
@@ -540,6 +552,7 @@ def run_b200(args):
                              "compulsory": {"bytes_per_voxel": b_min, "achieved": b_min * per_gpu / 1e9,
                                             "frac": b_min * per_gpu / 1e9 / hbm_peak},
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
+            "gather": (args.gather if world > 1 else None), "gather_note": gather_note,
             "kernels": kern, "per_rank": per_rank, "other_paths": other, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -158,26 +158,34 @@ class PeerCube:
         self.device = torch.device(device)
         self._peer_base = None
         self._own_base = None
+        payload = [None, None]
+        error = None
         if self.rank == 0:
             # a plain cudaMalloc allocation (torch's caching allocator sub-allocates and cannot be
             # exported portably), viewed as a torch tensor through __cuda_array_interface__
-            base = C.c_void_p()
-            nbytes = n_fft * nx1 * nx2 * 8
-            _lib.check(_lib.load().pkm_device_alloc(self.device.index or 0, nbytes, C.byref(base)))
-            self._own_base = base
-            handle = (C.c_uint8 * 64)()
-            _lib.check(_lib.load().pkm_ipc_export(base, handle))
+            try:
+                base = C.c_void_p()
+                nbytes = n_fft * nx1 * nx2 * 8
+                _lib.check(_lib.load().pkm_device_alloc(self.device.index or 0, nbytes, C.byref(base)))
+                self._own_base = base
+                handle = (C.c_uint8 * 64)()
+                _lib.check(_lib.load().pkm_ipc_export(base, handle))
 
-            class _View:
-                __cuda_array_interface__ = {"shape": (n_fft, nx1, nx2), "typestr": "<f8",
-                                            "data": (base.value, False), "version": 3, "strides": None}
-            self.cube = torch.as_tensor(_View(), device=self.device)
-            payload = [bytes(handle), 0]
-            self.ptr = base.value
+                class _View:
+                    __cuda_array_interface__ = {"shape": (n_fft, nx1, nx2), "typestr": "<f8",
+                                                "data": (base.value, False), "version": 3, "strides": None}
+                self.cube = torch.as_tensor(_View(), device=self.device)
+                payload = [bytes(handle), 0]
+                self.ptr = base.value
+            except Exception as exc:  # noqa: BLE001 - still take part in the broadcast below
+                error = exc
         else:
             self.cube = None
-            payload = [None, None]
         dist.broadcast_object_list(payload, src=0)
+        if error is not None:
+            raise error
+        if payload[0] is None:
+            raise RuntimeError("rank 0 could not allocate / export the cube")
         if self.rank != 0:
             handle = (C.c_uint8 * 64).from_buffer_copy(payload[0])
             base = C.c_void_p()
