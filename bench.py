@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--gather-tiles", type=int, default=1, help="sub-blocks per rank for the NCCL gather")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workspace-gb", type=float, default=0.0, help="device workspace cap of the plan (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-other", action="store_true", help="skip the brief timings of the other hot-path rows")
     ap.add_argument("--cpu-procs", type=int, default=0, help="host processes of the CPU legs (0 = all cores, max 64)")
@@ -291,6 +292,8 @@ def run_b200(args):
     nz, nt = cube.ssps.par_dims
     nv, nx, n_fft = args.nv, args.nx, int(cube.ssps.n_fft)
     plan = engine.Plan(cube, device=local)
+    if args.workspace_gb > 0:
+        plan.set_workspace_limit(int(args.workspace_gb * (1 << 30)))
 
     # ---- this rank's share of the pixels
     from popkinmocks_b200 import sharding

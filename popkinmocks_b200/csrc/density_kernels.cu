@@ -5,10 +5,11 @@
 //     Y-hat[k] = sum_{t,z} S'[k,t,z] * sum_{q<4} w[k][q] * c[i_k+q, t, z]
 //
 // kernel 1 (coeff):    c = (A^{-1} D) p   - a small dense real->complex transform per
-//                      (t,x,z) column, done as a register-tiled FP64 GEMM with the even/odd
-//                      fold of the real DFT (halves the flops), exp(log p) fused into the load.
-// kernel 2 (contract): streams S' (L2 resident) and the coefficient rows, evaluates the 4-tap
-//                      spline on the fly and accumulates over (t,z) in registers.
+//                      (t,x,z) column, done as an FP64 tensor-core (DMMA) GEMM on TMA-staged
+//                      density slabs, with the even/odd fold of the real DFT (halves the
+//                      flops) and exp(log p) fused into the fold.
+// kernel 2 (contract): streams S' (TMA-staged, L2 resident) and the coefficient rows, evaluates
+//                      the 4-tap spline on the fly and accumulates over (t,z) in registers.
 // P-hat (25 MB per pixel in the reference, base.py:846-853) is never materialised.
 #include <cuda.h>
 #include <cudaTypedefs.h>

@@ -118,11 +118,9 @@ struct pkm_plan {
   FoldTables fold;
   WsegTables wsegs;
   int nchunk = 0;               // ceil(ntz / PKM_TZC)
-  int TM = 0, nfiP = 0;         // row tiling of kernel 1 (nfiP = 8*TM padded rows)
-  double* d_CRt = nullptr;      // [ne][nfiP]  (u-major, rows padded with zeros)
-  double* d_CIt = nullptr;      // [no][nfiP]
-  int32_t* d_idx_plus = nullptr;
-  int32_t* d_idx_minus = nullptr;
+  int TM = 0, nfiP = 0;         // kernel 1: TM = 8-row output blocks, nfiP = doubles per A operand
+  double* d_CRt = nullptr;      // real-part operand (A^-1 x cosine fold) in DMMA fragment order [nks][TM][32]
+  double* d_CIt = nullptr;      // imaginary-part operand, same layout
   double2* d_Sw = nullptr;      // [nwseg][nchunk*TZC][KT]  S-hat' = FXw*dz*dt, tz = t*nz+z, zero padded
   float2* d_Sw32 = nullptr;     // float32 copy of d_Sw (precision = 1 only)
   int32_t* d_wseg = nullptr;    // [nwseg][4]
@@ -158,13 +156,13 @@ struct pkm_plan {
 // ----------------------------------------------------------------------------
 // kernel launchers (all asynchronous on `st`)
 // ----------------------------------------------------------------------------
-// kernel 1: density tile -> spline coefficients cT[t][z][m][xpad]
+// kernel 1: density tile -> spline coefficients cT[x/32][t*nz+z][m][x%32] (complex128, or float2 for precision 1)
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
                   int64_t pix0, int npix_tile, int xpad, double2* cT, cudaStream_t st);
-// kernel 2: coefficients -> Yhat[xpad][nfo]
+// kernel 2: coefficients -> Yhat[x][nfo]
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
                      cudaStream_t st);
-// gaussian path -> Yhat[xpad][nfo]
+// gaussian path -> Yhat[x][nfo]
 void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
                      int64_t pix0, int npix_tile, int xpad, double omega_step4, double2* yhat,
