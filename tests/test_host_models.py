@@ -153,3 +153,27 @@ def test_plans_are_not_pickled():
     cube._pkm_plans["fake"] = object()
     clone = dill.loads(dill.dumps(cube))
     assert clone._pkm_plans == {} and clone.ssps.n_fft == cube.ssps.n_fft
+
+
+def test_mixture_distributions_match_reference_on_host():
+    """Mixture.get_log_p composes the children's host-side marginals: checked against the
+    reference's outputs for the conftest galaxy (no GPU involved)."""
+    g = load_golden("g1_conftest_full_nv41")
+    cube = golden_cube("g1_conftest_full_nv41")
+    comps = [BUILDERS[t](cube) for t in ("d1_", "d2_", "s1_")]
+    mix = pkm.components.Mixture(cube=cube, component_list=comps, weights=g["mix_weights"])
+    keys = [k for k in g.files if k.startswith("mix_logp|")]
+    assert len(keys) == 12
+    for k in keys:
+        _, dist, lw, _ = k.split("|")
+        out = mix.get_log_p(dist, density=True, light_weighted=bool(int(lw)))
+        ok = np.isfinite(g[k])
+        assert out.shape == g[k].shape
+        assert np.allclose(out[ok], g[k][ok], rtol=0, atol=1e-10), k
+    # the pixelated copy of the mixture is what the reference feeds to the FFT path
+    log_p = mix.get_log_p("tvxz", density=True, light_weighted=False, collapse_cmps=True)
+    ok = np.isfinite(g["b_log_p_tvxz"])
+    assert np.array_equal(np.isfinite(log_p), ok)
+    assert np.allclose(log_p[ok], g["b_log_p_tvxz"][ok], rtol=0, atol=1e-10)
+    for lw in (False, True):
+        assert np.isclose(np.sum(mix.get_p("tvxz", density=False, light_weighted=lw)), 1.0, atol=1e-6)
