@@ -435,7 +435,14 @@ def run_b200(args):
         ms = timed(lambda: plan.ybar_gaussian(P, mu_v, sig_v, out=out))
         other["gaussian_path_A"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
                                     "ref": "ParametricComponent.evaluate_ybar parametric.py:335-407"}
-        del P, mu_v, sig_v
+        # analytic pixelation of the same Gaussian component into a second 5-D device array
+        log_w = torch.log(P)
+        pix = torch.empty_like(logp)
+        ms = timed(lambda: engine.pixelate_gaussian(log_w, mu_v, sig_v, cube.v_edg, device=local, out=pix))
+        other["pixelate_gaussian"] = {"ms": ms, "GB_per_s": pix.numel() * 8 / (ms * 1e-3) / 1e9,
+                                      "note": "pkm_pixelate_gaussian: writes log p(t,v,x,z) once (HBM-write bound)",
+                                      "ref": "ParametricComponent._get_log_p_tvxz parametric.py:567-596"}
+        del P, mu_v, sig_v, log_w, pix
         plan32 = engine.Plan(cube, device=local, precision="float32")
         ms = timed(lambda: plan32.ybar_density(logp, is_log=True, out=out))
         other["density_path_B_float32"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,

@@ -196,6 +196,21 @@ PKM_API int32_t pkm_histogram5d(const double* const* samples, const double* weig
                                 const double* const* edges, const int32_t* nbin, double* out,
                                 int32_t device, void* stream);
 
+/* Analytic pixelation of a Gaussian-LOSVD component on the device
+ * (ParametricComponent._get_log_p_tvxz, popkinmocks/components/parametric.py:567-596, with the
+ * velocity factor of _get_log_p_v_tx, parametric.py:180-211):
+ *   out[t][v][x][z] = log_w_txz[t][x][z]
+ *                   + log( Phi((v_edg[v+1]-mu[t][x])/sig[t][x]) - Phi((v_edg[v]-mu[t][x])/sig[t][x]) )
+ *                   - (density ? log(v_edg[v+1]-v_edg[v]) : 0)
+ * log_w_txz [nt][npix][nz] is log p(t,x,z) (density or volume-weighted, as the caller wants the
+ * result), mu_v / sig_v [nt][npix] dense, v_edg [nv+1] a host array.  log_w_txz, mu_v, sig_v and
+ * out [nt][nv][npix][nz] may each be host or device memory; a device `out` makes the 5-D array
+ * (20.8 GB at 201x201 px) exist only in HBM, ready for pkm_ybar_density / pkm_reduce_logp. */
+PKM_API int32_t pkm_pixelate_gaussian(const double* log_w_txz, const double* mu_v, const double* sig_v,
+                                      const double* v_edg, int32_t nt, int32_t nv, int64_t npix,
+                                      int32_t nz, int32_t density, double* out, int32_t device,
+                                      void* stream);
+
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA; best of `repeats`
  * timed launches of a register-resident DFMA chain on every SM).  The roofline denominator of
  * the FP64-pipe-bound kernels; MEASURED_PEAKS.json carries no FP64 figure. */

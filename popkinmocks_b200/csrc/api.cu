@@ -932,3 +932,42 @@ extern "C" int32_t pkm_histogram5d(const double* const* samples, const double* w
     buf.release(); obuf.release(); ebuf.release();
   });
 }
+
+extern "C" int32_t pkm_pixelate_gaussian(const double* log_w_txz, const double* mu_v, const double* sig_v,
+                                         const double* v_edg, int32_t nt, int32_t nv, int64_t npix,
+                                         int32_t nz, int32_t density, double* out, int32_t device,
+                                         void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(log_w_txz && mu_v && sig_v && v_edg && out, "bad argument");
+    PKM_REQUIRE(nt >= 1 && nv >= 1 && npix >= 1 && nz >= 1, "bad shape");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n_txz = (size_t)nt * npix * nz, n_tx = (size_t)nt * npix, n_out = n_txz * nv;
+    const bool w_host = !pkm_is_device_pointer(log_w_txz), m_host = !pkm_is_device_pointer(mu_v),
+               s_host = !pkm_is_device_pointer(sig_v), o_host = !pkm_is_device_pointer(out);
+    std::vector<double> h_tab(2 * (size_t)nv + 1);           // v_edg [nv+1], log dv [nv]
+    for (int i = 0; i <= nv; ++i) h_tab[i] = v_edg[i];
+    for (int i = 0; i < nv; ++i) h_tab[nv + 1 + i] = std::log(v_edg[i + 1] - v_edg[i]);
+    DevBuf buf;
+    buf.reserve(sizeof(double) * (h_tab.size() + (w_host ? n_txz : 0) + (m_host ? n_tx : 0) +
+                                  (s_host ? n_tx : 0) + (o_host ? n_out : 0)));
+    double* cur = buf.as<double>();
+    double* d_tab = cur; cur += h_tab.size();
+    PKM_CUDA(cudaMemcpyAsync(d_tab, h_tab.data(), sizeof(double) * h_tab.size(), cudaMemcpyHostToDevice, st));
+    auto stage = [&](const double* src, bool host, size_t n) -> const double* {
+      if (!host) return src;
+      double* d = cur; cur += n;
+      PKM_CUDA(cudaMemcpyAsync(d, src, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+      return d;
+    };
+    const double* d_w = stage(log_w_txz, w_host, n_txz);
+    const double* d_m = stage(mu_v, m_host, n_tx);
+    const double* d_s = stage(sig_v, s_host, n_tx);
+    double* d_out = o_host ? cur : out;
+    launch_pixelate(d_w, d_m, d_s, d_tab, density ? d_tab + nv + 1 : nullptr, nt, nv, npix, nz, d_out, st);
+    if (o_host) PKM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    PKM_CUDA(cudaStreamSynchronize(st));   // h_tab and the staging buffer die with this frame
+    buf.release();
+  });
+}

@@ -195,6 +195,9 @@ void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t 
 
 void launch_hist5d(const double* const samples[5], const double* weights, int64_t n, const double* d_edges,
                    const int nbin[5], double* out, int num_sms, cudaStream_t st);
+void launch_pixelate(const double* log_w, const double* mu, const double* sig, const double* d_v_edg,
+                     const double* d_log_dv, int nt, int nv, int64_t npix, int nz, double* out,
+                     cudaStream_t st);
 bool pkm_is_device_pointer(const void* p);
 
 // RAII CUDA-event bracket of one launch on its own stream (no-op unless plan->profiling)

@@ -519,3 +519,104 @@ double run_fma_probe(int num_sms, int repeats) {
   cudaFree(sink);
   return best;
 }
+
+// ----------------------------------------------------------------------------
+// Analytic pixelation of a Gaussian-LOSVD component on the device:
+//   out[t,v,x,z] = log_w[t,x,z] + log( Phi((e[v+1]-mu[t,x])/sig[t,x]) - Phi((e[v]-mu)/sig) ) - ldv[v]
+// i.e. ParametricComponent._get_log_p_tvxz (/root/reference/popkinmocks/components/
+// parametric.py:567-596) with the velocity factor of _get_log_p_v_tx (parametric.py:180-211):
+// normal log-cdf at the nv+1 velocity edges and a signed log-sum-exp of neighbouring edges.
+// The 5-D array (20.8 GB at 201x201 px) never exists on the host; the kernel is bound by the
+// HBM write of `out`.  One CTA = (age t, 32 consecutive pixels): the (nv+1) x 32 edge log-cdfs are
+// evaluated once into shared memory, turned in place into the nv x 32 bin terms, and then every
+// (t,v) row segment of 32*nz contiguous doubles is streamed out with evict-first stores.
+// ----------------------------------------------------------------------------
+namespace {
+constexpr int PIX_PXC = 32;
+
+// log of the standard normal cdf, accurate in both tails (erfcx form below -1, log1p form above 0)
+__device__ __forceinline__ double log_ndtr_dev(double x) {
+  const double rs2 = 0.70710678118654752440;
+  if (x < -1.0) return log(0.5 * erfcx(-x * rs2)) - 0.5 * x * x;
+  if (x < 0.0) return log(0.5 * erfc(-x * rs2));
+  return log1p(-0.5 * erfc(x * rs2));
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_pixelate(const double* __restrict__ log_w, const double* __restrict__ mu,
+           const double* __restrict__ sig, const double* __restrict__ v_edg,
+           const double* __restrict__ log_dv, int nt, int nv, long long npix, int nz,
+           double* __restrict__ out) {
+  extern __shared__ double s_lc[];            // [PIX_PXC][nv + 1] edge log-cdfs, then bin terms
+  const int ne = nv + 1;
+  const int t = blockIdx.y;
+  const long long x0 = (long long)blockIdx.x * PIX_PXC;
+  const int npx = (int)min((long long)PIX_PXC, npix - x0);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < npx * ne; i += blockDim.x) {
+    const int px = i / ne, e = i - px * ne;
+    const double m = mu[(long long)t * npix + x0 + px], s = sig[(long long)t * npix + x0 + px];
+    s_lc[px * ne + e] = log_ndtr_dev((v_edg[e] - m) / s);
+  }
+  __syncthreads();
+  // bin terms: each thread first reads all its (lo, hi) pairs, then the block overwrites in place
+  constexpr int MAXI = 16;
+  const int nitem = npx * nv;
+  for (int base = 0; base < nitem; base += MAXI * blockDim.x) {
+    double val[MAXI];
+#pragma unroll
+    for (int k = 0; k < MAXI; ++k) {
+      const int i = base + k * blockDim.x + tid;
+      val[k] = 0.0;
+      if (i < nitem) {
+        const int px = i / nv, v = i - px * nv;
+        const double lo = s_lc[px * ne + v], hi = s_lc[px * ne + v + 1];
+        // signed logsumexp([hi, lo], b=[1,-1]): hi + log(1 - exp(lo - hi)); an empty bin stays -inf
+        double r = hi;
+        if (hi != -INFINITY) r = hi + log1p(-exp(lo - hi));
+        val[k] = r - (log_dv ? log_dv[v] : 0.0);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < MAXI; ++k) {
+      const int i = base + k * blockDim.x + tid;
+      if (i < nitem) {
+        const int px = i / nv, v = i - px * nv;
+        s_lc[px * ne + v] = val[k];            // slot (px, v) was read only by this thread or earlier
+      }
+    }
+    __syncthreads();
+  }
+  // stream the rows: for fixed (t, v) the npx*nz outputs are contiguous
+  const int nrow = npx * nz;
+  for (int r0 = 0; r0 < nrow; r0 += 2 * blockDim.x) {
+    const int i0 = r0 + tid, i1 = r0 + blockDim.x + tid;
+    const bool ok0 = i0 < nrow, ok1 = i1 < nrow;
+    const int p0 = ok0 ? i0 / nz : 0, p1 = ok1 ? i1 / nz : 0;
+    const double w0 = ok0 ? log_w[((long long)t * npix + x0) * nz + i0] : 0.0;
+    const double w1 = ok1 ? log_w[((long long)t * npix + x0) * nz + i1] : 0.0;
+    double* o = out + (((long long)t * nv) * npix + x0) * nz;
+    for (int v = 0; v < nv; ++v) {
+      if (ok0) __stcs(o + i0, w0 + s_lc[p0 * ne + v]);
+      if (ok1) __stcs(o + i1, w1 + s_lc[p1 * ne + v]);
+      o += npix * nz;
+    }
+  }
+}
+}  // namespace
+
+void launch_pixelate(const double* log_w, const double* mu, const double* sig, const double* d_v_edg,
+                     const double* d_log_dv, int nt, int nv, int64_t npix, int nz, double* out,
+                     cudaStream_t st) {
+  if (npix <= 0) return;
+  const size_t smem = sizeof(double) * PIX_PXC * (size_t)(nv + 1);
+  PKM_REQUIRE(smem <= 200 * 1024, "nv=%d too large for the pixelation kernel", nv);
+  PKM_REQUIRE(nt <= 65535, "nt=%d too large for the pixelation kernel", nt);
+  if (smem > 48 * 1024)
+    PKM_CUDA(cudaFuncSetAttribute(k_pixelate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((npix + PIX_PXC - 1) / PIX_PXC), (unsigned)nt);
+  k_pixelate<<<grid, 256, smem, st>>>(log_w, mu, sig, d_v_edg, d_log_dv, nt, nv, (long long)npix, nz, out);
+  PKM_CUDA(cudaGetLastError());
+}

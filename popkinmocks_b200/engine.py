@@ -294,3 +294,38 @@ def histogram5d(samples, edges, weights=None, device=0):
         raise ValueError("weights must have one entry per particle")
     _lib.check(_lib.load().pkm_histogram5d(sp, _lib.ptr(w), n, ep, nbin, _lib.ptr(out), int(device), None))
     return out
+
+
+def pixelate_gaussian(log_w_txz, mu_v, sig_v, v_edg, density=True, device=0, on_device=True, out=None):
+    """log p(t,v,x,z) of a Gaussian-LOSVD component, pixelated on the device.
+
+    log_w_txz [nt, nx1, nx2, nz] = log p(t,x,z); mu_v, sig_v broadcastable to [nt, nx1, nx2];
+    v_edg [nv+1].  Adds the log of the normal-cdf difference over every velocity bin (minus
+    log dv if `density`), parametric.py:180-211,567-596.  Returns a CUDA tensor
+    [nt, nv, nx1, nx2, nz] (`on_device`, the 5-D array then never exists on the host) or a
+    NumPy array; `out` (contiguous float64, that shape, either side) is filled if given."""
+    _lib.require_gpu()
+    import torch
+    nt, nx1, nx2, nz = log_w_txz.shape
+    v_edg = _lib.as_f64(v_edg)
+    nv = v_edg.size - 1
+
+    def dense(a, shape):
+        if _is_cuda_tensor(a):
+            return a.to(torch.float64).expand(shape).contiguous()
+        return _lib.as_f64(np.broadcast_to(np.asarray(a, dtype=np.float64), shape))
+
+    log_w = dense(log_w_txz, (nt, nx1, nx2, nz))
+    mu = dense(mu_v, (nt, nx1, nx2))
+    sig = dense(sig_v, (nt, nx1, nx2))
+    if out is not None:
+        if tuple(out.shape) != (nt, nv, nx1, nx2, nz):
+            raise ValueError(f"`out` has shape {tuple(out.shape)}, expected {(nt, nv, nx1, nx2, nz)}")
+    elif on_device:
+        out = torch.empty((nt, nv, nx1, nx2, nz), dtype=torch.float64, device=f"cuda:{device}")
+    else:
+        out = np.empty((nt, nv, nx1, nx2, nz), dtype=np.float64)
+    _lib.check(_lib.load().pkm_pixelate_gaussian(
+        _lib.ptr(log_w), _lib.ptr(mu), _lib.ptr(sig), _lib.ptr(v_edg), nt, nv, nx1 * nx2, nz,
+        int(bool(density)), _lib.ptr(out), int(device), None))
+    return out

@@ -262,3 +262,104 @@ def test_from_particle_histogram_is_bit_identical_to_numpy(gpu_ok):
         inside &= (arr >= e[0]) & (arr <= e[-1])
     tz_in, _, _ = np.histogram2d(t[inside], z[inside], bins=[edges[0], edges[4]], density=True)
     assert np.allclose(comp.get_p("tz"), tz_in, rtol=1e-10)
+
+
+# ----------------------------------------------------------------------------------------------
+# device-side pixelation of parametric components
+# ----------------------------------------------------------------------------------------------
+G2 = "g2_rebin_nv21_prime"
+
+
+def test_device_pixelation_matches_reference(gpu_ok):
+    """`disk.pixelate()` == the reference's Component(cube, disk.get_log_p('tvxz')): the 5-D array,
+    the datacube, marginals and moments of the twin against outputs of the unmodified reference."""
+    g = load_golden(G2)
+    cube = golden_cube(G2)
+    disk = BUILDERS["d1_"](cube)
+    twin = disk.pixelate()
+    assert twin.log_p_tvxz.is_cuda and tuple(twin.log_p_tvxz.shape) == g["b_log_p_tvxz"].shape
+    got, ref = twin.log_p_tvxz.cpu().numpy(), g["b_log_p_tvxz"]
+    assert not np.isnan(got).any()
+    # empty (t,x,z) cells are -inf for every velocity on both sides
+    empty = np.isneginf(ref.max(axis=1, keepdims=True))
+    assert np.all(np.isneginf(got[np.broadcast_to(empty, ref.shape)]))
+    # log domain: bins within 1e-4 of the cell's peak bin.  (Far in the upper tail the reference's
+    # own 1 - exp(lo - hi) is quantised to 1.1e-16, so bins with P(v|t,x) ~ 1e-16 flip between a
+    # finite value and -inf on one-ulp differences of the cdf; those are covered in the p domain.)
+    bulk = ref > ref.max(axis=1, keepdims=True) + np.log(1e-4)
+    assert bulk.sum() > 0.2 * ref.size
+    assert np.max(np.abs(got[bulk] - ref[bulk])) < 1e-10
+    assert rel_err(np.exp(got), np.exp(ref)) < 1e-13
+    twin.evaluate_ybar()
+    assert rel_err(twin.ybar, g["b_ybar"]) < TOL
+    for dist in ("tv", "vxz", "v_x", "tz_x", "x"):
+        for lw in (0, 1):
+            ref_lp = g[f"b_logp|{dist}|{lw}|1"]
+            got_lp = twin.get_log_p(dist, density=True, light_weighted=bool(lw))
+            assert rel_err(np.exp(got_lp), np.exp(ref_lp)) < TOL, (dist, lw)
+    assert np.allclose(twin.get_mean("v_x"), g["b_mean|v_x|0"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(twin.get_variance("v_x"), g["b_var|v_x|0"], rtol=1e-9)
+
+
+def test_pixelation_kernel_edge_shapes_and_tails(gpu_ok):
+    """Ragged pixel counts (not a multiple of the 32-pixel chunk), several nz / nv, scalar sigma,
+    host output, probabilities (density=False), means far outside the velocity range and -inf
+    weights: against the reference formula (scipy log-cdf + signed logsumexp) evaluated here."""
+    from scipy import special, stats
+    rng = np.random.default_rng(11)
+    for (nt, nx1, nx2, nz, nv) in [(3, 3, 11, 5, 7), (2, 1, 1, 1, 1), (4, 8, 9, 12, 40), (1, 5, 13, 3, 301)]:
+        v_edg = np.linspace(-900.0, 1100.0, nv + 1)
+        log_w = np.log(rng.random((nt, nx1, nx2, nz)))
+        log_w[rng.random(log_w.shape) < 0.1] = -np.inf
+        mu = rng.normal(0.0, 400.0, (nt, nx1, nx2))
+        mu.flat[0] = 9000.0                                        # every bin deep in the lower tail
+        mu.flat[-1] = -20000.0                                     # upper tail: cdf differences vanish
+        sig = rng.uniform(20.0, 300.0, (nt, nx1, nx2))
+        for sig_in, dens in ((sig, True), (150.0, False)):
+            got = pkm.engine.pixelate_gaussian(log_w, mu, sig_in, v_edg, density=dens, on_device=False)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                log_cdf = stats.norm(loc=mu, scale=sig_in).logcdf(v_edg[:, None, None, None])
+                lpv = special.logsumexp(np.array([log_cdf[1:], log_cdf[:-1]]).T, -1, b=[1, -1]).T
+            if dens:
+                lpv = (lpv.T - np.log(np.diff(v_edg))).T
+            ref = np.moveaxis(lpv, 0, 1)[..., None] + log_w[:, None]
+            assert got.shape == ref.shape and not np.isnan(got).any()
+            # max-norm on probabilities; bins both sides call empty must agree where the weight is empty
+            assert np.all(np.isneginf(got[np.isneginf(np.broadcast_to(log_w[:, None], ref.shape))]))
+            scale = np.exp(ref[np.isfinite(ref)]).max()
+            assert np.max(np.abs(np.exp(got) - np.exp(np.where(np.isnan(ref), -np.inf, ref)))) <= 1e-12 * scale
+            # log domain: (i) bins within 1e-4 of the peak bin of their (t,x) velocity law, and
+            # (ii) every bin below the mean, however deep in the lower tail (log p down to -1e5)
+            # - there the reference's signed logsumexp is well conditioned.  Upper-tail bins with
+            # P(v|t,x) ~ 1e-16 are quantised by 1 - exp(lo - hi) and only checked as probabilities.
+            with np.errstate(invalid="ignore"):
+                bulk = lpv > np.max(lpv, axis=0) + np.log(1e-4)
+            below = np.broadcast_to(v_edg[1:, None, None, None] <= mu, lpv.shape)
+            for mask in (bulk, below):
+                m = np.broadcast_to(np.moveaxis(mask, 0, 1)[..., None], ref.shape) & np.isfinite(ref)
+                assert m.any()
+                assert np.all(np.abs(got[m] - ref[m]) < 1e-9 + 1e-12 * np.abs(ref[m]))
+
+
+def test_pixelation_at_scale_marginalises_back(gpu_ok):
+    """Size-independent property on a 5.1 GB device array (full grid, nv=101, 100x100 px): summing
+    the pixelated density over velocity returns P(t,x,z) times the cdf mass inside the velocity
+    range; the array never visits the host."""
+    from scipy import special
+    ssps = pkm.milesSSPs()
+    cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=100, nx2=100, nv=101, vrng=(-1000.0, 1000.0))
+    disk = BUILDERS["d1_"](cube)
+    twin = disk.pixelate()
+    assert twin.log_p_tvxz.is_cuda and twin.log_p_tvxz.numel() == 53 * 101 * 100 * 100 * 12
+    got = twin.get_log_p("txz", density=False)
+    with np.errstate(divide="ignore"):
+        lo = special.log_ndtr((cube.v_edg[0] - disk.mu_v) / disk.sig_v)
+        hi = special.log_ndtr((cube.v_edg[-1] - disk.mu_v) / disk.sig_v)
+        inside = np.log(np.exp(hi) - np.exp(lo))
+    ref = disk.get_log_p("txz", density=False) + inside[..., None]
+    assert rel_err(np.exp(got), np.exp(ref)) < TOL
+    twin.evaluate_ybar()
+    disk.evaluate_ybar()
+    # path B on the pixelated twin vs the analytic path A (test_all.py:103-115 tolerance)
+    err = np.abs(twin.ybar - disk.ybar) / np.abs(disk.ybar).max()
+    assert np.median(err) < 5e-4
