@@ -3,8 +3,9 @@
 //  * pkm_reduce_logp: every Component._get_log_p_* marginal
 //    (/root/reference/popkinmocks/components/base.py:884-1174) is
 //    logsumexp_{dropped axes}( log p + log dV [+ log L(t,z) - log norm] ) (base.py:1017-1041).
-//    One generic kernel does it in two streaming passes over the 5-D array (per-output maximum,
-//    then sum of exp relative to it) instead of the reference's 3+ full-array temporaries per call.
+//    One generic kernel does it in ONE streaming pass over the 5-D array (online log-sum-exp:
+//    running maximum + rescaled sum per output) instead of the reference's 3+ full-array
+//    temporaries per call.
 //  * pkm_moments: mean and central moments 2..4 of P[nvar][ncond] along axis 0 (base.py:208-260).
 //  * pkm_noise: ShotNoise / ConstantSNR sigma maps and Gaussian sampling (noise.py:29-71),
 //    Philox4x32-10 counter RNG + Box-Muller in FP64.
@@ -40,96 +41,195 @@ __device__ __forceinline__ long long out_index(const ReduceGeom& g, int t, int v
   return o;
 }
 
-// PASS 0: per-output maximum (atomic max into mx, also global max into gmax)
-// PASS 1: per-output sum of exp(a - mx[o]) (atomic add into out)
-// CTA = one kept (t, v) index (or the full range of a dropped axis) x a chunk of PB whole pixels;
-// thread = one (pixel, z) element, contiguous in memory for fixed (t, v).
-template <int PASS>
+// log-sum-exp kept as a pair (m, s): value = m + log(s), m = running maximum, s = sum of exp(a - m)
+struct Lse {
+  double m, s;
+};
+__device__ __forceinline__ Lse lse_merge(Lse a, Lse b) {
+  const double M = fmax(a.m, b.m);
+  if (!(M > -INFINITY)) return Lse{-INFINITY, 0.0};
+  return Lse{M, a.s * exp(a.m - M) + b.s * exp(b.m - M)};
+}
+
+// ONE streaming pass over the 5-D array ("online" log-sum-exp).
+// CTA = one kept (t, v) index (or the full range of a dropped axis) x pixel chunks of PB whole
+// pixels; thread = one (pixel-in-chunk, z) element, contiguous in memory for fixed (t, v).
+// x kept:    gridDim.x = number of chunks, every output cell has exactly one owner -> the pair is
+//            stored straight into (mx, out).
+// x dropped: gridDim.x = G chunk groups, CTA c walks chunks c, c+G, ...; the per-CTA pairs go to
+//            (mx, out)[o * G + c] and k_reduce_combine folds the G partials of every output.
+// Elements are consumed in batches of U: one maximum, then U+1 independent exps - the exp work
+// (not HBM) bounds this kernel, so nothing in the batch may sit on a dependent chain.
+constexpr int RED_U = 8;
 __global__ void __launch_bounds__(256)
-k_reduce_pass(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
-              const double* __restrict__ log_dv, const double* __restrict__ log_dz,
-              const double* __restrict__ log_lw, double* __restrict__ mx, double* __restrict__ out,
-              double* __restrict__ gmax, int PB) {
-  __shared__ double red[256];
+k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
+                const double* __restrict__ log_dv, const double* __restrict__ log_dz,
+                const double* __restrict__ log_lw, double* __restrict__ mx, double* __restrict__ out,
+                double* __restrict__ gmax, int PB, long long nchunk) {
+  extern __shared__ double s_tab[];          // this CTA's log_dt [t0,t1) | log_dv [v0,v1) | log_lw rows
+  __shared__ double red_m[256], red_s[256];
   const int tid = threadIdx.x;
-  const int nact = PB * g.nz;
-  const long long chunk = blockIdx.x;
-  const int xl = tid / g.nz, z = tid - xl * g.nz;
-  const long long x = chunk * PB + xl;
-  const bool active = tid < nact && x < g.npix;
   int t0 = 0, t1 = g.nt, v0 = 0, v1 = g.nv;
   if (g.kt) { t0 = blockIdx.y; t1 = t0 + 1; }
   if (g.kv) { v0 = blockIdx.z; v1 = v0 + 1; }
+  double* s_dt = s_tab;
+  double* s_dv = s_tab + (t1 - t0);
+  double* s_lw = s_dv + (v1 - v0);
+  for (int i = tid; i < t1 - t0; i += blockDim.x) s_dt[i] = log_dt[t0 + i];
+  for (int i = tid; i < v1 - v0; i += blockDim.x) s_dv[i] = log_dv[v0 + i];
+  if (log_lw) for (int i = tid; i < (t1 - t0) * g.nz; i += blockDim.x) s_lw[i] = log_lw[t0 * g.nz + i];
+  __syncthreads();
 
-  double val = PASS == 0 ? -INFINITY : 0.0;
-  if (active) {
+  const int nact = PB * g.nz;
+  const int xl = tid / g.nz, z = tid - xl * g.nz;
+  const long long G = gridDim.x;
+  const long long row = g.npix * g.nz;       // elements per (t, v)
+
+  Lse acc{-INFINITY, 0.0};
+  // consume a batch: one maximum, then RED_U + 1 independent exps
+  auto flush = [&acc](const double (&a)[RED_U]) {
+    double bm = a[0];
+#pragma unroll
+    for (int k = 1; k < RED_U; ++k) bm = fmax(bm, a[k]);
+    if (bm > -INFINITY) {
+      const double M = fmax(acc.m, bm);
+      double sum = acc.s * exp(acc.m - M);
+#pragma unroll
+      for (int k = 0; k < RED_U; ++k) sum += exp(a[k] - M);
+      acc.m = M;
+      acc.s = sum;
+    }
+  };
+  if (tid < nact) {
     const double cz = log_dz[z] + g.log_dxdy;
-    const long long o = out_index(g, t0, v0, x, z);  // kept indices are loop invariant
-    double ref = 0.0;
-    if (PASS == 1) ref = mx[o];
-    if (PASS == 0 || ref > -INFINITY) {
-      for (int t = t0; t < t1; ++t) {
-        const double ct = cz + log_dt[t] + (log_lw ? log_lw[t * g.nz + z] : 0.0);
-        const double* p = logp + (((long long)t * g.nv + v0) * g.npix + chunk * PB) * g.nz + tid;
-        for (int v = v0; v < v1; ++v) {
-          const double a = __ldg(p) + ct + log_dv[v];
-          p += g.npix * g.nz;
-          if (PASS == 0) val = fmax(val, a);
-          else val += exp(a - ref);
+    const int nT = t1 - t0, nV = v1 - v0;
+    const long long cstep = g.kx ? nchunk : G;          // x kept: exactly one chunk per CTA
+    if (nV > 1) {
+      // batches along v (stride = one (t,v) row)
+      for (long long chunk = blockIdx.x; chunk < nchunk; chunk += cstep) {
+        if (chunk * PB + xl >= g.npix) continue;
+        for (int t = t0; t < t1; ++t) {
+          const double ct = cz + s_dt[t - t0] + (log_lw ? s_lw[(t - t0) * g.nz + z] : 0.0);
+          const double* p = logp + ((long long)t * g.nv + v0) * row + chunk * nact + tid;
+          for (int vb = 0; vb < nV; vb += RED_U) {
+            double a[RED_U];
+#pragma unroll
+            for (int k = 0; k < RED_U; ++k) {
+              const bool ok = vb + k < nV;
+              const double ld = ok ? __ldg(p + (long long)(vb + k) * row) : -INFINITY;
+              a[k] = ld + ct + s_dv[ok ? vb + k : 0];
+            }
+            flush(a);
+          }
         }
+      }
+    } else if (nT > 1) {
+      // v kept, t summed: batches along t (stride = nv rows)
+      const double cv = s_dv[0];
+      for (long long chunk = blockIdx.x; chunk < nchunk; chunk += cstep) {
+        if (chunk * PB + xl >= g.npix) continue;
+        const double* p = logp + (long long)v0 * row + chunk * nact + tid;
+        for (int tb = 0; tb < nT; tb += RED_U) {
+          double a[RED_U];
+#pragma unroll
+          for (int k = 0; k < RED_U; ++k) {
+            const bool ok = tb + k < nT;
+            const int tt = ok ? tb + k : 0;
+            const double ld = ok ? __ldg(p + (long long)tt * g.nv * row) : -INFINITY;
+            a[k] = ld + (cz + s_dt[tt] + (log_lw ? s_lw[tt * g.nz + z] : 0.0)) + cv;
+          }
+          flush(a);
+        }
+      }
+    } else {
+      // t and v kept: batches along this CTA's pixel chunks (a single element when x is kept too)
+      const double c = cz + s_dt[0] + (log_lw ? s_lw[z] : 0.0);
+      const double cv = s_dv[0];
+      const double* p = logp + ((long long)t0 * g.nv + v0) * row + tid;
+      for (long long cb = blockIdx.x; cb < nchunk; cb += cstep * RED_U) {
+        double a[RED_U];
+#pragma unroll
+        for (int k = 0; k < RED_U; ++k) {
+          const long long chunk = cb + k * cstep;
+          const bool ok = chunk < nchunk && chunk * PB + xl < g.npix;
+          const double ld = ok ? __ldg(p + chunk * nact) : -INFINITY;
+          a[k] = ld + c + cv;
+        }
+        flush(a);
       }
     }
   }
-  // combine over the dropped in-CTA axes
-  if (g.kx && g.kz) {
-    if (active) {
-      long long o = out_index(g, t0, v0, x, z);
-      if (PASS == 0) { if (val > -INFINITY) atomic_max_double(mx + o, val); }
-      else if (val != 0.0) atomicAdd(out + o, val);
-    }
-  } else {
-    red[tid] = active ? val : (PASS == 0 ? -INFINITY : 0.0);
-    __syncthreads();
-    if (g.kx) {          // reduce over z, one thread per pixel
-      if (tid < PB && chunk * PB + tid < g.npix) {
-        double r = PASS == 0 ? -INFINITY : 0.0;
-        for (int zz = 0; zz < g.nz; ++zz) {
-          double e = red[tid * g.nz + zz];
-          r = PASS == 0 ? fmax(r, e) : r + e;
-        }
-        long long o = out_index(g, t0, v0, chunk * PB + tid, 0);
-        if (PASS == 0) { if (r > -INFINITY) atomic_max_double(mx + o, r); }
-        else if (r != 0.0) atomicAdd(out + o, r);
-      }
-    } else if (g.kz) {   // reduce over pixels, one thread per z
-      if (tid < g.nz) {
-        double r = PASS == 0 ? -INFINITY : 0.0;
-        for (int xx = 0; xx < PB; ++xx) {
-          double e = red[xx * g.nz + tid];
-          r = PASS == 0 ? fmax(r, e) : r + e;
-        }
-        long long o = out_index(g, t0, v0, 0, tid);
-        if (PASS == 0) { if (r > -INFINITY) atomic_max_double(mx + o, r); }
-        else if (r != 0.0) atomicAdd(out + o, r);
-      }
-    } else {             // reduce everything in the CTA
-      for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s) red[tid] = PASS == 0 ? fmax(red[tid], red[tid + s]) : red[tid] + red[tid + s];
-        __syncthreads();
-      }
-      if (tid == 0) {
-        long long o = out_index(g, t0, v0, 0, 0);
-        double r = red[0];
-        if (PASS == 0) { if (r > -INFINITY) atomic_max_double(mx + o, r); }
-        else if (r != 0.0) atomicAdd(out + o, r);
-      }
-    }
-  }
-  if (PASS == 0 && gmax) {
-    // global maximum (needed only for the light-weighted normalisation)
-    double r = active ? val : -INFINITY;
+
+  if (gmax) {                                 // global maximum (light-weighted normalisation)
+    double r = acc.m;
     for (int off = 16; off > 0; off >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, off));
     if ((tid & 31) == 0 && r > -INFINITY) atomic_max_double(gmax, r);
+  }
+
+  // combine over the dropped in-CTA axes and store the pair(s)
+  const long long part = g.kx ? 1 : G, pidx = g.kx ? 0 : blockIdx.x;
+  if (g.kx && g.kz) {
+    const long long x = (long long)blockIdx.x * PB + xl;
+    if (tid < nact && x < g.npix) {
+      const long long o = out_index(g, t0, v0, x, z);
+      mx[o] = acc.m;
+      out[o] = acc.s;
+    }
+    return;
+  }
+  red_m[tid] = tid < nact ? acc.m : -INFINITY;
+  red_s[tid] = tid < nact ? acc.s : 0.0;
+  __syncthreads();
+  if (g.kx) {            // reduce over z, one thread per pixel
+    const long long x = (long long)blockIdx.x * PB + tid;
+    if (tid < PB && x < g.npix) {
+      Lse r{-INFINITY, 0.0};
+      for (int zz = 0; zz < g.nz; ++zz) r = lse_merge(r, Lse{red_m[tid * g.nz + zz], red_s[tid * g.nz + zz]});
+      const long long o = out_index(g, t0, v0, x, 0);
+      mx[o] = r.m;
+      out[o] = r.s;
+    }
+  } else if (g.kz) {     // reduce over the chunk's pixels, one thread per z
+    if (tid < g.nz) {
+      Lse r{-INFINITY, 0.0};
+      for (int xx = 0; xx < PB; ++xx) r = lse_merge(r, Lse{red_m[xx * g.nz + tid], red_s[xx * g.nz + tid]});
+      const long long o = out_index(g, t0, v0, 0, tid) * part + pidx;
+      mx[o] = r.m;
+      out[o] = r.s;
+    }
+  } else {               // reduce everything in the CTA
+    for (int st = 128; st > 0; st >>= 1) {
+      if (tid < st) {
+        const Lse r = lse_merge(Lse{red_m[tid], red_s[tid]}, Lse{red_m[tid + st], red_s[tid + st]});
+        red_m[tid] = r.m;
+        red_s[tid] = r.s;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const long long o = out_index(g, t0, v0, 0, 0) * part + pidx;
+      mx[o] = red_m[0];
+      out[o] = red_s[0];
+    }
+  }
+}
+
+// fold the G partial pairs of every output: (pm, ps)[o * G + c] -> (mx, out)[o]
+__global__ void k_reduce_combine(const double* __restrict__ pm, const double* __restrict__ ps,
+                                 long long nout, int G, double* __restrict__ mx,
+                                 double* __restrict__ out) {
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= nout) return;
+  const int lane = threadIdx.x & 31;
+  Lse r{-INFINITY, 0.0};
+  for (int c = lane; c < G; c += 32) r = lse_merge(r, Lse{pm[o * G + c], ps[o * G + c]});
+  for (int off = 16; off > 0; off >>= 1) {
+    Lse other{__shfl_xor_sync(0xffffffffu, r.m, off), __shfl_xor_sync(0xffffffffu, r.s, off)};
+    r = lse_merge(r, other);
+  }
+  if (lane == 0) {
+    mx[o] = r.m;
+    out[o] = r.s;
   }
 }
 
@@ -295,6 +395,41 @@ __global__ void k_noise(const double* __restrict__ ybar, long long n, double snr
 
 }  // namespace
 
+// number of pixel-chunk groups (CTAs along x) when x is summed over: enough CTAs to fill the GPU
+// several times over, never more than there are chunks
+static int reduce_groups(const pkm_plan* pl, const ReduceGeom& g, long long nchunk) {
+  const long long n_outer = (long long)(g.kt ? g.nt : 1) * (g.kv ? g.nv : 1);
+  long long G = ((long long)pl->num_sms * 32 + n_outer - 1) / n_outer;
+  G = std::max<long long>(1, std::min<long long>(G, nchunk));
+  return (int)G;
+}
+
+// one online pass + (x dropped) the fold of the chunk-group partials; leaves the pairs in (mx, sum)
+static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, const double* d_log_dv,
+                         const double* d_log_lw, double* d_mx, double* d_sum, double* d_part,
+                         long long nout, double* d_gmax, cudaStream_t st) {
+  const int PB = 256 / g.nz;
+  const long long nchunk = (g.npix + PB - 1) / PB;
+  const int n_outer = (g.kt ? g.nt : 1) * (g.kv ? g.nv : 1);
+  const size_t smem = sizeof(double) * ((size_t)g.nt + g.nv + (size_t)g.nt * g.nz);
+  PKM_REQUIRE(smem <= 40 * 1024, "age/velocity/metallicity grid too large for the reduction kernel");
+  if (g.kx) {
+    dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
+    k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
+                                            d_mx, d_sum, d_gmax, PB, nchunk);
+    return 1;
+  }
+  const int G = reduce_groups(pl, g, nchunk);
+  double* pm = d_part;
+  double* ps = d_part + nout * G;
+  dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
+  (void)n_outer;
+  k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
+                                          pm, ps, d_gmax, PB, nchunk);
+  k_reduce_combine<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(pm, ps, nout, G, d_mx, d_sum);
+  return 2;
+}
+
 void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const double* d_log_dv,
                         const double* d_log_lw, uint32_t keep_mask, int density, double* out,
                         cudaStream_t st) {
@@ -314,35 +449,36 @@ void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const do
   PKM_REQUIRE(nchunk < (1LL << 31), "too many pixels");
   const bool lw = d_log_lw != nullptr;
   const int fgrid = (int)std::min<long long>((nout + 255) / 256, (long long)pl->num_sms * 16);
-
-  // scratch: [gmax, total] (+ mx[nout] unless all axes are kept)
   const bool all_kept = keep_mask == 0xF;
-  pl->misc.reserve(sizeof(double) * (size_t)(2 + (all_kept ? 1 : nout) + 2));
+
+  // scratch: [gmax, total, mx0, sum0] + mx[nout] + partial pairs (x dropped)
+  ReduceGeom g0 = g;
+  g0.kt = g0.kv = g0.kx = g0.kz = 0;
+  const size_t n_mx = all_kept ? 0 : (size_t)nout;
+  const size_t n_part = all_kept ? 2 * (size_t)reduce_groups(pl, g0, nchunk)
+                                 : (g.kx ? 0 : 2 * (size_t)nout * reduce_groups(pl, g, nchunk));
+  pl->misc.reserve(sizeof(double) * (4 + n_mx + n_part));
   double* d_gmax = pl->misc.as<double>();
   double* d_total = d_gmax + 1;
-  double* d_mx = d_gmax + 2;
+  double* d_mx0 = d_gmax + 2;
+  double* d_sum0 = d_gmax + 3;
+  double* d_mx = d_gmax + 4;
+  double* d_part = d_mx + n_mx;
   k_fill<<<1, 32, 0, st>>>(d_gmax, 1, -INFINITY);
   k_fill<<<1, 32, 0, st>>>(d_total, 1, 0.0);
+  pl->launches += 2;
 
   if (all_kept) {
     const int grid = (int)std::min<long long>((ntot + 255) / 256, (long long)pl->num_sms * 16);
     k_reduce_identity<<<grid, 256, 0, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, out, ntot);
-    pl->launches += 3;
+    pl->launches += 1;
     if (lw) {
-      // normalisation: scalar log-sum-exp of the weighted array (two more passes)
-      ReduceGeom g0 = g;
-      g0.kt = g0.kv = g0.kx = g0.kz = 0;
-      double* d_mx0 = d_mx;      // 1 element
-      double* d_sum0 = d_mx + 1; // 1 element
-      k_fill<<<1, 32, 0, st>>>(d_mx0, 1, -INFINITY);
-      k_fill<<<1, 32, 0, st>>>(d_sum0, 1, 0.0);
-      dim3 grid0((unsigned)nchunk, 1, 1);
-      k_reduce_pass<0><<<grid0, 256, 0, st>>>(logp, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx0, d_sum0, nullptr, PB);
-      k_reduce_pass<1><<<grid0, 256, 0, st>>>(logp, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx0, d_sum0, nullptr, PB);
+      // normalisation: scalar log-sum-exp of the weighted array (one more pass)
+      pl->launches += reduce_online(pl, logp, g0, d_log_dv, d_log_lw, d_mx0, d_sum0, d_part, 1, nullptr, st);
       // d_sum0 <- mx0 + log(sum0) = log normalisation (finalize on the 1-element array)
       k_reduce_finalize<<<1, 32, 0, st>>>(d_sum0, d_mx0, 1, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, nullptr, nullptr, 0);
       k_sub_density<<<grid, 256, 0, st>>>(out, ntot, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_sum0, density);
-      pl->launches += 6;
+      pl->launches += 2;
     } else if (density) {
       k_sub_density<<<grid, 256, 0, st>>>(out, ntot, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, nullptr, density);
       pl->launches += 1;
@@ -351,16 +487,12 @@ void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const do
     return;
   }
 
-  k_fill<<<fgrid, 256, 0, st>>>(d_mx, nout, -INFINITY);
-  k_fill<<<fgrid, 256, 0, st>>>(out, nout, 0.0);
-  dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
-  k_reduce_pass<0><<<grid, 256, 0, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx, out, lw ? d_gmax : nullptr, PB);
-  k_reduce_pass<1><<<grid, 256, 0, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, d_mx, out, nullptr, PB);
+  pl->launches += reduce_online(pl, logp, g, d_log_dv, d_log_lw, d_mx, out, d_part, nout, lw ? d_gmax : nullptr, st);
   if (lw) k_reduce_total<<<fgrid, 256, 0, st>>>(d_mx, out, nout, d_gmax, d_total);
   k_reduce_finalize<<<fgrid, 256, 0, st>>>(out, d_mx, nout, g, pl->d_log_dt, d_log_dv, pl->d_log_dz,
                                            lw ? d_gmax : nullptr, lw ? d_total : nullptr, density);
   PKM_CUDA(cudaGetLastError());
-  pl->launches += 6 + (lw ? 1 : 0);
+  pl->launches += 1 + (lw ? 1 : 0);
 }
 
 void launch_moments(const double* P, const double* values, int64_t nvar, int64_t ncond, double* out,
