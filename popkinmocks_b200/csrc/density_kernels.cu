@@ -100,6 +100,20 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+#ifdef PKM_K1_PROF
+__device__ unsigned long long k1_prof[32];
+#define K1_TICK(slot)                                                        \
+  do {                                                                       \
+    if (blockIdx.x == 0 && lane == 0 && warp == 0) {                         \
+      const long long now_ = clock64();                                      \
+      atomicAdd(&k1_prof[grp * 16 + (slot)], (unsigned long long)(now_ - tick_)); \
+      tick_ = now_;                                                          \
+    }                                                                        \
+  } while (0)
+#else
+#define K1_TICK(slot) do {} while (0)
+#endif
+
 template <int TM>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tmap, K1Geom g,
@@ -185,6 +199,9 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
   };
 
   unsigned phases = 0u;      // bit b = parity the next TMA completion on buffer b will have
+#ifdef PKM_K1_PROF
+  long long tick_ = clock64();
+#endif
   bool cur_tma = false, next_tma = false;
   const long long tstep = (long long)gridDim.x * g.ngroup;
   long long tile = (long long)blockIdx.x * g.ngroup + grp;
@@ -199,6 +216,7 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
     } else {
       group_sync();
     }
+    K1_TICK(0);
     const int t = (int)(tile / nxb);
     const int xb = (int)(tile - (long long)t * nxb);
     double* Bs = Bbuf + (size_t)b * buf_elems;
@@ -216,7 +234,9 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
       *pa = make_double2(a.x + bb.x, a.y + bb.y);
       if (rp != rm) *pb = make_double2(a.x - bb.x, a.y - bb.y);
     }
+    K1_TICK(1);
     group_sync();
+    K1_TICK(2);
     // phase 2: FP64 tensor-core GEMM (DMMA m8n8k4).  One work item per warp = (16-column chunk,
     // real | imaginary part): MB x 2 accumulator tiles of 8x8; per k-step of 4 rolled velocities
     // a lane loads MB A-fragment doubles (pre-arranged, conflict-free) and 2 B-fragment doubles
@@ -253,7 +273,9 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
         }
       }
     }
+    K1_TICK(3);
     group_sync();  // every warp of the group is done reading the slab: reuse it as the staging area
+    K1_TICK(4);
     // phase 3: Cs[z][m][x] complex; lane holds C[row fr][cols 2 fk, 2 fk + 1] of every 8x8 tile
     double* Cs = Bs;
     if (item < nitem) {
@@ -272,7 +294,9 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
           }
         }
     }
+    K1_TICK(5);
     group_sync();
+    K1_TICK(6);
     // phase 4: cT[x/32][t*nz + z][m][x%32]
     for (int i = tid; i < nz * nfi * pxb; i += GT) {
       const int zm = i / pxb, xs = i - zm * pxb;
@@ -285,8 +309,188 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
       else cT[ci] = v;
     }
     // order this tile's generic-proxy accesses to the buffer before the TMA refill of it
+    K1_TICK(7);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     group_sync();
+    K1_TICK(8);
+  }
+}
+
+// exp for the fold phase of the octet kernel, which runs at the FP64-pipe limit with the library
+// exp (~26 FP64 instructions): k = rint(x 64/ln 2), exp(x) = 2^(k>>6) * T[k&63] * e^r with a 64-entry
+// table of 2^(j/64) and a degree-6 polynomial on |r| <= ln2/128 (truncation 3e-20) - 11 FP64
+// instructions, error < 2 ulp.  Below -708 the result is flushed to 0 (the library would return
+// a denormal < 3e-308), above 709 it is +inf.
+__constant__ double c_exp2_tab[64];
+__device__ __forceinline__ double exp_tab64(double x, const double* __restrict__ tab) {
+  const double t = fma(x, 92.332482616893658071, 6755399441055744.0);   // 64/ln2, 1.5 * 2^52
+  const int k = __double2loint(t);
+  const double fk = t - 6755399441055744.0;
+  double r = fma(fk, -1.08304246932675596326e-02, x);                    // ln2/64 high part
+  r = fma(fk, -2.98158582698529328128e-12, r);                           // ln2/64 low part
+  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  const double p = fma(r * r, q, r);                                     // e^r - 1
+  const double T = tab[k & 63];
+  const double v = fma(T, p, T);                                         // in [1, 2.02)
+  const double y = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+  return x < -708.0 ? 0.0 : (x > 709.0 ? INFINITY : y);
+}
+
+// ----------------------------------------------------------------------------
+// Variant used whenever the slab can be fetched as one 2-D tensor copy: one warp = (metallicity z,
+// 8 consecutive pixels), real AND imaginary part.  The 8 columns of a warp's DMMA tile are then 8
+// pixels of one (t,z) row of the output layout cT[x/32][tz][m][x%32], and a lane ends up holding
+// the complex coefficients of two adjacent pixels: they go from the accumulator registers
+// straight to global memory as 16-byte stores.  No staging pass, no second sweep over shared
+// memory, two CTA barriers per tile instead of five, and all 12 warps issue DMMAs at the same time.
+// Tile = (age t, PXB = 8 or 16 pixels); the slab buffer is free as soon as the GEMM has read it, so
+// the tensor copy of tile i+2 is issued there while tile i is being stored.
+// ----------------------------------------------------------------------------
+template <int TM>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __restrict__ CRt,
+            const double* __restrict__ CIt, double2* __restrict__ cT) {
+  extern __shared__ __align__(128) double smem[];
+  constexpr int MB = TM;
+  const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, pxb = g.pxb, v0 = g.v0;
+  const int nks = (ne + 3) >> 2;
+  const int frag_elems = nks * MB * 32;
+  const int NC = pxb * nz;                       // dense box pitch (a multiple of 16)
+  const int buf_elems = nv * NC;
+  double* As_r = smem;
+  double* As_i = As_r + frag_elems;
+  double* Bbuf = As_i + frag_elems;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Bbuf + 2 * (size_t)buf_elems);
+  double* exp_tab = reinterpret_cast<double*>(bars + 2);                 // [64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < frag_elems; i += K1_THREADS) {
+    As_r[i] = CRt[i];
+    As_i[i] = CIt[i];
+  }
+  if (tid < 64) exp_tab[tid] = c_exp2_tab[tid];
+  const unsigned bar0 = smem_u32(bars);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nxb = (g.npix_tile + pxb - 1) / pxb;
+  const long long ntile = (long long)nxb * g.nt;
+  const long long tstep = gridDim.x;
+  auto issue = [&](long long tile, int b) {      // thread 0 only
+    const int t = (int)(tile / nxb);
+    const int xb = (int)(tile - (long long)t * nxb);
+    const unsigned bar = bar0 + 8u * b;
+    mbar_expect_tx(bar, (unsigned)buf_elems * 8u);
+    tensor2d_g2s(smem_u32(Bbuf + (size_t)b * buf_elems), &tmap,
+                 (int)((g.pix0 + (long long)xb * pxb) * nz), t * nv, bar);
+  };
+  long long tile = blockIdx.x;
+  if (tid == 0) {
+    if (tile < ntile) issue(tile, 0);
+    if (tile + tstep < ntile) issue(tile + tstep, 1);
+  }
+  // this warp's GEMM item and this thread's slice of the fold (both tile independent)
+  const int nitem = nz * (pxb >> 3);
+  const int iz = warp % nz, oct = warp / nz;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int half = NC >> 1;                      // double2 columns per velocity row
+  const int fu0 = tid / half, fc0 = tid - fu0 * half;
+  const int fdu = K1_THREADS / half, fdc = K1_THREADS - fdu * half;
+
+  unsigned phases = 0u;
+#ifdef PKM_K1_PROF
+  const int grp = 0;
+  long long tick_ = clock64();
+#endif
+  for (int it = 0; tile < ntile; tile += tstep, ++it) {
+    const int b = it & 1;
+    mbar_wait(bar0 + 8u * b, (phases >> b) & 1u);
+    phases ^= 1u << b;
+    K1_TICK(0);
+    const int t = (int)(tile / nxb);
+    const int xb = (int)(tile - (long long)t * nxb);
+    double* Bs = Bbuf + (size_t)b * buf_elems;
+    // fold v <-> -v in place (e = sum, o = difference of the rolled profile), exp fused; two
+    // row pairs per pass so that eight exps are in flight per thread
+    for (int u = fu0, c2 = fc0; u < ne;) {
+      int u2 = u + fdu, c22 = c2 + fdc;
+      if (c22 >= half) { c22 -= half; ++u2; }
+      const bool two = u2 < ne;
+      double2* pa = reinterpret_cast<double2*>(Bs + (size_t)row_plus(u, v0, nv) * NC) + c2;
+      double2* pb = reinterpret_cast<double2*>(Bs + (size_t)row_minus(u, v0, nv) * NC) + c2;
+      double2* qa = reinterpret_cast<double2*>(Bs + (size_t)row_plus(two ? u2 : u, v0, nv) * NC) + (two ? c22 : c2);
+      double2* qb = reinterpret_cast<double2*>(Bs + (size_t)row_minus(two ? u2 : u, v0, nv) * NC) + (two ? c22 : c2);
+      double2 a = *pa, bb = *pb, c = *qa, d = *qb;
+      if (g.is_log) {
+        a.x = exp_tab64(a.x, exp_tab); a.y = exp_tab64(a.y, exp_tab);
+        bb.x = exp_tab64(bb.x, exp_tab); bb.y = exp_tab64(bb.y, exp_tab);
+        c.x = exp_tab64(c.x, exp_tab); c.y = exp_tab64(c.y, exp_tab);
+        d.x = exp_tab64(d.x, exp_tab); d.y = exp_tab64(d.y, exp_tab);
+      }
+      *pa = make_double2(a.x + bb.x, a.y + bb.y);
+      if (pa != pb) *pb = make_double2(a.x - bb.x, a.y - bb.y);
+      if (two) {
+        *qa = make_double2(c.x + d.x, c.y + d.y);
+        if (qa != qb) *qb = make_double2(c.x - d.x, c.y - d.y);
+      }
+      u = u2 + fdu;
+      c2 = c22 + fdc;
+      if (c2 >= half) { c2 -= half; ++u; }
+    }
+    K1_TICK(1);
+    __syncthreads();
+    K1_TICK(2);
+    // GEMM on the FP64 tensor cores: C[m][x] for this warp's 8 pixels at metallicity iz
+    double accr[MB][2], acci[MB][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) accr[mb][0] = accr[mb][1] = acci[mb][0] = acci[mb][1] = 0.0;
+    if (warp < nitem) {
+      const double* Bcol = Bs + (oct * 8 + fr) * nz + iz;
+      const double* Ar = As_r + lane;
+      const double* Ai = As_i + lane;
+      for (int ks = 0; ks < nks; ++ks) {
+        // E[u] lives in row +u, O[u] (u >= 1) in row -u of the folded slab; u >= K has zero A
+        const int ue = min(ks * 4 + fk, ne - 1), uo = min(ks * 4 + fk, no - 1);
+        const double be = Bcol[(size_t)row_plus(ue, v0, nv) * NC];
+        const double bo = Bcol[(size_t)row_minus(uo + 1, v0, nv) * NC];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          dmma_m8n8k4(accr[mb][0], accr[mb][1], Ar[(ks * MB + mb) * 32], be);
+          dmma_m8n8k4(acci[mb][0], acci[mb][1], Ai[(ks * MB + mb) * 32], bo);
+        }
+      }
+    }
+    K1_TICK(3);
+    // every warp is done with the slab: refill it with the tile after next, then store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    K1_TICK(4);
+    if (tid == 0 && tile + 2 * tstep < ntile) issue(tile + 2 * tstep, b);
+    if (warp < nitem) {
+      const int xg0 = xb * pxb + oct * 8;
+      const size_t base = (((size_t)(xg0 >> 5) * g.nt * nz + (size_t)t * nz + iz) * nfi) * 32 + (xg0 & 31) + 2 * fk;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int m = mb * 8 + fr;
+        if (m < nfi) {
+          const size_t ci = base + (size_t)m * 32;
+          // two adjacent pixels = one full 32-byte sector (ci is even): a single 256-bit store
+          if (g.out_f32)
+            *reinterpret_cast<float4*>(reinterpret_cast<float2*>(cT) + ci) =
+                make_float4((float)accr[mb][0], (float)acci[mb][0], (float)accr[mb][1], (float)acci[mb][1]);
+          else
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(cT + ci), "d"(accr[mb][0]),
+                         "d"(acci[mb][0]), "d"(accr[mb][1]), "d"(acci[mb][1]) : "memory");
+        }
+      }
+    }
+    K1_TICK(5);
   }
 }
 
@@ -311,6 +515,9 @@ void density_tables_upload(pkm_plan* pl) {
   pl->nfiP = nks * pl->TM * 32;  // doubles per A operand
   upload_fragments(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, nks, &pl->d_CRt);
   upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt);
+  double tab[64];
+  for (int j = 0; j < 64; ++j) tab[j] = (double)exp2l((long double)j / 64.0L);
+  PKM_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
 }
 
 // [rows][cols] float64 matrix view of the density, box = box_rows x box_cols (tiled, no swizzle)
@@ -394,7 +601,81 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   KernelTimer tm(pl, PKM_K_COEFF, st);
   k_coeff<TM><<<grid, K1_THREADS, smem, st>>>(dens, tmap, g, pl->d_CRt, pl->d_CIt, cT);
   PKM_CUDA(cudaGetLastError());
+#ifdef PKM_K1_PROF
+  {
+    unsigned long long h[32];
+    PKM_CUDA(cudaStreamSynchronize(st));
+    PKM_CUDA(cudaMemcpyFromSymbol(h, k1_prof, sizeof(h)));
+    const long long tiles_per_group = (ntile / ngroup + grid - 1) / grid;
+    for (int gi = 0; gi < ngroup; ++gi) {
+      fprintf(stderr, "k1prof grp%d tiles~%lld cyc/tile:", gi, tiles_per_group);
+      for (int k = 0; k < 9; ++k) fprintf(stderr, " %llu", h[gi * 16 + k] / (unsigned long long)std::max<long long>(tiles_per_group, 1));
+      fprintf(stderr, "\n");
+    }
+    memset(h, 0, sizeof(h));
+    PKM_CUDA(cudaMemcpyToSymbol(k1_prof, h, sizeof(h)));
+  }
+#endif
   pl->launches++;
+}
+
+// Pixel block of the octet variant: 16 or 8 pixels such that there are 6..12 (z, octet) items
+// (one per warp), the box is a legal tensor-map box and two slab buffers fit shared memory.
+static int coeff_oct_pxb(const pkm_plan* pl) {
+  const char* force = getenv("PKM_COEFF_KERNEL");      // "0" = always the staged kernel
+  if (force && atoi(force) == 0) return 0;
+  const char* mode = getenv("PKM_COEFF_TMA_MODE");     // the fallbacks under test need the staged kernel
+  if (mode && atoi(mode) < 2) return 0;
+  for (int pxb : {16, 8}) {
+    const int NC = pxb * pl->d.nz, nitem = pl->d.nz * (pxb / 8);
+    if (NC % 16 != 0 || NC > 256 || pl->d.nv > 256 || nitem > K1_WARPS || nitem < 6) continue;
+    const size_t bytes = ((size_t)2 * pl->nfiP + (size_t)2 * pl->d.nv * NC + 64) * sizeof(double) + 16;
+    if (bytes <= 227 * 1024) return pxb;
+  }
+  return 0;
+}
+
+template <int TM>
+static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
+                               int64_t pix0, int npix_tile, int xpad, double2* cT, cudaStream_t st) {
+  const int pxb = coeff_oct_pxb(pl);
+  const int nz = pl->d.nz, nv = pl->d.nv;
+  if (!pxb) return false;
+  const int NC = pxb * nz;
+  const bool base_ok = reinterpret_cast<uintptr_t>(dens) % 16 == 0 && (npix_total * nz) % 2 == 0 &&
+                       npix_total * nz < (1LL << 31);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (!base_ok || !encode_density_map(&tmap, dens, npix_total * nz, (int64_t)pl->d.nt * nv, NC, nv)) return false;
+  const size_t smem = ((size_t)2 * pl->nfiP + (size_t)2 * nv * NC + 64) * sizeof(double) + 16;
+  PKM_CUDA(cudaFuncSetAttribute(k_coeff_oct<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntile = (int64_t)((npix_tile + pxb - 1) / pxb) * pl->d.nt;
+  const int grid = (int)std::min<int64_t>(ntile, pl->num_sms);
+  K1Geom g;
+  g.ngroup = 1;
+  g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile; g.xpad = xpad;
+  g.nv = nv; g.nz = nz; g.nfi = pl->nfi; g.ne = pl->fold.ne; g.no = pl->fold.no;
+  g.pxb = pxb; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
+  g.out_f32 = pl->d.precision == 1;
+  g.use_tma = 2;
+  KernelTimer tm(pl, PKM_K_COEFF, st);
+  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, g, pl->d_CRt, pl->d_CIt, cT);
+  PKM_CUDA(cudaGetLastError());
+#ifdef PKM_K1_PROF
+  {
+    unsigned long long h[32];
+    PKM_CUDA(cudaStreamSynchronize(st));
+    PKM_CUDA(cudaMemcpyFromSymbol(h, k1_prof, sizeof(h)));
+    const long long tiles = std::max<long long>((ntile + grid - 1) / grid, 1);
+    fprintf(stderr, "k1oct pxb=%d tiles~%lld cyc/tile:", pxb, tiles);
+    for (int k = 0; k < 6; ++k) fprintf(stderr, " %llu", h[k] / (unsigned long long)tiles);
+    fprintf(stderr, "\n");
+    memset(h, 0, sizeof(h));
+    PKM_CUDA(cudaMemcpyToSymbol(k1_prof, h, sizeof(h)));
+  }
+#endif
+  pl->launches++;
+  return true;
 }
 
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total, int64_t pix0,
@@ -402,6 +683,14 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
   int ngroup = 1;
   const int pxb = coeff_choose_pxb(pl, &ngroup);
   PKM_REQUIRE(xpad % 32 == 0 && xpad >= npix_tile, "internal: xpad=%d not a multiple of 32", xpad);
+  bool done = false;
+  switch (pl->TM) {
+#define CASE(T) case T: done = launch_coeff_oct_t<T>(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, cT, st); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    default: break;
+  }
+  if (done) return;
   switch (pl->TM) {
 #define CASE(T) case T: launch_coeff_t<T>(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, pxb, ngroup, cT, st); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
