@@ -316,26 +316,30 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
   }
 }
 
-// exp for the fold phase of the octet kernel, which runs at the FP64-pipe limit with the library
-// exp (~26 FP64 instructions): k = rint(x 64/ln 2), exp(x) = 2^(k>>6) * T[k&63] * e^r with a 64-entry
-// table of 2^(j/64) and a degree-6 polynomial on |r| <= ln2/128 (truncation 3e-20) - 11 FP64
-// instructions, error < 2 ulp.  Below -708 the result is flushed to 0 (the library would return
-// a denormal < 3e-308), above 709 it is +inf.
-__constant__ double c_exp2_tab[64];
-__device__ __forceinline__ double exp_tab64(double x, const double* __restrict__ tab) {
-  const double t = fma(x, 92.332482616893658071, 6755399441055744.0);   // 64/ln2, 1.5 * 2^52
+// exp for the fold phase of the octet kernel, which ran at the FP64-pipe limit with the library
+// exp (~26 FP64 instructions): k = rint(x 16/ln 2), exp(x) = 2^(k>>4) * T[k&15] * e^r with a 16-entry
+// table of 2^(j/16) and a degree-8 polynomial on |r| <= ln2/32 (truncation 3e-21) - 13 FP64
+// instructions, error < 2 ulp.  The table is one 128-byte shared-memory row: every entry sits in
+// its own bank, so the data-dependent lookup never conflicts (a 64-entry table did, and made the
+// fold shared-memory bound).  Below -708 the result is flushed to 0 (the library would return a
+// denormal < 3e-308), above 709 it is +inf.
+__constant__ double c_exp2_tab[16];
+__device__ __forceinline__ double exp_tab16(double x, const double* __restrict__ tab) {
+  const double t = fma(x, 23.083120654223414518, 6755399441055744.0);   // 16/ln2, 1.5 * 2^52
   const int k = __double2loint(t);
   const double fk = t - 6755399441055744.0;
-  double r = fma(fk, -1.08304246932675596326e-02, x);                    // ln2/64 high part
-  r = fma(fk, -2.98158582698529328128e-12, r);                           // ln2/64 low part
-  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  double r = fma(fk, -4.33216987730702385306e-02, x);                    // ln2/16 high part
+  r = fma(fk, -1.19263433079411731251e-11, r);                           // ln2/16 low part
+  double q = fma(r, 1.0 / 40320.0, 1.0 / 5040.0);
+  q = fma(q, r, 1.0 / 720.0);
+  q = fma(q, r, 1.0 / 120.0);
   q = fma(q, r, 1.0 / 24.0);
   q = fma(q, r, 1.0 / 6.0);
   q = fma(q, r, 0.5);
   const double p = fma(r * r, q, r);                                     // e^r - 1
-  const double T = tab[k & 63];
-  const double v = fma(T, p, T);                                         // in [1, 2.02)
-  const double y = __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+  const double T = tab[k & 15];
+  const double v = fma(T, p, T);                                         // in [1, 2.05)
+  const double y = __hiloint2double(__double2hiint(v) + ((k >> 4) << 20), __double2loint(v));
   return x < -708.0 ? 0.0 : (x > 709.0 ? INFINITY : y);
 }
 
@@ -363,14 +367,14 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
   double* As_r = smem;
   double* As_i = As_r + frag_elems;
   double* Bbuf = As_i + frag_elems;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Bbuf + 2 * (size_t)buf_elems);
-  double* exp_tab = reinterpret_cast<double*>(bars + 2);                 // [64]
+  double* exp_tab = Bbuf + 2 * (size_t)buf_elems;                        // [16], one 128-byte aligned row
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(exp_tab + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < frag_elems; i += K1_THREADS) {
     As_r[i] = CRt[i];
     As_i[i] = CIt[i];
   }
-  if (tid < 64) exp_tab[tid] = c_exp2_tab[tid];
+  if (tid < 16) exp_tab[tid] = c_exp2_tab[tid];
   const unsigned bar0 = smem_u32(bars);
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -403,6 +407,23 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
   const int fu0 = tid / half, fc0 = tid - fu0 * half;
   const int fdu = K1_THREADS / half, fdc = K1_THREADS - fdu * half;
 
+  // accumulators: C[m = mb*8 + fr][pixels 2 fk, 2 fk + 1] of this warp's item, real and imaginary
+  double accr[MB][2] = {}, acci[MB][2] = {};
+  size_t pbase = 0;          // where the pending (previous) tile's coefficients go
+  bool pending = false;
+  auto store_block = [&](int mb) {
+    const int m = mb * 8 + fr;
+    if (m < nfi) {
+      const size_t ci = pbase + (size_t)m * 32;
+      // two adjacent pixels = one full 32-byte sector (ci is even): a single 256-bit store
+      if (g.out_f32)
+        *reinterpret_cast<float4*>(reinterpret_cast<float2*>(cT) + ci) =
+            make_float4((float)accr[mb][0], (float)acci[mb][0], (float)accr[mb][1], (float)acci[mb][1]);
+      else
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(cT + ci), "d"(accr[mb][0]),
+                     "d"(acci[mb][0]), "d"(accr[mb][1]), "d"(acci[mb][1]) : "memory");
+    }
+  };
   unsigned phases = 0u;
 #ifdef PKM_K1_PROF
   const int grp = 0;
@@ -417,8 +438,11 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
     const int xb = (int)(tile - (long long)t * nxb);
     double* Bs = Bbuf + (size_t)b * buf_elems;
     // fold v <-> -v in place (e = sum, o = difference of the rolled profile), exp fused; two
-    // row pairs per pass so that eight exps are in flight per thread
-    for (int u = fu0, c2 = fc0; u < ne;) {
+    // row pairs per pass so that eight exps are in flight per thread.  The previous tile's
+    // coefficients are still in the accumulator registers: their global stores are issued between
+    // the passes, so the write queue drains behind the FP64 work instead of stalling the warp.
+    int u = fu0, c2 = fc0;
+    auto fold_pass = [&]() {
       int u2 = u + fdu, c22 = c2 + fdc;
       if (c22 >= half) { c22 -= half; ++u2; }
       const bool two = u2 < ne;
@@ -428,10 +452,10 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
       double2* qb = reinterpret_cast<double2*>(Bs + (size_t)row_minus(two ? u2 : u, v0, nv) * NC) + (two ? c22 : c2);
       double2 a = *pa, bb = *pb, c = *qa, d = *qb;
       if (g.is_log) {
-        a.x = exp_tab64(a.x, exp_tab); a.y = exp_tab64(a.y, exp_tab);
-        bb.x = exp_tab64(bb.x, exp_tab); bb.y = exp_tab64(bb.y, exp_tab);
-        c.x = exp_tab64(c.x, exp_tab); c.y = exp_tab64(c.y, exp_tab);
-        d.x = exp_tab64(d.x, exp_tab); d.y = exp_tab64(d.y, exp_tab);
+        a.x = exp_tab16(a.x, exp_tab); a.y = exp_tab16(a.y, exp_tab);
+        bb.x = exp_tab16(bb.x, exp_tab); bb.y = exp_tab16(bb.y, exp_tab);
+        c.x = exp_tab16(c.x, exp_tab); c.y = exp_tab16(c.y, exp_tab);
+        d.x = exp_tab16(d.x, exp_tab); d.y = exp_tab16(d.y, exp_tab);
       }
       *pa = make_double2(a.x + bb.x, a.y + bb.y);
       if (pa != pb) *pb = make_double2(a.x - bb.x, a.y - bb.y);
@@ -442,12 +466,20 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
       u = u2 + fdu;
       c2 = c22 + fdc;
       if (c2 >= half) { c2 -= half; ++u; }
+    };
+#pragma unroll
+    for (int j = 0; j < (MB + 1) / 2; ++j) {
+      if (u < ne) fold_pass();
+      if (pending) {
+        store_block(2 * j);
+        if (2 * j + 1 < MB) store_block(2 * j + 1);
+      }
     }
+    while (u < ne) fold_pass();
     K1_TICK(1);
     __syncthreads();
     K1_TICK(2);
     // GEMM on the FP64 tensor cores: C[m][x] for this warp's 8 pixels at metallicity iz
-    double accr[MB][2], acci[MB][2];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) accr[mb][0] = accr[mb][1] = acci[mb][0] = acci[mb][1] = 0.0;
     if (warp < nitem) {
@@ -472,25 +504,16 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
     __syncthreads();
     K1_TICK(4);
     if (tid == 0 && tile + 2 * tstep < ntile) issue(tile + 2 * tstep, b);
-    if (warp < nitem) {
+    {
       const int xg0 = xb * pxb + oct * 8;
-      const size_t base = (((size_t)(xg0 >> 5) * g.nt * nz + (size_t)t * nz + iz) * nfi) * 32 + (xg0 & 31) + 2 * fk;
-#pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
-        const int m = mb * 8 + fr;
-        if (m < nfi) {
-          const size_t ci = base + (size_t)m * 32;
-          // two adjacent pixels = one full 32-byte sector (ci is even): a single 256-bit store
-          if (g.out_f32)
-            *reinterpret_cast<float4*>(reinterpret_cast<float2*>(cT) + ci) =
-                make_float4((float)accr[mb][0], (float)acci[mb][0], (float)accr[mb][1], (float)acci[mb][1]);
-          else
-            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(cT + ci), "d"(accr[mb][0]),
-                         "d"(acci[mb][0]), "d"(accr[mb][1]), "d"(acci[mb][1]) : "memory");
-        }
-      }
+      pbase = (((size_t)(xg0 >> 5) * g.nt * nz + (size_t)t * nz + iz) * nfi) * 32 + (xg0 & 31) + 2 * fk;
+      pending = warp < nitem;
     }
     K1_TICK(5);
+  }
+  if (pending) {
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) store_block(mb);
   }
 }
 
@@ -515,8 +538,8 @@ void density_tables_upload(pkm_plan* pl) {
   pl->nfiP = nks * pl->TM * 32;  // doubles per A operand
   upload_fragments(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, nks, &pl->d_CRt);
   upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt);
-  double tab[64];
-  for (int j = 0; j < 64; ++j) tab[j] = (double)exp2l((long double)j / 64.0L);
+  double tab[16];
+  for (int j = 0; j < 16; ++j) tab[j] = (double)exp2l((long double)j / 16.0L);
   PKM_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
 }
 
@@ -629,7 +652,7 @@ static int coeff_oct_pxb(const pkm_plan* pl) {
   for (int pxb : {16, 8}) {
     const int NC = pxb * pl->d.nz, nitem = pl->d.nz * (pxb / 8);
     if (NC % 16 != 0 || NC > 256 || pl->d.nv > 256 || nitem > K1_WARPS || nitem < 6) continue;
-    const size_t bytes = ((size_t)2 * pl->nfiP + (size_t)2 * pl->d.nv * NC + 64) * sizeof(double) + 16;
+    const size_t bytes = ((size_t)2 * pl->nfiP + (size_t)2 * pl->d.nv * NC + 16) * sizeof(double) + 16;
     if (bytes <= 227 * 1024) return pxb;
   }
   return 0;
@@ -647,7 +670,7 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!base_ok || !encode_density_map(&tmap, dens, npix_total * nz, (int64_t)pl->d.nt * nv, NC, nv)) return false;
-  const size_t smem = ((size_t)2 * pl->nfiP + (size_t)2 * nv * NC + 64) * sizeof(double) + 16;
+  const size_t smem = ((size_t)2 * pl->nfiP + (size_t)2 * nv * NC + 16) * sizeof(double) + 16;
   PKM_CUDA(cudaFuncSetAttribute(k_coeff_oct<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntile = (int64_t)((npix_tile + pxb - 1) / pxb) * pl->d.nt;
   const int grid = (int)std::min<int64_t>(ntile, pl->num_sms);
