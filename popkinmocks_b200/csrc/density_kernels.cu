@@ -317,29 +317,26 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
 }
 
 // exp for the fold phase of the octet kernel, which ran at the FP64-pipe limit with the library
-// exp (~26 FP64 instructions): k = rint(x 16/ln 2), exp(x) = 2^(k>>4) * T[k&15] * e^r with a 16-entry
-// table of 2^(j/16) and a degree-8 polynomial on |r| <= ln2/32 (truncation 3e-21) - 13 FP64
-// instructions, error < 2 ulp.  The table is one 128-byte shared-memory row: every entry sits in
-// its own bank, so the data-dependent lookup never conflicts (a 64-entry table did, and made the
-// fold shared-memory bound).  Below -708 the result is flushed to 0 (the library would return a
-// denormal < 3e-308), above 709 it is +inf.
-__constant__ double c_exp2_tab[16];
-__device__ __forceinline__ double exp_tab16(double x, const double* __restrict__ tab) {
-  const double t = fma(x, 23.083120654223414518, 6755399441055744.0);   // 16/ln2, 1.5 * 2^52
+// exp (~26 FP64 instructions): k = rint(x 256/ln 2), exp(x) = 2^(k>>8) * T[k&255] * e^r with a
+// 256-entry table of 2^(j/256) in shared memory and a degree-4 polynomial on |r| <= ln2/512
+// (truncation 4e-17) - 9 FP64 instructions, error < 2 ulp.  (A conflict-free 16-entry table with a
+// degree-8 polynomial measured slower: the fold is bound by FP64 issue, not by the lookups.)
+// Below -708 the result is flushed to 0 (the library would return a denormal < 3e-308), above
+// 709 it is +inf.
+constexpr int EXP_TAB = 256;
+__constant__ double c_exp2_tab[EXP_TAB];
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+  const double t = fma(x, 369.32993046757463228, 6755399441055744.0);   // 256/ln2, 1.5 * 2^52
   const int k = __double2loint(t);
   const double fk = t - 6755399441055744.0;
-  double r = fma(fk, -4.33216987730702385306e-02, x);                    // ln2/16 high part
-  r = fma(fk, -1.19263433079411731251e-11, r);                           // ln2/16 low part
-  double q = fma(r, 1.0 / 40320.0, 1.0 / 5040.0);
-  q = fma(q, r, 1.0 / 720.0);
-  q = fma(q, r, 1.0 / 120.0);
-  q = fma(q, r, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
+  double r = fma(fk, -2.70760617331688990816e-03, x);                    // ln2/256 high part
+  r = fma(fk, -7.45396456746323320321e-13, r);                           // ln2/256 low part
+  double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
   q = fma(q, r, 0.5);
   const double p = fma(r * r, q, r);                                     // e^r - 1
-  const double T = tab[k & 15];
-  const double v = fma(T, p, T);                                         // in [1, 2.05)
-  const double y = __hiloint2double(__double2hiint(v) + ((k >> 4) << 20), __double2loint(v));
+  const double T = tab[k & (EXP_TAB - 1)];
+  const double v = fma(T, p, T);                                         // in [1, 2.01)
+  const double y = __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));
   return x < -708.0 ? 0.0 : (x > 709.0 ? INFINITY : y);
 }
 
@@ -355,26 +352,27 @@ __device__ __forceinline__ double exp_tab16(double x, const double* __restrict__
 // ----------------------------------------------------------------------------
 template <int TM>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __restrict__ CRt,
-            const double* __restrict__ CIt, double2* __restrict__ cT) {
+k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap, K1Geom g,
+            const double* __restrict__ CRt, const double* __restrict__ CIt) {
   extern __shared__ __align__(128) double smem[];
   constexpr int MB = TM;
   const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, pxb = g.pxb, v0 = g.v0;
   const int nks = (ne + 3) >> 2;
   const int frag_elems = nks * MB * 32;
   const int NC = pxb * nz;                       // dense box pitch (a multiple of 16)
-  const int buf_elems = nv * NC;
+  const int slab_elems = nv * NC;
+  const int buf_elems = (max(nv, 2 * nfi) * NC + 15) & ~15;   // slab, later the [nz][nfi][2 pxb] staging box
   double* As_r = smem;
   double* As_i = As_r + frag_elems;
   double* Bbuf = As_i + frag_elems;
-  double* exp_tab = Bbuf + 2 * (size_t)buf_elems;                        // [16], one 128-byte aligned row
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(exp_tab + 16);
+  double* etab = Bbuf + 2 * (size_t)buf_elems;                           // [EXP_TAB] 2^(j/256)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(etab + EXP_TAB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < frag_elems; i += K1_THREADS) {
     As_r[i] = CRt[i];
     As_i[i] = CIt[i];
   }
-  if (tid < 16) exp_tab[tid] = c_exp2_tab[tid];
+  for (int i = tid; i < EXP_TAB; i += K1_THREADS) etab[i] = c_exp2_tab[i];
   const unsigned bar0 = smem_u32(bars);
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -390,7 +388,7 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
     const int t = (int)(tile / nxb);
     const int xb = (int)(tile - (long long)t * nxb);
     const unsigned bar = bar0 + 8u * b;
-    mbar_expect_tx(bar, (unsigned)buf_elems * 8u);
+    mbar_expect_tx(bar, (unsigned)slab_elems * 8u);
     tensor2d_g2s(smem_u32(Bbuf + (size_t)b * buf_elems), &tmap,
                  (int)((g.pix0 + (long long)xb * pxb) * nz), t * nv, bar);
   };
@@ -407,23 +405,6 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
   const int fu0 = tid / half, fc0 = tid - fu0 * half;
   const int fdu = K1_THREADS / half, fdc = K1_THREADS - fdu * half;
 
-  // accumulators: C[m = mb*8 + fr][pixels 2 fk, 2 fk + 1] of this warp's item, real and imaginary
-  double accr[MB][2] = {}, acci[MB][2] = {};
-  size_t pbase = 0;          // where the pending (previous) tile's coefficients go
-  bool pending = false;
-  auto store_block = [&](int mb) {
-    const int m = mb * 8 + fr;
-    if (m < nfi) {
-      const size_t ci = pbase + (size_t)m * 32;
-      // two adjacent pixels = one full 32-byte sector (ci is even): a single 256-bit store
-      if (g.out_f32)
-        *reinterpret_cast<float4*>(reinterpret_cast<float2*>(cT) + ci) =
-            make_float4((float)accr[mb][0], (float)acci[mb][0], (float)accr[mb][1], (float)acci[mb][1]);
-      else
-        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(cT + ci), "d"(accr[mb][0]),
-                     "d"(acci[mb][0]), "d"(accr[mb][1]), "d"(acci[mb][1]) : "memory");
-    }
-  };
   unsigned phases = 0u;
 #ifdef PKM_K1_PROF
   const int grp = 0;
@@ -438,9 +419,7 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
     const int xb = (int)(tile - (long long)t * nxb);
     double* Bs = Bbuf + (size_t)b * buf_elems;
     // fold v <-> -v in place (e = sum, o = difference of the rolled profile), exp fused; two
-    // row pairs per pass so that eight exps are in flight per thread.  The previous tile's
-    // coefficients are still in the accumulator registers: their global stores are issued between
-    // the passes, so the write queue drains behind the FP64 work instead of stalling the warp.
+    // row pairs per pass so that eight exps are in flight per thread
     int u = fu0, c2 = fc0;
     auto fold_pass = [&]() {
       int u2 = u + fdu, c22 = c2 + fdc;
@@ -452,10 +431,10 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
       double2* qb = reinterpret_cast<double2*>(Bs + (size_t)row_minus(two ? u2 : u, v0, nv) * NC) + (two ? c22 : c2);
       double2 a = *pa, bb = *pb, c = *qa, d = *qb;
       if (g.is_log) {
-        a.x = exp_tab16(a.x, exp_tab); a.y = exp_tab16(a.y, exp_tab);
-        bb.x = exp_tab16(bb.x, exp_tab); bb.y = exp_tab16(bb.y, exp_tab);
-        c.x = exp_tab16(c.x, exp_tab); c.y = exp_tab16(c.y, exp_tab);
-        d.x = exp_tab16(d.x, exp_tab); d.y = exp_tab16(d.y, exp_tab);
+        a.x = exp_tab(a.x, etab); a.y = exp_tab(a.y, etab);
+        bb.x = exp_tab(bb.x, etab); bb.y = exp_tab(bb.y, etab);
+        c.x = exp_tab(c.x, etab); c.y = exp_tab(c.y, etab);
+        d.x = exp_tab(d.x, etab); d.y = exp_tab(d.y, etab);
       }
       *pa = make_double2(a.x + bb.x, a.y + bb.y);
       if (pa != pb) *pb = make_double2(a.x - bb.x, a.y - bb.y);
@@ -467,19 +446,19 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
       c2 = c22 + fdc;
       if (c2 >= half) { c2 -= half; ++u; }
     };
-#pragma unroll
-    for (int j = 0; j < (MB + 1) / 2; ++j) {
-      if (u < ne) fold_pass();
-      if (pending) {
-        store_block(2 * j);
-        if (2 * j + 1 < MB) store_block(2 * j + 1);
-      }
-    }
     while (u < ne) fold_pass();
     K1_TICK(1);
     __syncthreads();
     K1_TICK(2);
-    // GEMM on the FP64 tensor cores: C[m][x] for this warp's 8 pixels at metallicity iz
+    // the other buffer holds the previous tile's staged coefficients: once the store engine has
+    // read them (it had the whole fold to do so) the slab of the next tile streams in
+    if (tid == 0 && it > 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (tile + tstep < ntile) issue(tile + tstep, b ^ 1);
+    }
+    // GEMM on the FP64 tensor cores: C[m = mb*8 + fr][pixels 2 fk, 2 fk + 1] of this warp's 8 pixels
+    // at metallicity iz, real and imaginary part
+    double accr[MB][2], acci[MB][2];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) accr[mb][0] = accr[mb][1] = acci[mb][0] = acci[mb][1] = 0.0;
     if (warp < nitem) {
@@ -499,22 +478,40 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __
       }
     }
     K1_TICK(3);
-    // every warp is done with the slab: refill it with the tile after next, then store
+    __syncthreads();   // every warp is done reading the slab: it becomes the staging box
+    K1_TICK(4);
+    // stage as the output box [z][m][2 pxb] (pixel fastest, re/im interleaved): a lane owns the
+    // complex coefficients of two adjacent pixels = 32 contiguous bytes
+    if (warp < nitem) {
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int m = mb * 8 + fr;
+        if (m < nfi) {
+          const size_t o = ((size_t)iz * nfi + m) * (2 * pxb) + oct * 16 + 4 * fk;
+          if (g.out_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(Bs) + o) =
+                make_float4((float)accr[mb][0], (float)acci[mb][0], (float)accr[mb][1], (float)acci[mb][1]);
+          } else {
+            *reinterpret_cast<double2*>(Bs + o) = make_double2(accr[mb][0], acci[mb][0]);
+            *reinterpret_cast<double2*>(Bs + o + 2) = make_double2(accr[mb][1], acci[mb][1]);
+          }
+        }
+      }
+    }
+    // generic-proxy writes -> async-proxy read: one 4-D tensor store moves the whole box to
+    // cT[x/32][t*nz + z][m][x%32]; it drains behind the next tile's fold and GEMM
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    K1_TICK(4);
-    if (tid == 0 && tile + 2 * tstep < ntile) issue(tile + 2 * tstep, b);
-    {
-      const int xg0 = xb * pxb + oct * 8;
-      pbase = (((size_t)(xg0 >> 5) * g.nt * nz + (size_t)t * nz + iz) * nfi) * 32 + (xg0 & 31) + 2 * fk;
-      pending = warp < nitem;
+    if (tid == 0) {
+      const int xg0 = xb * pxb;
+      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                   ::"l"(reinterpret_cast<unsigned long long>(&omap)), "r"(2 * (xg0 & 31)), "r"(0),
+                     "r"(t * nz), "r"(xg0 >> 5), "r"(smem_u32(Bs)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     K1_TICK(5);
   }
-  if (pending) {
-#pragma unroll
-    for (int mb = 0; mb < MB; ++mb) store_block(mb);
-  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // A operand in DMMA fragment order: element [ks][mb][lane] = C[m = mb*8 + lane/4][u = ks*4 + lane%4]
@@ -538,14 +535,12 @@ void density_tables_upload(pkm_plan* pl) {
   pl->nfiP = nks * pl->TM * 32;  // doubles per A operand
   upload_fragments(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, nks, &pl->d_CRt);
   upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt);
-  double tab[16];
-  for (int j = 0; j < 16; ++j) tab[j] = (double)exp2l((long double)j / 16.0L);
+  double tab[EXP_TAB];
+  for (int j = 0; j < EXP_TAB; ++j) tab[j] = (double)exp2l((long double)j / (long double)EXP_TAB);
   PKM_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
 }
 
-// [rows][cols] float64 matrix view of the density, box = box_rows x box_cols (tiled, no swizzle)
-static bool encode_density_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows,
-                               int box_cols, int box_rows) {
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   static bool looked_up = false;
   if (!looked_up) {
@@ -558,6 +553,13 @@ static bool encode_density_map(CUtensorMap* map, const double* base, int64_t col
     else
       cudaGetLastError();
   }
+  return encode;
+}
+
+// [rows][cols] float64 matrix view of the density, box = box_rows x box_cols (tiled, no swizzle)
+static bool encode_density_map(CUtensorMap* map, const double* base, int64_t cols, int64_t rows,
+                               int box_cols, int box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensor_map_encoder();
   if (!encode) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(double)};
@@ -642,6 +644,28 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   pl->launches++;
 }
 
+static size_t coeff_oct_smem(const pkm_plan* pl, int NC) {
+  const size_t buf_elems = ((size_t)std::max(pl->d.nv, 2 * pl->nfi) * NC + 15) & ~size_t(15);
+  return ((size_t)2 * pl->nfiP + 2 * buf_elems + EXP_TAB) * sizeof(double) + 16;
+}
+
+// 4-D view of the coefficient array cT[x/32][t*nz+z][m][x%32] (complex) in scalar elements:
+// dims {64 = 32 pixels x re/im, nfi, nt*nz, xpad/32}; box = {2 pxb, nfi, nz, 1} = one tile
+static bool encode_coeff_map(CUtensorMap* map, void* cT, bool f32, int nfi, int ntz, int ngroup32,
+                             int pxb, int nz) {
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensor_map_encoder();
+  if (!encode) return false;
+  const size_t es = f32 ? sizeof(float) : sizeof(double);
+  cuuint64_t dims[4] = {64, (cuuint64_t)nfi, (cuuint64_t)ntz, (cuuint64_t)ngroup32};
+  cuuint64_t strides[3] = {64 * es, (cuuint64_t)nfi * 64 * es, (cuuint64_t)ntz * nfi * 64 * es};
+  cuuint32_t box[4] = {(cuuint32_t)(2 * pxb), (cuuint32_t)nfi, (cuuint32_t)nz, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, cT,
+                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // Pixel block of the octet variant: 16 or 8 pixels such that there are 6..12 (z, octet) items
 // (one per warp), the box is a legal tensor-map box and two slab buffers fit shared memory.
 static int coeff_oct_pxb(const pkm_plan* pl) {
@@ -652,7 +676,7 @@ static int coeff_oct_pxb(const pkm_plan* pl) {
   for (int pxb : {16, 8}) {
     const int NC = pxb * pl->d.nz, nitem = pl->d.nz * (pxb / 8);
     if (NC % 16 != 0 || NC > 256 || pl->d.nv > 256 || nitem > K1_WARPS || nitem < 6) continue;
-    const size_t bytes = ((size_t)2 * pl->nfiP + (size_t)2 * pl->d.nv * NC + 16) * sizeof(double) + 16;
+    const size_t bytes = coeff_oct_smem(pl, NC);
     if (bytes <= 227 * 1024) return pxb;
   }
   return 0;
@@ -670,7 +694,12 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!base_ok || !encode_density_map(&tmap, dens, npix_total * nz, (int64_t)pl->d.nt * nv, NC, nv)) return false;
-  const size_t smem = ((size_t)2 * pl->nfiP + (size_t)2 * nv * NC + 16) * sizeof(double) + 16;
+  CUtensorMap omap;
+  memset(&omap, 0, sizeof(omap));
+  if (nz > 256 || pl->nfi > 256 ||
+      !encode_coeff_map(&omap, cT, pl->d.precision == 1, pl->nfi, pl->d.nt * nz, xpad / 32, pxb, nz))
+    return false;
+  const size_t smem = coeff_oct_smem(pl, NC);
   PKM_CUDA(cudaFuncSetAttribute(k_coeff_oct<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntile = (int64_t)((npix_tile + pxb - 1) / pxb) * pl->d.nt;
   const int grid = (int)std::min<int64_t>(ntile, pl->num_sms);
@@ -682,7 +711,7 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   g.out_f32 = pl->d.precision == 1;
   g.use_tma = 2;
   KernelTimer tm(pl, PKM_K_COEFF, st);
-  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, g, pl->d_CRt, pl->d_CIt, cT);
+  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt);
   PKM_CUDA(cudaGetLastError());
 #ifdef PKM_K1_PROF
   {
