@@ -54,6 +54,24 @@ def test_density_path_matches_reference(gpu_ok, name, tags):
         assert rel_err(y2, ref) < TOL
 
 
+@pytest.mark.parametrize("env", [
+    {"PKM_COEFF_KERNEL": "0"},                                  # staged kernel, 2-D tensor copies
+    {"PKM_COEFF_TMA_MODE": "1"},                                # staged kernel, 1-D bulk copies
+    {"PKM_COEFF_TMA_MODE": "0"},                                # staged kernel, plain loads
+    {"PKM_COEFF_KERNEL": "0", "PKM_COEFF_GROUPS": "1"},         # staged kernel, one warp group
+])
+def test_coefficient_kernel_fallbacks_match_reference(gpu_ok, monkeypatch, env):
+    """The default path uses the octet coefficient kernel; the staged kernel and its load modes
+    (taken for shapes the tensor maps cannot describe) are forced here through the developer
+    switches and held to the same parity bar, on white-noise and pixelated-disk densities."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name, tag in (("g2_rebin_nv21_prime", "wn_"), ("g1_conftest_full_nv41", "b_"), ("g3_full_nv101_odd", "wn_")):
+        g = load_golden(name)
+        y = _plan(name).ybar_density(g[tag + "log_p_tvxz"], is_log=True)
+        assert rel_err(y, g[tag + "ybar"]) < TOL, (env, name, rel_err(y, g[tag + "ybar"]))
+
+
 def test_density_even_nv_raises_index_error(gpu_ok):
     g = load_golden("g4_even_nv40")
     assert str(g["b_error"]) == "IndexError"

@@ -56,7 +56,7 @@ def main():
         scale = 1.0
         if len(sys.argv) > 6:
             scale = (npix / float(sys.argv[6])) / float(sys.argv[5])
-        short = {"k_contract": "contract", "k_coeff<7>": "coeff", "k_irfft_czt": "irfft"}
+        short = {"k_contract": "contract", "k_coeff<7>": "coeff", "k_coeff_oct<7>": "coeff", "k_irfft_czt": "irfft"}
         out = {}
         for name, t in traffic.items():
             for key, s in short.items():
