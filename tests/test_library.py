@@ -75,3 +75,12 @@ def test_no_cpu_fallback_without_a_gpu():
         comp.get_p("t")
     out = ctypes.c_double()
     assert _lib.load().pkm_fp64_fma_peak(0, 1, ctypes.byref(out)) == _lib.PKM_ERR_CUDA
+    # device-side pixelation of a parametric component, through the class and through the C ABI
+    from test_host_models import BUILDERS
+    with pytest.raises(_lib.PkmError, match="no CUDA device"):
+        BUILDERS["d1_"](cube).pixelate()
+    lw, mu, sig = np.zeros((2, 3, 4)), np.zeros((2, 3)), np.ones((2, 3))
+    v_edg, res = np.linspace(-1.0, 1.0, 6), np.empty((2, 5, 3, 4))
+    rc = _lib.load().pkm_pixelate_gaussian(_lib.ptr(lw), _lib.ptr(mu), _lib.ptr(sig), _lib.ptr(v_edg),
+                                           2, 5, 3, 4, 1, _lib.ptr(res), 0, None)
+    assert rc == _lib.PKM_ERR_CUDA
