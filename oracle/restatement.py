@@ -17,7 +17,7 @@ numpy.fft.rfft/irfft (pocketfft), scipy.interpolate.interp1d(kind="cubic")
 are used here, so these functions need numpy+scipy only and travel to the GPU box.
 """
 import numpy as np
-from scipy import interpolate, special
+from scipy import interpolate, special, stats
 
 
 # ----------------------------------------------------------------------------
@@ -233,6 +233,33 @@ def standardised_moment_1d(P, values, j):
     mu = mean_1d(P, values)
     with np.errstate(invalid="ignore", divide="ignore"):
         return noncentral_moment_1d(P, values, j, mu) / noncentral_moment_1d(P, values, 2, mu) ** (0.5 * j)
+
+
+# ----------------------------------------------------------------------------
+# analytic pixelation of a Gaussian-LOSVD component
+#                       /root/reference/popkinmocks/components/parametric.py:180-211, 567-596
+# ----------------------------------------------------------------------------
+def log_p_v_tx_gaussian(mu_v, sig_v, v_edg, density=True):
+    """log p(v-bin | t,x): normal log-cdf at the bin edges, signed logsumexp of neighbouring
+    edges (parametric.py:193-200), minus log dv for a density (parametric.py:208-210).
+    mu_v, sig_v broadcastable to [t, x1, x2]; returns [v, t, x1, x2]."""
+    v_edg = np.asarray(v_edg, dtype=np.float64)[:, None, None, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        norm = stats.norm(loc=mu_v, scale=sig_v)
+        log_cdf_0 = norm.logcdf(v_edg[:-1])
+        log_cdf_1 = norm.logcdf(v_edg[1:])
+        out = special.logsumexp(np.array([log_cdf_1, log_cdf_0]).T, -1, b=[1, -1]).T
+    if density:
+        out = (out.T - np.log(np.diff(v_edg[:, 0, 0, 0]))).T
+    return out
+
+
+def pixelate_gaussian(log_p_txz, mu_v, sig_v, v_edg, density=True):
+    """log p(t,v,x,z) = log p(t,x,z) + log p(v|t,x)  (parametric.py:589-592, mass weighted).
+    `log_p_txz` [t, x1, x2, z] is the density or the volume-weighted probability, matching
+    `density`."""
+    log_p_v_tx = log_p_v_tx_gaussian(mu_v, sig_v, v_edg, density=density)
+    return np.moveaxis(log_p_v_tx[..., None], 0, 1) + np.asarray(log_p_txz)[:, None]
 
 
 # ----------------------------------------------------------------------------

@@ -410,7 +410,6 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
                          long long nout, double* d_gmax, cudaStream_t st) {
   const int PB = 256 / g.nz;
   const long long nchunk = (g.npix + PB - 1) / PB;
-  const int n_outer = (g.kt ? g.nt : 1) * (g.kv ? g.nv : 1);
   const size_t smem = sizeof(double) * ((size_t)g.nt + g.nv + (size_t)g.nt * g.nz);
   PKM_REQUIRE(smem <= 40 * 1024, "age/velocity/metallicity grid too large for the reduction kernel");
   if (g.kx) {
@@ -423,7 +422,6 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
   double* pm = d_part;
   double* ps = d_part + nout * G;
   dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
-  (void)n_outer;
   k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
                                           pm, ps, d_gmax, PB, nchunk);
   k_reduce_combine<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(pm, ps, nout, G, d_mx, d_sum);

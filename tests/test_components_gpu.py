@@ -304,8 +304,9 @@ def test_device_pixelation_matches_reference(gpu_ok):
 def test_pixelation_kernel_edge_shapes_and_tails(gpu_ok):
     """Ragged pixel counts (not a multiple of the 32-pixel chunk), several nz / nv, scalar sigma,
     host output, probabilities (density=False), means far outside the velocity range and -inf
-    weights: against the reference formula (scipy log-cdf + signed logsumexp) evaluated here."""
-    from scipy import special, stats
+    weights: against the oracle (oracle/restatement.py::pixelate_gaussian, the reference's scipy
+    log-cdf + signed logsumexp, pinned to the reference golden in tests/test_oracle.py)."""
+    from oracle import restatement as R
     rng = np.random.default_rng(11)
     for (nt, nx1, nx2, nz, nv) in [(3, 3, 11, 5, 7), (2, 1, 1, 1, 1), (4, 8, 9, 12, 40), (1, 5, 13, 3, 301)]:
         v_edg = np.linspace(-900.0, 1100.0, nv + 1)
@@ -317,12 +318,8 @@ def test_pixelation_kernel_edge_shapes_and_tails(gpu_ok):
         sig = rng.uniform(20.0, 300.0, (nt, nx1, nx2))
         for sig_in, dens in ((sig, True), (150.0, False)):
             got = pkm.engine.pixelate_gaussian(log_w, mu, sig_in, v_edg, density=dens, on_device=False)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                log_cdf = stats.norm(loc=mu, scale=sig_in).logcdf(v_edg[:, None, None, None])
-                lpv = special.logsumexp(np.array([log_cdf[1:], log_cdf[:-1]]).T, -1, b=[1, -1]).T
-            if dens:
-                lpv = (lpv.T - np.log(np.diff(v_edg))).T
-            ref = np.moveaxis(lpv, 0, 1)[..., None] + log_w[:, None]
+            lpv = R.log_p_v_tx_gaussian(mu, sig_in, v_edg, density=dens)
+            ref = R.pixelate_gaussian(log_w, mu, sig_in, v_edg, density=dens)
             assert got.shape == ref.shape and not np.isnan(got).any()
             # max-norm on probabilities; bins both sides call empty must agree where the weight is empty
             assert np.all(np.isneginf(got[np.isneginf(np.broadcast_to(log_w[:, None], ref.shape))]))

@@ -5,6 +5,7 @@ under oracle/ref_shim.py.  These tests pin every oracle function; they run witho
 """
 import numpy as np
 import pytest
+from scipy import stats
 
 from conftest import load_golden, rel_err
 from oracle import restatement as R
@@ -97,6 +98,27 @@ def test_moments(name):
             ok = np.isfinite(ref)
             out = R.standardised_moment_1d(P, values[var], j)
             assert np.allclose(out[ok], ref[ok], rtol=1e-8, atol=1e-8), (nm, k)
+
+
+def test_gaussian_pixelation():
+    """oracle pixelate_gaussian vs the reference's disk.get_log_p('tvxz') (golden g2)."""
+    g = load_golden("g2_rebin_nv21_prime")
+    grid = _grid(g)
+    log_dV = np.log(R.volume_element("txz", grid["delta_t"], grid["dv_bins"], grid["dx"], grid["dy"],
+                                     grid["delta_z"]))
+    with np.errstate(divide="ignore"):
+        log_P_txz = np.log(g["d1_P_txz"])
+    ref = g["b_log_p_tvxz"]
+    got = R.pixelate_gaussian(log_P_txz - log_dV, g["d1_mu_v"], g["d1_sig_v"], g["v_edg"], density=True)
+    assert got.shape == ref.shape
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin])) < 1e-11
+    # probabilities: log P(t,v,x,z) sums back to P(t,x,z) times the cdf mass inside the velocity range
+    logP = R.pixelate_gaussian(log_P_txz, g["d1_mu_v"], g["d1_sig_v"], g["v_edg"], density=False)
+    inside = stats.norm(g["d1_mu_v"], g["d1_sig_v"]).cdf(g["v_edg"][-1]) - \
+        stats.norm(g["d1_mu_v"], g["d1_sig_v"]).cdf(g["v_edg"][0])
+    assert np.allclose(np.exp(logP).sum(1), g["d1_P_txz"] * inside[..., None], rtol=1e-12, atol=0)
 
 
 def test_noise_sigma():
