@@ -252,11 +252,36 @@ class Component(object):
 
     # ------------------------------------------------------------------ persistence
     def dill_dump(self, fname, direc=None):
-        """Pickle this component with dill (device plans are dropped, base.py:1176-1190)."""
+        """Pickle this component with dill into `direc + fname`, creating `direc` if needed
+        (base.py:1176-1190).  Device plans and device copies are dropped from the pickle."""
         import dill
-        path = fname if direc is None else os.path.join(direc, fname)
-        with open(path, "wb") as fh:
+        with open(self._out_path(fname, direc), "wb") as fh:
             dill.dump(self, fh)
+
+    @staticmethod
+    def _out_path(fname, direc):
+        # the reference concatenates `direc + fname` (base.py:1189, 1213); `direc=None` (its
+        # default, on which it raises) writes to the working directory here
+        if direc is None:
+            return fname
+        if not os.path.isdir(direc):
+            os.mkdir(direc)
+        return direc + fname
+
+    def save_numpy(self, fname, yobs=None, direc=None):
+        """The v0.0 `npz` format (base.py:1192-1225, deprecated there in favour of `dill_dump`):
+        cube geometry, SSP templates, `ybar`, and the density rearranged to `f_xvtz`
+        [x1, x2, v, z, t].  A `Mixture` stores the component-collapsed density."""
+        cube = self.cube
+        try:
+            p_tvxz = self.get_p("tvxz", collapse_cmps=True, density=True)     # Mixture
+        except TypeError:
+            p_tvxz = self.get_p("tvxz", density=True)
+        f_xvtz = np.moveaxis(p_tvxz, [0, 1, 2, 3, 4], [4, 2, 0, 1, 3])
+        np.savez(self._out_path(fname, direc), yobs=yobs, nx1=cube.nx, nx2=cube.ny, x1rng=cube.x1rng,
+                 x2rng=cube.x2rng, S=cube.ssps.Xw.reshape((-1,) + tuple(cube.ssps.par_dims)),
+                 w=cube.ssps.w, z_bin_edges=cube.ssps.par_edges[0], t_bin_edges=cube.ssps.par_edges[1],
+                 ybar=self.ybar, v_edg=cube.v_edg, f_xvtz=f_xvtz)
 
 
 def _make_marginal(keep):

@@ -177,3 +177,39 @@ def test_mixture_distributions_match_reference_on_host():
     assert np.allclose(log_p[ok], g["b_log_p_tvxz"][ok], rtol=0, atol=1e-10)
     for lw in (False, True):
         assert np.isclose(np.sum(mix.get_p("tvxz", density=False, light_weighted=lw)), 1.0, atol=1e-6)
+
+
+def test_save_numpy_and_dill_dump_formats(tmp_path):
+    """The reference's two on-disk formats (base.py:1176-1225): the dill pickle round-trips without
+    device handles, the v0.0 npz carries the same keys and the density rearranged to f_xvtz."""
+    import dill
+    g = load_golden("g1_conftest_full_nv41")
+    cube = golden_cube("g1_conftest_full_nv41")
+    comps = [BUILDERS[t](cube) for t in ("d1_", "s1_")]
+    mix = pkm.components.Mixture(cube=cube, component_list=comps, weights=[0.7, 0.3])
+    mix.ybar = 0.7 * g["d1_ybar"] + 0.3 * g["s1_ybar"]        # stands in for evaluate_ybar (GPU)
+    direc = str(tmp_path / "out") + "/"                        # the reference concatenates direc + fname
+    mix.save_numpy("mix.npz", yobs=mix.ybar + 1.0, direc=direc)
+    z = np.load(direc + "mix.npz")
+    assert sorted(z.files) == sorted(["yobs", "nx1", "nx2", "x1rng", "x2rng", "S", "w", "z_bin_edges",
+                                      "t_bin_edges", "ybar", "v_edg", "f_xvtz"])
+    p = mix.get_p("tvxz", density=True, collapse_cmps=True)
+    nt, nv, nx1, nx2, nz = p.shape
+    assert z["f_xvtz"].shape == (nx1, nx2, nv, nz, nt)
+    assert np.array_equal(z["f_xvtz"], np.transpose(p, (2, 3, 1, 4, 0)))
+    assert z["S"].shape == (cube.ssps.Xw.shape[0], nz, nt) and np.array_equal(z["w"], cube.ssps.w)
+    assert int(z["nx1"]) == nx1 and int(z["nx2"]) == nx2 and np.array_equal(z["ybar"], mix.ybar)
+    assert z["z_bin_edges"].size == nz + 1 and z["t_bin_edges"].size == nt + 1
+    # a single parametric component goes through the same writer (no collapse_cmps argument)
+    comps[0].ybar = g["d1_ybar"]
+    comps[0].save_numpy("disk.npz", direc=direc)
+    zd = np.load(direc + "disk.npz", allow_pickle=True)
+    assert np.array_equal(zd["f_xvtz"], np.transpose(comps[0].get_p("tvxz"), (2, 3, 1, 4, 0)))
+    # dill
+    cube._pkm_plans["fake"] = object()
+    comps[0].dill_dump("disk.dill", direc=direc)
+    cube._pkm_plans.pop("fake")
+    with open(direc + "disk.dill", "rb") as fh:
+        clone = dill.load(fh)
+    assert clone.cube._pkm_plans == {} and np.array_equal(clone.ybar, comps[0].ybar)
+    assert np.array_equal(clone.mu_v, comps[0].mu_v)
