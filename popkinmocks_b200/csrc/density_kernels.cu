@@ -7,7 +7,9 @@
 // kernel 1 (coeff):    c = (A^{-1} D) p   - a small dense real->complex transform per
 //                      (t,x,z) column, done as an FP64 tensor-core (DMMA) GEMM on TMA-staged
 //                      density slabs, with the even/odd fold of the real DFT (halves the
-//                      flops) and exp(log p) fused into the fold.
+//                      flops) and exp(log p) fused into the fold.  Two variants: k_coeff_oct
+//                      (default: TMA tensor load AND store, warp = z x 8 pixels) and the
+//                      staged k_coeff (any shape / alignment).
 // kernel 2 (contract): streams S' (TMA-staged, L2 resident) and the coefficient rows, evaluates
 //                      the 4-tap spline on the fly and accumulates over (t,z) in registers.
 // P-hat (25 MB per pixel in the reference, base.py:846-853) is never materialised.
@@ -56,7 +58,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 
 
 // ============================================================================
-// kernel 1
+// kernel 1, staged variant (the fallback; the default is k_coeff_oct further down)
 // ============================================================================
 // Persistent CTAs (one per SM), each looping over tiles = (age t, block of PXB pixels), i.e.
 // NC = PXB*nz density columns of nv velocities.  The folded DFT*spline matrices stay resident
