@@ -33,9 +33,15 @@ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_doub
 // `in(idx)` supplies the inputs of the FIRST pass (so the caller's load / pre-multiply pass is
 // fused into it); if `post` is non-null every output of the LAST pass is multiplied by
 // post[idx] (the filter spectrum of the chirp-z convolution).
+// Shared-memory index padding: one empty 16-byte slot after every 32 elements.  Without it the
+// passes with small strides (radix-16 with quarter size 2 or 1) put 16 or 32 lanes of a warp on
+// the same bank group; with it every pass of every transform size is conflict-free.
+__device__ __forceinline__ int sp(int i) { return i + (i >> 5); }
+__host__ __device__ constexpr size_t sp_elems(size_t n) { return n + (n >> 5); }
+
 struct SmemInput {
   const double2* s;
-  __device__ __forceinline__ double2 operator()(int i) const { return s[i]; }
+  __device__ __forceinline__ double2 operator()(int i) const { return s[sp(i)]; }
 };
 
 // 4-point DIF butterfly (forward) and its inverse, twiddles applied by the caller
@@ -109,7 +115,7 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int idx = base + a * q + b * qq;
-          x[a][b] = first ? in(idx) : s[idx];
+          x[a][b] = first ? in(idx) : s[sp(idx)];
         }
       // All 15 twiddles of the step derive from ONE table entry u = W^(j stride): level 1 needs
       // u^m W16^(m b), level 2 (u^4)^n.  (The 128 KB table does not fit next to the 128 KB
@@ -135,7 +141,7 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int idx = base + a * q + b * qq;
-          s[idx] = last ? cmul(x[a][b], __ldg(post + idx)) : x[a][b];
+          s[sp(idx)] = last ? cmul(x[a][b], __ldg(post + idx)) : x[a][b];
         }
       }
     }
@@ -151,7 +157,7 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
       if (first) {
         a = in(base); b = in(base + q); c = in(base + 2 * q); d = in(base + 3 * q);
       } else {
-        a = s[base]; b = s[base + q]; c = s[base + 2 * q]; d = s[base + 3 * q];
+        a = s[sp(base)]; b = s[sp(base + q)]; c = s[sp(base + 2 * q)]; d = s[sp(base + 3 * q)];
       }
       bfly4_fwd(a, b, c, d);
       const double2* tp = twp + (M - 4 * q) + j;
@@ -164,23 +170,23 @@ __device__ void fft_forward(double2* s, int M, int logM, const double2* __restri
         c = cmul(c, __ldg(post + base + 2));
         d = cmul(d, __ldg(post + base + 3));
       }
-      s[base] = a;
-      s[base + q] = b;
-      s[base + 2 * q] = c;
-      s[base + 3 * q] = d;
+      s[sp(base)] = a;
+      s[sp(base + q)] = b;
+      s[sp(base + 2 * q)] = c;
+      s[sp(base + 3 * q)] = d;
     }
     __syncthreads();
   }
   if (Nb == 2) {
     for (int i = tid; i < (M >> 1); i += nthr) {
-      double2 a = first ? in(2 * i) : s[2 * i], b = first ? in(2 * i + 1) : s[2 * i + 1];
+      double2 a = first ? in(2 * i) : s[sp(2 * i)], b = first ? in(2 * i + 1) : s[sp(2 * i + 1)];
       double2 y0 = cadd(a, b), y1 = csub(a, b);
       if (post) {
         y0 = cmul(y0, __ldg(post + 2 * i));
         y1 = cmul(y1, __ldg(post + 2 * i + 1));
       }
-      s[2 * i] = y0;
-      s[2 * i + 1] = y1;
+      s[sp(2 * i)] = y0;
+      s[sp(2 * i + 1)] = y1;
     }
     __syncthreads();
   }
@@ -196,9 +202,9 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
   if (logM & 1) {
     const bool last = M == 2;
     for (int i = tid; i < (M >> 1); i += nthr) {
-      const double2 a = s[2 * i], b = s[2 * i + 1];
+      const double2 a = s[sp(2 * i)], b = s[sp(2 * i + 1)];
       if (last) { out(2 * i, cadd(a, b)); out(2 * i + 1, csub(a, b)); }
-      else { s[2 * i] = cadd(a, b); s[2 * i + 1] = csub(a, b); }
+      else { s[sp(2 * i)] = cadd(a, b); s[sp(2 * i + 1)] = csub(a, b); }
     }
     __syncthreads();
     D = 2;
@@ -210,15 +216,15 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
       const int j = i & (q - 1);
       const int base = (i - j) * 4 + j;
       const double2* tp = twp + (M - 4 * q) + j;
-      double2 y0 = s[base];
-      double2 y1 = cmulc(s[base + q], __ldg(tp));
-      double2 y2 = cmulc(s[base + 2 * q], __ldg(tp + q));
-      double2 y3 = cmulc(s[base + 3 * q], __ldg(tp + 2 * q));
+      double2 y0 = s[sp(base)];
+      double2 y1 = cmulc(s[sp(base + q)], __ldg(tp));
+      double2 y2 = cmulc(s[sp(base + 2 * q)], __ldg(tp + q));
+      double2 y3 = cmulc(s[sp(base + 3 * q)], __ldg(tp + 2 * q));
       bfly4_inv(y0, y1, y2, y3);
       if (last) {
         out(base, y0); out(base + q, y1); out(base + 2 * q, y2); out(base + 3 * q, y3);
       } else {
-        s[base] = y0; s[base + q] = y1; s[base + 2 * q] = y2; s[base + 3 * q] = y3;
+        s[sp(base)] = y0; s[sp(base + q)] = y1; s[sp(base + 2 * q)] = y2; s[sp(base + 3 * q)] = y3;
       }
     }
     __syncthreads();
@@ -237,10 +243,10 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int ib = base + a * q;
-        x[a][0] = s[ib];
-        x[a][1] = cmulc(s[ib + qq], w1);
-        x[a][2] = cmulc(s[ib + 2 * qq], w2);
-        x[a][3] = cmulc(s[ib + 3 * qq], w3);
+        x[a][0] = s[sp(ib)];
+        x[a][1] = cmulc(s[sp(ib + qq)], w1);
+        x[a][2] = cmulc(s[sp(ib + 2 * qq)], w2);
+        x[a][3] = cmulc(s[sp(ib + 3 * qq)], w3);
         bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
       }
 #pragma unroll
@@ -253,7 +259,7 @@ __device__ void fft_inverse(double2* s, int M, int logM, const double2* __restri
         for (int a = 0; a < 4; ++a) {
           const int idx = base + a * q + b * qq;
           if (last) out(idx, x[a][b]);
-          else s[idx] = x[a][b];
+          else s[sp(idx)] = x[a][b];
         }
       }
     }
@@ -266,10 +272,10 @@ k_filter_spectrum(const double2* __restrict__ bfilt, double2* __restrict__ Bhat,
                   const double2* __restrict__ tw, double2* scratch) {
   extern __shared__ double2 sbuf[];
   double2* s = scratch ? scratch : sbuf;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) s[i] = bfilt[i];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s[sp(i)] = bfilt[i];
   __syncthreads();
   fft_forward(s, M, logM, tw, SmemInput{s}, nullptr);
-  for (int i = threadIdx.x; i < M; i += blockDim.x) Bhat[i] = s[i];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) Bhat[i] = s[sp(i)];
 }
 
 // chirp-z input: alpha_k Yhat[k] chi[k] for k < nfo, zero above (numpy c2r semantics for DC/Nyquist)
@@ -360,7 +366,7 @@ __device__ void fft4_forward(double2* g, double2* s, int C, int logC, const doub
   __syncthreads();
   for (int k1 = 0; k1 < R; ++k1) {
     fft_forward(s, C, logC, tw, RowInput{g + (size_t)k1 * C}, post ? post + (size_t)k1 * C : nullptr);
-    for (int i = threadIdx.x; i < C; i += blockDim.x) g[(size_t)k1 * C + i] = s[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) g[(size_t)k1 * C + i] = s[sp(i)];
     __syncthreads();
   }
 }
@@ -372,7 +378,7 @@ __device__ void fft4_inverse(double2* g, double2* s, int C, int logC, const doub
   const double2* twM = tw + C;
   const double2* twR = tw + 2 * C;
   for (int k1 = 0; k1 < R; ++k1) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s[i] = g[(size_t)k1 * C + i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s[sp(i)] = g[(size_t)k1 * C + i];
     __syncthreads();
     fft_inverse(s, C, logC, tw, RowOutput{g + (size_t)k1 * C});
   }
@@ -476,7 +482,7 @@ __global__ void k_axpy(int n_cmps, const double* const* __restrict__ ptrs,
 template <int R>
 static void filter4_t(pkm_plan* pl, const double2* d_b) {
   const CztTables& c = pl->czt;
-  const size_t smem = sizeof(double2) * c.C;
+  const size_t smem = sizeof(double2) * sp_elems(c.C);
   PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_filter_spectrum4<R><<<1, 512, smem>>>(d_b, pl->d_Bhat, c.C, c.logC, pl->d_twiddle);
 }
@@ -487,7 +493,7 @@ void czt_prepare_filter(pkm_plan* pl) {
   PKM_CUDA(cudaMalloc(&d_b, sizeof(double2) * c.M));
   PKM_CUDA(cudaMemcpy(d_b, c.bfilt.data(), sizeof(double2) * c.M, cudaMemcpyHostToDevice));
   if (c.R == 1) {
-    const size_t smem = sizeof(double2) * c.M;
+    const size_t smem = sizeof(double2) * sp_elems(c.M);
     PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_filter_spectrum<<<1, 256, smem>>>(d_b, pl->d_Bhat, c.M, c.logM, pl->d_twiddle, nullptr);
   } else {
@@ -507,7 +513,7 @@ void czt_prepare_filter(pkm_plan* pl) {
 template <int R>
 static void irfft4_t(pkm_plan* pl, const double2* yhat, int64_t npix, double s, double* out, cudaStream_t st) {
   const CztTables& c = pl->czt;
-  const size_t smem = sizeof(double2) * c.C;
+  const size_t smem = sizeof(double2) * sp_elems(c.C);
   PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * 2);
   pl->misc.reserve(sizeof(double2) * (size_t)c.M * grid);
@@ -522,7 +528,7 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
   const double s = scale / ((double)c.M * (double)c.n);
   KernelTimer tm(pl, PKM_K_IRFFT, st);
   if (c.R == 1) {
-    const size_t smem = sizeof(double2) * c.M;
+    const size_t smem = sizeof(double2) * sp_elems(c.M);
     PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
     const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
