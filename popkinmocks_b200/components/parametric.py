@@ -136,18 +136,24 @@ class ParametricComponent(base.Component):
         onto the SSP metallicity edges and normalised over the grid."""
         grid = self.z_t_interp_grid
         nearest = np.argmin(np.abs(t_dep[:, :, None] - grid["t_dep"]), axis=-1)
-        z_mu = np.moveaxis(grid["z"][nearest], -1, 0)                     # [t, x1, x2]
+        # p(z|t,x) depends on x only through the tabulated depletion time nearest to t_dep[x]:
+        # evaluate the model once per distinct table row and gather (same arithmetic per element
+        # as the reference, which works on the full [z+1, t, x1, x2] arrays - bit-identical, and
+        # 10-100x less work for maps with few distinct depletion times)
+        rows, inverse = np.unique(nearest.ravel(), return_inverse=True)
+        inverse = inverse.reshape(nearest.shape)
+        z_mu = grid["z"][rows].T                                          # [t, row]
         z_sd = (self.ahat * z_mu ** self.bhat) ** 0.5
         lin_z_edges = 10.0 ** self.cube.ssps.par_edges[0]
         # = stats.norm(z_mu, z_sd).logcdf(edges): the same log_ndtr call without the frozen-
-        # distribution overhead (bit-identical, ~2x faster on these [z+1, t, x1, x2] arrays)
+        # distribution overhead
         with np.errstate(divide="ignore", invalid="ignore"):
-            log_cdf = special.log_ndtr((lin_z_edges[:, None, None, None] - z_mu) / z_sd)
-        log_P = _log_diff_exp(log_cdf[1:], log_cdf[:-1])                  # [z, t, x1, x2]
+            log_cdf = special.log_ndtr((lin_z_edges[:, None, None] - z_mu) / z_sd)
+        log_P = _log_diff_exp(log_cdf[1:], log_cdf[:-1])                  # [z, t, row]
         log_dz = np.log(self.cube.construct_volume_element("z"))
         log_norm = special.logsumexp(log_P.T + log_dz, -1).T
-        log_p_z_tx = log_P - log_norm
-        return log_p_z_tx, np.exp(log_p_z_tx)
+        log_p_z_t_row = log_P - log_norm
+        return log_p_z_t_row[:, :, inverse], np.exp(log_p_z_t_row)[:, :, inverse]   # [z, t, x1, x2]
 
     def set_p_z_tx(self):
         self.log_p_z_tx, self.p_z_tx = self.evaluate_chemical_enrichment_model_base(self.t_dep)

@@ -26,10 +26,14 @@ class Stream(parametric.ParametricComponent):
         radius = mu_r_lims[0] + (mu_r_lims[1] - mu_r_lims[0]) * ((theta - th0) / (th1 - th0))
 
         def log_pixel_mass(coord, half_width, centres):
-            law = stats.norm(centres, sig)
-            hi = law.logcdf(coord[:, :, None] + half_width)
-            lo = law.logcdf(coord[:, :, None] - half_width)
-            return parametric._log_diff_exp(hi, lo)                       # [x1, x2, nsmp]
+            # stats.norm(centres, sig).logcdf(.) is log_ndtr((. - centres)/sig); evaluated once per
+            # distinct coordinate value (an unrotated cube has nx1 of them, not nx1*nx2) and
+            # gathered - the same arithmetic per element as the reference's full [x1, x2, nsmp] arrays
+            values, inverse = np.unique(coord.ravel(), return_inverse=True)
+            with np.errstate(divide="ignore"):
+                hi = special.log_ndtr((values[:, None] + half_width - centres) / sig)
+                lo = special.log_ndtr((values[:, None] - half_width - centres) / sig)
+            return parametric._log_diff_exp(hi, lo)[inverse.reshape(coord.shape)]   # [x1, x2, nsmp]
 
         log_p = (log_pixel_mass(self.xxp, cube.dx / 2.0, radius * np.cos(theta))
                  + log_pixel_mass(self.yyp, cube.dy / 2.0, radius * np.sin(theta)))
