@@ -146,6 +146,13 @@ PKM_API int32_t pkm_ybar_gaussian(pkm_plan* plan, const double* P_txz, const dou
 PKM_API int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
                        int64_t n, double* out, int32_t device, void* stream);
 
+/* Component-collapsed log density of a Mixture (Mixture.get_log_p(..., collapse_cmps=True),
+ * popkinmocks/components/mixture.py:50-80): out[i] = log sum_c exp(log_weights[c] + log_ps[c][i]).
+ * log_ps: n_cmps pointers to n float64 each; log_ps and out host or device (same side),
+ * log_weights [n_cmps] host. */
+PKM_API int32_t pkm_logsumexp_cubes(int32_t n_cmps, const double* const* log_ps, const double* log_weights,
+                                    int64_t n, double* out, int32_t device, void* stream);
+
 /* Spaxel-major [npix][n] -> cube layout [n][npix] (device pointers only). */
 PKM_API int32_t pkm_transpose_to_cube(const double* pixel_major, int64_t npix, int64_t n, double* cube,
                               int32_t device, void* stream);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "pkm_ybar_gaussian": (_I32, [_P, _P, _P, C.POINTER(_I64), _P, C.POINTER(_I64), _P, _I32, _I32,
                                  _I32, _I32, _P, _I32, _P]),
     "pkm_axpy_cubes": (_I32, [_I32, C.POINTER(_P), _P, _I64, _P, _I32, _P]),
+    "pkm_logsumexp_cubes": (_I32, [_I32, C.POINTER(_P), _P, _I64, _P, _I32, _P]),
     "pkm_transpose_to_cube": (_I32, [_P, _I64, _I64, _P, _I32, _P]),
     "pkm_irfft_batch": (_I32, [_P, _P, _I64, _F64, _P, _P]),
     "pkm_irfft_naive": (_I32, [_P, _P, _I64, _F64, _P, _P]),

@@ -34,6 +34,24 @@ class Mixture(base.Component):
         self.ybar = engine.axpy_cubes([c.ybar for c in self.component_list], self.weights,
                                       device=device)
 
+    def pixelate(self, device=0):
+        """`Component(cube, self.get_log_p("tvxz", collapse_cmps=True))` built and kept on the
+        device: the children are pixelated there (`ParametricComponent.pixelate`, or the stored
+        array of an already pixelated child) and collapsed by pkm_logsumexp_cubes, so the
+        5-D arrays of a large cube never exist on the host."""
+        import torch
+        terms = []
+        for cmp in self.component_list:
+            if hasattr(cmp, "pixelate"):
+                terms.append(cmp.pixelate(device=device).log_p_tvxz)
+            else:
+                log_p = cmp.log_p_tvxz
+                if not engine._is_cuda_tensor(log_p):
+                    log_p = torch.from_numpy(np.ascontiguousarray(log_p, dtype=np.float64)).to(f"cuda:{device}")
+                terms.append(log_p)
+        log_p = engine.logsumexp_cubes(terms, self.weights, device=device)
+        return base.Component(cube=self.cube, log_p_tvxz=log_p)
+
     # ------------------------------------------------------------------ distributions
     def get_p(self, which_dist, collapse_cmps=True, density=True, light_weighted=False):
         return np.exp(self.get_log_p(which_dist, collapse_cmps=collapse_cmps, density=density,

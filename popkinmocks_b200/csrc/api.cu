@@ -647,8 +647,9 @@ extern "C" int32_t pkm_ybar_gaussian(pkm_plan* pl, const double* P_txz, const do
 // ----------------------------------------------------------------------------
 // small operators
 // ----------------------------------------------------------------------------
-extern "C" int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
-                                  int64_t n, double* out, int32_t device, void* stream) {
+// mode 0: out = sum_c w[c] * cube_c;  mode 1: out = log sum_c exp(w[c] + cube_c)
+static int32_t combine_cubes(int mode, int32_t n_cmps, const double* const* ybars, const double* weights,
+                             int64_t n, double* out, int32_t device, void* stream) {
   return guarded([&] {
     PKM_REQUIRE(n_cmps >= 1 && ybars && weights && out && n >= 0, "bad argument");
     if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
@@ -674,12 +675,23 @@ extern "C" int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, co
     double* d_w = reinterpret_cast<double*>(d_ptrs + n_cmps);
     PKM_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), sizeof(double*) * n_cmps, cudaMemcpyHostToDevice, st));
     PKM_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * n_cmps, cudaMemcpyHostToDevice, st));
-    launch_axpy(n_cmps, d_ptrs, d_w, n, d_out, st);
+    if (mode == 0) launch_axpy(n_cmps, d_ptrs, d_w, n, d_out, st);
+    else launch_logsumexp_cubes(n_cmps, d_ptrs, d_w, n, d_out, st);
     if (host) PKM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     PKM_CUDA(cudaStreamSynchronize(st));  // the pointer table is a local
     tab.release();
     data.release();
   });
+}
+
+extern "C" int32_t pkm_axpy_cubes(int32_t n_cmps, const double* const* ybars, const double* weights,
+                                  int64_t n, double* out, int32_t device, void* stream) {
+  return combine_cubes(0, n_cmps, ybars, weights, n, out, device, stream);
+}
+
+extern "C" int32_t pkm_logsumexp_cubes(int32_t n_cmps, const double* const* log_ps, const double* log_weights,
+                                       int64_t n, double* out, int32_t device, void* stream) {
+  return combine_cubes(1, n_cmps, log_ps, log_weights, n, out, device, stream);
 }
 
 extern "C" int32_t pkm_transpose_to_cube(const double* pixel_major, int64_t npix, int64_t n,

@@ -477,6 +477,21 @@ __global__ void k_axpy(int n_cmps, const double* const* __restrict__ ptrs,
   }
 }
 
+// out[i] = log sum_c exp(log_w[c] + ptrs[c][i]): the component-collapsed log density of a Mixture
+// (scipy.special.logsumexp over the component axis, mixture.py:50-80), max-shifted
+__global__ void k_logsumexp_cubes(int n_cmps, const double* const* __restrict__ ptrs,
+                                  const double* __restrict__ log_w, long long n, double* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double m = -INFINITY;
+    for (int c = 0; c < n_cmps; ++c) m = fmax(m, log_w[c] + ptrs[c][i]);
+    double acc = 0.0;
+    if (m > -INFINITY)
+      for (int c = 0; c < n_cmps; ++c) acc += exp(log_w[c] + ptrs[c][i] - m);
+    out[i] = m > -INFINITY ? m + log(acc) : -INFINITY;
+  }
+}
+
 }  // namespace
 
 template <int R>
@@ -575,5 +590,13 @@ void launch_axpy(int n_cmps, const double* const* d_ptrs_dev, const double* d_w,
   if (n <= 0) return;
   int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   k_axpy<<<grid, 256, 0, st>>>(n_cmps, d_ptrs_dev, d_w, n, out);
+  PKM_CUDA(cudaGetLastError());
+}
+
+void launch_logsumexp_cubes(int n_cmps, const double* const* d_ptrs_dev, const double* d_log_w, int64_t n,
+                            double* out, cudaStream_t st) {
+  if (n <= 0) return;
+  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  k_logsumexp_cubes<<<grid, 256, 0, st>>>(n_cmps, d_ptrs_dev, d_log_w, n, out);
   PKM_CUDA(cudaGetLastError());
 }

@@ -179,6 +179,8 @@ void launch_transpose(const double* src, int64_t npix, int64_t n, double* dst, i
                       int64_t col0, cudaStream_t st);
 void launch_axpy(int n_cmps, const double* const* d_ptrs_dev, const double* d_w, int64_t n,
                  double* out, cudaStream_t st);
+void launch_logsumexp_cubes(int n_cmps, const double* const* d_ptrs_dev, const double* d_log_w, int64_t n,
+                            double* out, cudaStream_t st);
 
 // statistics kernels (stats.cu)
 void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const double* d_log_dv,

@@ -232,6 +232,25 @@ def axpy_cubes(ybars, weights, device=0):
     return out
 
 
+def logsumexp_cubes(log_ps, weights, device=0):
+    """log sum_i w_i exp(log_p_i): the collapsed log density of a Mixture (mixture.py:50-80).
+    `log_ps`: equally shaped NumPy arrays or CUDA tensors; the result lives on the same side."""
+    _lib.require_gpu()
+    if _is_cuda_tensor(log_ps[0]):
+        import torch
+        log_ps = [a.contiguous() for a in log_ps]
+        out = torch.empty_like(log_ps[0])
+    else:
+        log_ps = [_lib.as_f64(a) for a in log_ps]
+        out = np.empty_like(log_ps[0])
+    n = int(np.prod(log_ps[0].shape))
+    ptrs = (C.c_void_p * len(log_ps))(*[_lib.ptr(a) for a in log_ps])
+    log_w = _lib.as_f64(np.log(np.asarray(weights, dtype=np.float64)))
+    _lib.check(_lib.load().pkm_logsumexp_cubes(len(log_ps), ptrs, _lib.ptr(log_w), n, _lib.ptr(out),
+                                               int(device), None))
+    return out
+
+
 def moments(P, values, device=0):
     """Mean and central moments 2..4 along axis 0 of P[nvar, ...] (base.py:208-260).
 

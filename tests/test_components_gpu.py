@@ -360,3 +360,22 @@ def test_pixelation_at_scale_marginalises_back(gpu_ok):
     # path B on the pixelated twin vs the analytic path A (test_all.py:103-115 tolerance)
     err = np.abs(twin.ybar - disk.ybar) / np.abs(disk.ybar).max()
     assert np.median(err) < 5e-4
+
+
+def test_mixture_pixelation_matches_reference(galaxy, base_component):
+    """`galaxy.pixelate()` == the reference's Component(cube, galaxy.get_log_p('tvxz')) (golden g1):
+    children pixelated on the device, collapsed by pkm_logsumexp_cubes."""
+    g = load_golden(G1)
+    twin = galaxy.pixelate()
+    assert twin.log_p_tvxz.is_cuda
+    got, ref = twin.log_p_tvxz.cpu().numpy(), g["b_log_p_tvxz"]
+    assert got.shape == ref.shape and not np.isnan(got).any()
+    bulk = ref > ref.max(axis=1, keepdims=True) + np.log(1e-4)
+    assert bulk.sum() > 0.1 * ref.size
+    assert np.max(np.abs(got[bulk] - ref[bulk])) < 1e-10
+    assert rel_err(np.exp(got), np.exp(ref)) < 1e-13
+    twin.evaluate_ybar()
+    assert rel_err(twin.ybar, g["b_ybar"]) < TOL
+    assert rel_err(twin.ybar, base_component.ybar) < 1e-12
+    for dist in ("tz", "v_x"):
+        assert rel_err(twin.get_p(dist), np.exp(g[f"b_logp|{dist}|0|1"])) < TOL
