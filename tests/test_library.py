@@ -79,6 +79,9 @@ def test_no_cpu_fallback_without_a_gpu():
     from test_host_models import BUILDERS
     with pytest.raises(_lib.PkmError, match="no CUDA device"):
         BUILDERS["d1_"](cube).pixelate()
+    from popkinmocks_b200 import engine
+    with pytest.raises(_lib.PkmError, match="no CUDA device"):
+        engine.logsumexp_cubes([np.zeros(4), np.zeros(4)], [0.5, 0.5])
     lw, mu, sig = np.zeros((2, 3, 4)), np.zeros((2, 3)), np.ones((2, 3))
     v_edg, res = np.linspace(-1.0, 1.0, 6), np.empty((2, 5, 3, 4))
     rc = _lib.load().pkm_pixelate_gaussian(_lib.ptr(lw), _lib.ptr(mu), _lib.ptr(sig), _lib.ptr(v_edg),
