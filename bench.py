@@ -9,12 +9,16 @@ full MILES_BASTI grid (nt=53, nz=12), nv=101, lambda 4700-6500 A -> n_fft=4907; 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
     python bench.py --impl reference [...]                        # the reference's CPU algorithm
 
-N > 1 (torchrun, one rank per GPU): strong scaling of the named configuration - the x1 rows of
-ONE 201x201-pixel cube are sharded over the ranks (pixels are independent),
-every rank evaluates its block and its last kernel (the transpose to the reference layout) stores
-the rows straight into rank 0's cube through NVLink peer memory (CUDA IPC), followed by one small
-NCCL all-reduce as the barrier; all inside the timed region (`--gather nccl`: NCCL send/recv).
-`--scaling weak` evaluates a (201*N)x201 mosaic instead (201 rows per rank).
+N > 1 (torchrun, one rank per GPU): strong scaling of the named configuration - the flattened
+pixel axis of ONE 201x201-pixel cube is sharded over the ranks in contiguous ranges (pixels are
+independent).  Every rank's density shard is a slice of the same seeded
+cube (pkm_synth_log_density is indexed by the global element index).  Each rank evaluates its
+range tile by tile; a finished tile is transposed locally and moved into rank 0's cube by a
+strided copy-engine transfer over NVLink peer memory (CUDA IPC), followed by one small NCCL
+all-reduce as the barrier; all inside the timed region (`--gather nccl`: NCCL send/recv).
+`--scaling weak` evaluates a (201*N)x201 mosaic instead (201x201 pixels per rank).
+After the timed region rank 0 checks the assembled cube: 16 spot pixels against the oracle and
+a bit checksum that must be the same for every N (`verify`); a mismatch exits non-zero.
 
 The JSON line printed by rank 0 follows the driver contract: `value` = device-resident
 throughput, `e2e` = the same call through the C ABI with pinned HOST buffers (H2D of the
@@ -37,6 +41,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "evaluate_ybar cube voxels/s"
 UNIT = "voxel/s"
+SEED = 20241019
+VERIFY_TOL = 1e-10
 B_VOX_NOTE = "SURVEY.md 8d canonical bytes/voxel with P-hat staged through HBM once"
 
 
@@ -57,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=0.0, help="device workspace cap of the plan (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle spot check of the evaluated cube")
     ap.add_argument("--no-other", action="store_true", help="skip the brief timings of the other hot-path rows")
     ap.add_argument("--cpu-procs", type=int, default=0, help="host processes of the CPU legs (0 = all cores, max 64)")
     ap.add_argument("--cpu-px", type=int, default=2, help="pixels per CPU task")
@@ -316,13 +323,14 @@ def run_b200(args):
     nx1_total = total_pix if world > 1 else nx
     voxels_per_step = total_pix * n_fft
 
-    # ---- synthetic density (log p, as Component(cube, log_p_tvxz) holds it), generated on device
-    gen = torch.Generator(device=dev).manual_seed(20241019 + rank)
-    logp = torch.empty((nt, nv, rows, nxl, nz), dtype=torch.float64, device=dev)
-    for t in range(nt):                 # slab-wise to keep the temporary small
-        logp[t] = torch.rand((nv, rows, nxl, nz), dtype=torch.float64, device=dev, generator=gen)
+    # ---- synthetic density (log p, as Component(cube, log_p_tvxz) holds it), generated on device by a
+    # counter-based generator indexed by the GLOBAL element index (pkm_synth_log_density): every
+    # rank's shard is a slice of ONE seeded cube, so N = 1, 2, 4, 8 evaluate identical inputs
+    gen = torch.Generator(device=dev).manual_seed(20241019 + rank)   # only for the other_paths operands
     dV = float(np.mean(cube.ssps.delta_t) * np.mean(cube.ssps.delta_z) * cube.dx * cube.dy * cube.ssps.dv)
-    logp.mul_(1.0 / (0.5 * nt * nv * total_pix * nz * dV)).clamp_(min=1e-300).log_()
+    synth = dict(nt=int(nt), nv=nv, total_pix=int(total_pix), nz=int(nz), seed=SEED,
+                 scale=1.0 / (0.5 * nt * nv * total_pix * nz * dV))
+    logp = engine.synth_log_density(pix0=r0, npix=npix, device=local, **synth).view(nt, nv, rows, nxl, nz)
 
     gather_note = None
     if world == 1:
@@ -411,6 +419,19 @@ def run_b200(args):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = voxels_per_step / (ms_step * 1e-3)
+
+    # ---- verification of the assembled cube (after the timed region, rank 0): spot pixels against
+    # the oracle's literal restatement of base.py:836-859 on the same seeded inputs, plus an
+    # order-independent bit checksum that must be identical for every N
+    verify = None
+    if rank == 0 and not args.no_verify:
+        verify = verify_cube(out.reshape(n_fft, total_pix), cube, synth, total_pix)
+    if world > 1:
+        bad = torch.tensor([1.0 if (verify and not verify["ok"]) else 0.0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        verify_failed = bool(bad.item() > 0)
+    else:
+        verify_failed = bool(verify and not verify["ok"])
 
     # ---- the other rows of the hot-path table, timed briefly on the same cube (N=1 only; reported
     # under "other_paths", not part of `value`)
@@ -567,6 +588,7 @@ def run_b200(args):
                                             "frac": b_min * per_gpu / 1e9 / hbm_peak},
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
             "gather": (args.gather if world > 1 else None), "gather_note": gather_note,
+            "verify": verify,
             "kernels": kern, "per_rank": per_rank, "other_paths": other, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -578,6 +600,48 @@ def run_b200(args):
             pc.close()
         dist.barrier()
         dist.destroy_process_group()
+    if verify_failed:
+        raise SystemExit(f"bench.py: the evaluated cube differs from the oracle by more than {VERIFY_TOL:g}")
+
+
+def spot_pixels(total_pix):
+    """First and last pixel of every block of an 8-way partition of the flattened pixel axis (the
+    same list for every N, so the spot checks of N = 1, 2, 4, 8 look at the same pixels)."""
+    from popkinmocks_b200 import sharding
+    b = sharding.row_partition(total_pix, 8)
+    return sorted({p for r in range(8) if b[r + 1] > b[r] for p in (b[r], b[r + 1] - 1)})
+
+
+def cube_checksum(cube2d):
+    """(bit checksum, float sum) of a float64 CUDA tensor.  The checksum is the sum of the IEEE-754
+    bit patterns modulo 2^64 - exact, independent of summation order and of how the cube was
+    sharded; it changes if any voxel changes in its last bit."""
+    import torch
+    bits = cube2d.contiguous().view(torch.int64).reshape(-1)
+    lo = int((bits & 0xFFFFFFFF).sum().item())
+    hi = int(((bits >> 32) & 0xFFFFFFFF).sum().item())
+    return f"{(lo + (hi << 32)) & ((1 << 64) - 1):016x}", float(cube2d.sum().item())
+
+
+def verify_cube(cube2d, cube, synth, total_pix):
+    """cube2d: [n_fft, total_pix] on the device.  Returns the `verify` object of the JSON line."""
+    from oracle import restatement as R
+    from popkinmocks_b200 import engine
+    s = cube.ssps
+    px = spot_pixels(total_pix)
+    logp = engine.synth_log_density_host(synth["nt"], synth["nv"], total_pix, px, synth["nz"],
+                                         synth["seed"], synth["scale"])
+    p = np.exp(logp)[:, :, None, :, :]                                   # [nt, nv, 1, npx, nz]
+    y_ref = R.ybar_density_literal(p, cube.v_edg, s.FXw, s.par_dims, s.n_fft, s.dv, s.delta_t, s.delta_z,
+                                   cube.dx, cube.dy)[:, 0, :]
+    y_gpu = cube2d[:, px].cpu().numpy()
+    err = float(np.max(np.abs(y_gpu - y_ref)) / np.max(np.abs(y_ref)))
+    chk, total = cube_checksum(cube2d)
+    return {"max_rel_err": err, "tol": VERIFY_TOL, "ok": bool(err < VERIFY_TOL), "pixels": len(px),
+            "pixel_index": px, "checksum": chk, "sum": total,
+            "oracle": "oracle/restatement.py ybar_density_literal (base.py:836-859) on the same seeded inputs",
+            "note": "checksum = sum of the float64 bit patterns of the whole cube mod 2^64 (identical "
+                    "for N = 1, 2, 4, 8 iff the assembled cubes are bit-identical)"}
 
 
 def ncu_traffic(kernel, npix):

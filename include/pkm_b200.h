@@ -218,6 +218,16 @@ PKM_API int32_t pkm_pixelate_gaussian(const double* log_w_txz, const double* mu_
                                       int32_t nz, int32_t density, double* out, int32_t device,
                                       void* stream);
 
+/* Synthetic white-noise log density of the benchmark workload (SURVEY.md section 8d, config C4:
+ * uniform(0,1) values; the reference has no generator of its own - its tests draw from NumPy).
+ * out (device) receives [nt][nv][npix][nz] float64 for the pixel range [pix0, pix0+npix) of a
+ * cube with total_pix pixels: out = log(u * scale), u = (splitmix64(seed + g) >> 11 + 0.5) * 2^-53,
+ * g = the element's flat index in the WHOLE [nt][nv][total_pix][nz] array, so the values of a
+ * pixel do not depend on how the cube is sharded. */
+PKM_API int32_t pkm_synth_log_density(double* out, int32_t nt, int32_t nv, int64_t total_pix, int64_t pix0,
+                                      int64_t npix, int32_t nz, uint64_t seed, double scale,
+                                      int32_t device, void* stream);
+
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA; best of `repeats`
  * timed launches of a register-resident DFMA chain on every SM).  The roofline denominator of
  * the FP64-pipe-bound kernels; MEASURED_PEAKS.json carries no FP64 figure. */

@@ -889,6 +889,23 @@ extern "C" int32_t pkm_fp64_fma_peak(int32_t device, int32_t repeats, double* tf
   });
 }
 
+extern "C" int32_t pkm_synth_log_density(double* out, int32_t nt, int32_t nv, int64_t total_pix, int64_t pix0,
+                                         int64_t npix, int32_t nz, uint64_t seed, double scale,
+                                         int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(out && nt >= 1 && nv >= 1 && nz >= 1 && npix >= 0 && pix0 >= 0 && pix0 + npix <= total_pix,
+                "bad argument");
+    PKM_REQUIRE(scale > 0.0, "scale must be positive");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    PKM_REQUIRE(pkm_is_device_pointer(out), "out must be device memory");
+    use_device(device);
+    cudaDeviceProp prop;
+    PKM_CUDA(cudaGetDeviceProperties(&prop, device));
+    launch_synth_logp(out, nt, nv, total_pix, pix0, npix, nz, seed, scale, prop.multiProcessorCount,
+                      reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
 extern "C" int32_t pkm_histogram5d(const double* const* samples, const double* weights, int64_t n,
                                    const double* const* edges, const int32_t* nbin, double* out,
                                    int32_t device, void* stream) {

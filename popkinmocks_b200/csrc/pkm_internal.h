@@ -200,6 +200,8 @@ void launch_hist5d(const double* const samples[5], const double* weights, int64_
 void launch_pixelate(const double* log_w, const double* mu, const double* sig, const double* d_v_edg,
                      const double* d_log_dv, int nt, int nv, int64_t npix, int nz, double* out,
                      cudaStream_t st);
+void launch_synth_logp(double* out, int nt, int nv, int64_t total_pix, int64_t pix0, int64_t npix, int nz,
+                       uint64_t seed, double scale, int num_sms, cudaStream_t st);
 bool pkm_is_device_pointer(const void* p);
 
 // RAII CUDA-event bracket of one launch on its own stream (no-op unless plan->profiling)

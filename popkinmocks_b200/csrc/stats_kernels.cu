@@ -605,6 +605,44 @@ void launch_hist5d(const double* const samples[5], const double* weights, int64_
 }
 
 // ----------------------------------------------------------------------------
+// Synthetic white-noise log density for the benchmark workload: a
+// counter-based generator indexed by the GLOBAL element index of the [nt][nv][total_pix][nz]
+// array, so any pixel range of the cube - a rank's shard, a spot pixel checked on the host -
+// holds the same values whatever the sharding.  u = splitmix64(seed + index) mapped to (0,1);
+// out = log(u * scale).  The host replica is popkinmocks_b200.engine.synth_log_density_host.
+// ----------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_synth_logp(double* __restrict__ out, int nt, int nv, long long total_pix, long long pix0,
+                             long long npix, int nz, unsigned long long seed, double scale) {
+  const long long row = npix * nz;
+  const long long n = (long long)nt * nv * row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long tv = i / row, r = i - tv * row;          // r = x_local * nz + z
+    const unsigned long long gidx = (unsigned long long)(tv * total_pix * nz + pix0 * nz + r);
+    const unsigned long long h = splitmix64(seed + gidx);
+    const double u = ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    out[i] = log(u * scale);
+  }
+}
+}  // namespace
+
+void launch_synth_logp(double* out, int nt, int nv, int64_t total_pix, int64_t pix0, int64_t npix, int nz,
+                       uint64_t seed, double scale, int num_sms, cudaStream_t st) {
+  const long long n = (long long)nt * nv * npix * nz;
+  if (n <= 0) return;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms * 32);
+  k_synth_logp<<<grid, 256, 0, st>>>(out, nt, nv, total_pix, pix0, npix, nz, seed, scale);
+  PKM_CUDA(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------
 // FP64 FMA throughput probe (roofline denominator of the FP64-pipe-bound kernels; the
 // driver-written MEASURED_PEAKS.json has no FP64 figure).  8 independent DFMA chains per
 // thread, 256 threads x 8 CTAs per SM.

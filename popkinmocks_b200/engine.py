@@ -348,3 +348,35 @@ def pixelate_gaussian(log_w_txz, mu_v, sig_v, v_edg, density=True, device=0, on_
         _lib.ptr(log_w), _lib.ptr(mu), _lib.ptr(sig), _lib.ptr(v_edg), nt, nv, nx1 * nx2, nz,
         int(bool(density)), _lib.ptr(out), int(device), None))
     return out
+
+
+_SM64 = (1 << 64) - 1
+
+
+def synth_log_density(nt, nv, total_pix, pix0, npix, nz, seed, scale, device=0, out=None):
+    """Pixels [pix0, pix0+npix) of the synthetic white-noise log density of the benchmark cube,
+    generated on the device (pkm_synth_log_density).  Returns a CUDA tensor [nt, nv, npix, nz]."""
+    _lib.require_gpu()
+    import torch
+    if out is None:
+        out = torch.empty((nt, nv, npix, nz), dtype=torch.float64, device=f"cuda:{device}")
+    _lib.check(_lib.load().pkm_synth_log_density(_lib.ptr(out), nt, nv, int(total_pix), int(pix0), int(npix),
+                                                 nz, int(seed) & _SM64, float(scale), int(device), None))
+    return out
+
+
+def synth_log_density_host(nt, nv, total_pix, pixels, nz, seed, scale):
+    """NumPy replica of pkm_synth_log_density for a list of global pixel indices:
+    [nt, nv, len(pixels), nz].  Same integer hash; `log` may differ from CUDA's in the last bit."""
+    pixels = np.asarray(pixels, dtype=np.uint64)
+    t = np.arange(nt, dtype=np.uint64)[:, None, None, None]
+    v = np.arange(nv, dtype=np.uint64)[None, :, None, None]
+    z = np.arange(nz, dtype=np.uint64)[None, None, None, :]
+    g = ((t * np.uint64(nv) + v) * np.uint64(total_pix) + pixels[None, None, :, None]) * np.uint64(nz) + z
+    with np.errstate(over="ignore"):
+        x = g + np.uint64(int(seed) & _SM64) + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    u = ((x >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+    return np.log(u * scale)

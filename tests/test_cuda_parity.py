@@ -307,3 +307,20 @@ def test_full_size_201_cube_properties(gpu_ok):
                                                           _lib.ptr(big), nx * nx, bounds[r], None))
     torch.cuda.synchronize()
     assert torch.equal(big.reshape(ssps.n_fft, nx, nx), y)
+
+
+def test_synthetic_density_is_shard_independent(gpu_ok):
+    """pkm_synth_log_density: the values of a pixel depend only on its GLOBAL index, and the NumPy
+    replica used by bench.py's verification reproduces them (integer hash exact, log to 1 ulp)."""
+    import torch
+    from popkinmocks_b200 import engine
+    kw = dict(nt=5, nv=7, total_pix=1000, nz=3, seed=20241019, scale=2.5e-4)
+    whole = engine.synth_log_density(pix0=0, npix=1000, **kw)
+    part = engine.synth_log_density(pix0=613, npix=200, **kw)
+    assert torch.equal(whole[:, :, 613:813], part)
+    px = [0, 1, 613, 812, 999]
+    host = engine.synth_log_density_host(kw["nt"], kw["nv"], 1000, px, kw["nz"], kw["seed"], kw["scale"])
+    dev = whole[:, :, px].cpu().numpy()
+    assert np.max(np.abs(host - dev)) < 1e-14
+    u = np.exp(dev) / kw["scale"]
+    assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.05
