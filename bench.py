@@ -547,9 +547,9 @@ def run_b200(args):
         # ---- roofline of the dominant kernel (live CUDA-event times of this run)
         nfo, ntz, nfi = n_fft // 2 + 1, nt * nz, nv // 2 + 1
         # executed FP64 work per pixel: contraction = per (k, t, z) 6 FMA for the 3-weight spline
-        # form + 4 FMA complex MAC (20 flops) + 6 DADD per (t,z) shared by 10 frequencies;
+        # form + 4 FMA complex MAC (20 flops) + 6 DADD per (t,z) shared by the 25 frequencies of a warp;
         # coefficient GEMM = nfi x nv real MACs per (t, z) column
-        flops_px = {"contract": 20.6 * nfo * ntz, "coeff": 2.0 * nfi * nv * ntz}
+        flops_px = {"contract": (20.0 + 6.0 / 25.0) * nfo * ntz, "coeff": 2.0 * nfi * nv * ntz}
         tot_k = sum(m for m, _ in ktimes.values()) or 1.0
         kern = {k: {"ms_per_step": m / args.steps, "launches_per_step": c / args.steps, "share": m / tot_k}
                 for k, (m, c) in ktimes.items() if c}

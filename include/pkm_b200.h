@@ -130,6 +130,13 @@ PKM_API int32_t pkm_ipc_export(const void* dev_ptr, uint8_t* handle64);
 PKM_API int32_t pkm_ipc_open(const uint8_t* handle64, int32_t device, void** ptr_out);
 PKM_API int32_t pkm_ipc_close(void* ptr);
 
+/* Page-lock a caller-owned host buffer in place (cudaHostRegister) so that the pipelined staging of
+ * pkm_ybar_density / pkm_reduce_logp reads it at full PCIe rate; a buffer that is already pinned
+ * is left alone.  The Python host side registers a component's log_p_tvxz on first use and
+ * unregisters it when the array is garbage collected. */
+PKM_API int32_t pkm_host_register(void* ptr, int64_t bytes);
+PKM_API int32_t pkm_host_unregister(void* ptr);
+
 /* Gaussian-LOSVD path.  P_txz [nt][nx1][nx2][nz] (volume-weighted probabilities),
  * mu_v / sig_v addressed as base[t*s[0] + x1*s[1] + x2*s[2]] with ELEMENT strides
  * (0 strides allow numpy broadcast views, stream.py:126); omega [n_fft/2+1] is the
@@ -175,6 +182,35 @@ PKM_API int32_t pkm_irfft_naive(pkm_plan* plan, const double* Yhat, int64_t npix
 PKM_API int32_t pkm_reduce_logp(pkm_plan* plan, const double* log_p_tvxz, int64_t npix,
                         const double* log_dv, const double* light_weights, uint32_t keep_mask,
                         int32_t density, double* out, void* stream);
+
+/* Several log-marginals of the same array in one call.  keep_masks / density [n_out] and the output
+ * pointers outs [n_out] are host arrays; every output is laid out like pkm_reduce_logp's.  Nested
+ * requests share work: a marginal whose axes are a subset of another requested one is reduced from
+ * that (small) result instead of the 5-D array, so e.g. {vx, x, v} or {txz, tz, t, z, x} read the
+ * 5-D array ONCE.  (The reductions are bound by one exponential per source element, not by HBM,
+ * so requests that are not nested each make their own pass.)  All outputs share the weighting
+ * (light_weights NULL = mass weighted).  n_out <= 16. */
+PKM_API int32_t pkm_reduce_logp_multi(pkm_plan* plan, const double* log_p_tvxz, int64_t npix,
+                                      const double* log_dv, const double* light_weights, int32_t n_out,
+                                      const uint32_t* keep_masks, const int32_t* density,
+                                      double* const* outs, void* stream);
+
+/* A log-marginal reduced from an already computed one.  log_P_src (device) holds volume-weighted
+ * log PROBABILITIES (density = 0 output of pkm_reduce_logp*) over the axes of src_mask; keep_mask
+ * must be a subset.  light_weights != NULL applies log L(t,z) and renormalises (the source must be
+ * mass weighted and keep t and z): this is how light-weighted marginals without v follow from the
+ * mass-weighted p(t,x,z) without touching the 5-D array again.  Device buffers only. */
+PKM_API int32_t pkm_reduce_logp_from(pkm_plan* plan, const double* log_P_src, uint32_t src_mask, int64_t npix,
+                                     const double* log_dv, const double* light_weights, uint32_t keep_mask,
+                                     int32_t density, double* out, void* stream);
+
+/* Moments of a conditional 1-D distribution straight from device-resident log marginals
+ * (base.py:130-177 + 208-260 in one kernel): P_i = exp(log_joint[a][i][b] - log_given[a][b]) with the
+ * variable on the middle axis (nouter x nvar x ninner, C order; log_given [nouter][ninner] or NULL),
+ * out[4][nouter*ninner] = mean and central moments 2..4.  Device buffers only. */
+PKM_API int32_t pkm_moments_logp(const double* log_joint, const double* log_given, const double* values,
+                                 int64_t nouter, int64_t nvar, int64_t ninner, double* out, int32_t device,
+                                 void* stream);
 
 /* Moments of a conditional 1-D distribution held as probabilities P[nvar][ncond]
  * (axis 0 = variable, base.py:208-260): out[0][c]=mean, out[1..3][c]= central moments 2,3,4.

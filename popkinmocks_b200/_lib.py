@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpkm_b200.so")
+# PKM_B200_LIB: development override (kernel-variant builds); the product is csrc/libpkm_b200.so
+LIB_PATH = os.environ.get("PKM_B200_LIB") or os.path.join(_HERE, "csrc", "libpkm_b200.so")
 
 PKM_OK = 0
 PKM_ERR_INVALID = -1
@@ -59,6 +60,8 @@ SIGNATURES = {
     "pkm_ipc_export": (_I32, [_P, _P]),
     "pkm_ipc_open": (_I32, [_P, _I32, C.POINTER(_P)]),
     "pkm_ipc_close": (_I32, [_P]),
+    "pkm_host_register": (_I32, [_P, _I64]),
+    "pkm_host_unregister": (_I32, [_P]),
     "pkm_ybar_gaussian": (_I32, [_P, _P, _P, C.POINTER(_I64), _P, C.POINTER(_I64), _P, _I32, _I32,
                                  _I32, _I32, _P, _I32, _P]),
     "pkm_axpy_cubes": (_I32, [_I32, C.POINTER(_P), _P, _I64, _P, _I32, _P]),
@@ -67,6 +70,9 @@ SIGNATURES = {
     "pkm_irfft_batch": (_I32, [_P, _P, _I64, _F64, _P, _P]),
     "pkm_irfft_naive": (_I32, [_P, _P, _I64, _F64, _P, _P]),
     "pkm_reduce_logp": (_I32, [_P, _P, _I64, _P, _P, _U32, _I32, _P, _P]),
+    "pkm_reduce_logp_multi": (_I32, [_P, _P, _I64, _P, _P, _I32, _P, _P, C.POINTER(_P), _P]),
+    "pkm_reduce_logp_from": (_I32, [_P, _P, _U32, _I64, _P, _P, _U32, _I32, _P, _P]),
+    "pkm_moments_logp": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P]),
     "pkm_moments": (_I32, [_P, _P, _I64, _I64, _P, _I32, _P]),
     "pkm_noise": (_I32, [_P, _I64, _F64, _I32, _U64, _U64, _F64, _P, _P, _I32, _P]),
     "pkm_max": (_I32, [_P, _I64, _P, _I32, _P]),

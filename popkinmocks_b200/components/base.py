@@ -113,11 +113,51 @@ class Component(object):
             out = out - np.log(self.cube.construct_volume_element(which_dist))
         return out
 
-    # device-resident copy of log_p_tvxz, shared by evaluate_ybar / get_p / moments so that a
-    # sequence of calls uploads the 5-D array once (the reference re-derives it per call)
+    # ------------------------------------------------------------------ device state
+    # `log_p_tvxz` is a property so that rebinding it drops everything derived from the old array:
+    # the device-resident copy (shared by evaluate_ybar / get_p / moments so that a sequence of
+    # calls uploads the 5-D array once - the reference re-derives it per call), the cached log
+    # marginals and the cached moments.  An IN-PLACE edit of the array cannot be detected: call
+    # `invalidate_cache()` after one.
     _DEVICE_CACHE_LIMIT = 64 << 30
+    _MARGINAL_CACHE_ITEM = 1 << 30       # marginals above this size are not kept on the device
+    _MARGINAL_CACHE_TOTAL = 4 << 30
 
-    def _device_log_p(self, device=0):
+    @property
+    def log_p_tvxz(self):
+        d = self.__dict__
+        if "_log_p_tvxz" in d:
+            return d["_log_p_tvxz"]
+        if "log_p_tvxz" in d:                # instance state written before this was a property
+            return d["log_p_tvxz"]
+        raise AttributeError(f"{type(self).__name__} has no pixelated density `log_p_tvxz`")
+
+    @log_p_tvxz.setter
+    def log_p_tvxz(self, value):
+        self.invalidate_cache()
+        self.__dict__["_log_p_tvxz"] = value
+
+    def invalidate_cache(self):
+        """Forget the device copy of `log_p_tvxz` and every cached marginal / moment (call this
+        after modifying the array in place)."""
+        for key in ("_pkm_dev", "_pkm_marg", "_pkm_mom"):
+            self.__dict__.pop(key, None)
+
+    release_device = invalidate_cache
+
+    def _device_index(self, device=None):
+        """The GPU this component computes on: where `log_p_tvxz` lives if it is a CUDA tensor,
+        else `device`, else the device of the cached copy, else 0."""
+        src = self.log_p_tvxz
+        if engine._is_cuda_tensor(src):
+            return int(src.device.index or 0)
+        if device is not None:
+            return int(device)
+        cached = self.__dict__.get("_pkm_dev")
+        return int(cached[1]) if cached is not None else 0
+
+    def _device_log_p(self, device=None):
+        device = self._device_index(device)
         cached = self.__dict__.get("_pkm_dev")
         src = self.log_p_tvxz
         if cached is not None and cached[0] is src and cached[1] == device:
@@ -127,24 +167,70 @@ class Component(object):
         engine._lib.require_gpu()
         if src.nbytes > self._DEVICE_CACHE_LIMIT:
             return src                       # too large to keep resident: stream it per call
-        import torch
-        dev = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64)).to(f"cuda:{device}")
+        dev = engine.to_device(src, device)  # pinned, chunked upload (no pageable full-array copy)
         self.__dict__["_pkm_dev"] = (src, device, dev)
         return dev
 
     def __getstate__(self):
         state = dict(self.__dict__)
-        state.pop("_pkm_dev", None)          # never pickle device handles (dill_dump must keep working)
+        for key in ("_pkm_dev", "_pkm_marg", "_pkm_mom", "_pkm_ybar_pin"):
+            state.pop(key, None)             # never pickle device handles (dill_dump must keep working)
+        if "ybar" in state and state["ybar"] is not None:
+            state["ybar"] = np.array(state["ybar"])     # a plain copy of the page-locked view
         return state
+
+    # Device-resident log PROBABILITY marginals (density=False), keyed by (axes, light_weighted).
+    # A marginal whose axes are a subset of a cached one is reduced from that small array
+    # (pkm_reduce_logp_from) instead of the 5-D array: `get_skewness("v_x")` reads the 5-D array
+    # once (for p(v,x)); p(x), the conditional and all four moments follow from the 32 MB result.
+    def _log_marginal_dev(self, keep, light_weighted=False, device=None):
+        device = self._device_index(device)
+        cache = self.__dict__.setdefault("_pkm_marg", {})
+        key = (keep, bool(light_weighted), device)
+        if key in cache:
+            return cache[key]
+        cube = self.cube
+        plan = engine.get_plan(cube, device=device)
+        log_dv = np.log(cube.v_edg[1:] - cube.v_edg[:-1])
+        lw = cube.ssps.light_weights
+        npix = cube.nx * cube.ny
+        # smallest cached superset: same weighting, or mass weighted with t and z kept (re-weightable)
+        best = None
+        for (k2, lw2, dev2), arr in cache.items():
+            if dev2 != device or not set(keep) <= set(k2) or k2 == "tvxz":
+                continue
+            if lw2 != bool(light_weighted) and not (light_weighted and not lw2 and "t" in k2 and "z" in k2):
+                continue
+            if best is None or arr.numel() < best[2].numel():
+                best = (k2, lw2, arr)
+        if best is not None:
+            k2, lw2, arr = best
+            out = plan.reduce_logp_from(arr, k2, npix, log_dv, keep, False,
+                                        light_weights=lw if (light_weighted and not lw2) else None)
+        else:
+            src = self._device_log_p(device)
+            out = plan.reduce_logp(src, log_dv, keep, False, light_weights=lw if light_weighted else None)
+            if not engine._is_torch(out):        # host array too large to keep resident: no caching
+                return out
+        nbytes = out.numel() * 8
+        total = sum(a.numel() * 8 for a in cache.values())
+        if nbytes <= self._MARGINAL_CACHE_ITEM and total + nbytes <= self._MARGINAL_CACHE_TOTAL:
+            cache[key] = out
+        return out
 
     def _log_marginal(self, keep, density=True, light_weighted=False):
         """log-marginal over the axes not in `keep`, on the GPU (pkm_reduce_logp)."""
-        cube = self.cube
-        plan = engine.get_plan(cube)
-        log_dv = np.log(cube.v_edg[1:] - cube.v_edg[:-1])
-        lw = cube.ssps.light_weights if light_weighted else None
-        out = plan.reduce_logp(self._device_log_p(), log_dv, keep, density, light_weights=lw)
-        return out.cpu().numpy() if engine._is_torch(out) else out
+        out = self._log_marginal_dev(keep, light_weighted)
+        if not engine._is_torch(out):
+            if density:
+                out = out - np.log(self.cube.construct_volume_element(keep))
+            return out
+        if density:
+            cube = self.cube
+            plan = engine.get_plan(cube, device=int(out.device.index or 0))
+            log_dv = np.log(cube.v_edg[1:] - cube.v_edg[:-1])
+            out = plan.reduce_logp_from(out, keep, cube.nx * cube.ny, log_dv, keep, True)
+        return out.cpu().numpy()
 
     # ------------------------------------------------------------------ moments
     def _moment_axis(self, which_dist):
@@ -153,11 +239,32 @@ class Component(object):
         return variable
 
     def _raw_moments(self, which_dist, light_weighted):
-        """[mean, mu2, mu3, mu4] of a 1-D (conditional) distribution of t, v or z on the GPU."""
+        """[mean, mu2, mu3, mu4] of a 1-D (conditional) distribution of t, v or z.
+
+        One kernel on the device-resident log marginals (pkm_moments_logp): the conditional
+        P = exp(log P(joint) - log P(given)) is formed on the fly and never visits the host."""
+        cache = self.__dict__.setdefault("_pkm_mom", {})
+        key = (which_dist, bool(light_weighted))
+        if key in cache:
+            return cache[key]
         variable = self._moment_axis(which_dist)
-        P = self.get_p(which_dist, light_weighted=light_weighted, density=False)
-        values = self.cube.get_variable_values(variable)
-        return engine.moments(P, values)
+        given = which_dist.split("_")[1] if "_" in which_dist else ""
+        joint = "".join(sorted(variable + given))
+        log_joint = self._log_marginal_dev(joint, light_weighted)
+        if not engine._is_torch(log_joint):        # streamed (host) arrays: the probability route
+            P = self.get_p(which_dist, light_weighted=light_weighted, density=False)
+            out = engine.moments(P, self.cube.get_variable_values(variable))
+        else:
+            log_given = self._log_marginal_dev(given, light_weighted) if given else None
+            shape = self.cube.get_distribution_shape(joint)
+            axis = joint.replace("x", "xy").find(variable)
+            nouter = int(np.prod(shape[:axis], dtype=np.int64))
+            ninner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+            out = engine.moments_logp(log_joint, log_given, self.cube.get_variable_values(variable),
+                                      nouter, shape[axis], ninner)
+            out = out.reshape((4,) + tuple(shape[:axis]) + tuple(shape[axis + 1:]))
+        cache[key] = out
+        return out
 
     def get_mean(self, which_dist, light_weighted=False):
         """Mean of a 1-D distribution, e.g. 'v' -> E(v), 'v_x' -> E(v|x).
@@ -234,21 +341,44 @@ class Component(object):
         return self.get_excess_central_moment(which_dist, 4, light_weighted=light_weighted)
 
     # ------------------------------------------------------------------ the hot path
-    def evaluate_ybar(self, batch="none", device=0, dtype="float64"):
+    def evaluate_ybar(self, batch="none", device=None, dtype="float64"):
         """Evaluate the datacube  ybar(omega, x) = sum_{t,z} p(t,x,z) [S_tz * p(v|t,x,z)](omega).
 
         Stores `self.ybar` [n_fft, nx1, nx2] (float64 NumPy).  `batch` ('none', 'column',
         'spaxel') is accepted for compatibility: the device path tiles pixels internally so
         all three give the same result (base.py:789-882).  `dtype="float32"` (extension) runs
         the contraction in float32 arithmetic (~1e-7 relative; default float64 matches the
-        reference to 1e-10)."""
+        reference to 1e-10).
+
+        A host `log_p_tvxz` is page-locked in place on first use and STREAMED through the
+        library's pipelined staging (H2D of tile i+1, kernels of tile i, D2H of tile i-1): no
+        device copy of the 5-D array is made for this call.  If a device copy already exists
+        (because `get_p` / the moments made one) it is used instead.  The result lands in a
+        page-locked buffer from torch's caching allocator, viewed as a NumPy array."""
         if batch not in ("none", "column", "spaxel"):
             raise ValueError("Unknown option for batch")
         check_velocity_grid(self.cube)
+        device = self._device_index(device)
         plan = engine.get_plan(self.cube, device=device, precision=dtype)
+        src = self.log_p_tvxz
+        cached = self.__dict__.get("_pkm_dev")
+        if engine._is_cuda_tensor(src):
+            self.ybar = plan.ybar_density(src, is_log=True).cpu().numpy()
+            return
+        if cached is not None and cached[0] is src and cached[1] == device:
+            self.ybar = plan.ybar_density(cached[2], is_log=True).cpu().numpy()
+            return
         # the reference evaluates get_p('tvxz') = exp(log p + log dV - log dV); exp is fused
-        out = plan.ybar_density(self._device_log_p(device), is_log=True)
-        self.ybar = out.cpu().numpy() if engine._is_torch(out) else out
+        host = np.ascontiguousarray(src, dtype=np.float64)
+        engine.pin_host_array(host)
+        # drop the previous result first so that its page-locked block can be reused (it is not,
+        # and stays valid, if the caller still holds the old array)
+        self.__dict__.pop("ybar", None)
+        self.__dict__.pop("_pkm_ybar_pin", None)
+        keep, out = engine.pinned_empty((plan.n_fft, self.cube.nx, self.cube.ny))
+        plan.ybar_density(host, is_log=True, out=out)
+        self.__dict__["_pkm_ybar_pin"] = keep
+        self.ybar = out
 
     # ------------------------------------------------------------------ persistence
     def dill_dump(self, fname, direc=None):

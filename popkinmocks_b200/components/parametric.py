@@ -205,6 +205,13 @@ class ParametricComponent(base.Component):
             log_P = log_P - np.log(self.cube.construct_volume_element(keep))
         return log_P
 
+    def _raw_moments(self, which_dist, light_weighted):
+        """[mean, mu2, mu3, mu4] of a 1-D (conditional) distribution of t or z: the analytic
+        marginals live on the host, so the probabilities are handed to pkm_moments."""
+        variable = self._moment_axis(which_dist)
+        P = self.get_p(which_dist, light_weighted=light_weighted, density=False)
+        return engine.moments(P, self.cube.get_variable_values(variable))
+
     # hard-coded conditionals kept for API parity: mass-weighted they are the stored factors
     def _get_log_p_x_t(self, density=True, light_weighted=False):
         if light_weighted:

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 
+#include "exp_tab.cuh"
 #include "pkm_internal.h"
 
 // ----------------------------------------------------------------------------
@@ -125,11 +126,14 @@ static void plan_free(pkm_plan* pl) {
   fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_Sw); fr(pl->d_Sw32);
   fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_omega);
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
-  fr(pl->d_log_dt); fr(pl->d_log_dz);
+  fr(pl->d_log_dt); fr(pl->d_log_dz); fr(pl->d_exp_tab);
   collect_timers(pl);
   for (int i = 0; i < 2; ++i)
     for (cudaEvent_t e : {pl->ev_in[i], pl->ev_done[i], pl->ev_out[i], pl->ev_ready[i]})
       if (e) cudaEventDestroy(e);
+  if (pl->s_k2) cudaStreamDestroy(pl->s_k2);
+  if (pl->ev_k2_fork) cudaEventDestroy(pl->ev_k2_fork);
+  if (pl->ev_k2_join) cudaEventDestroy(pl->ev_k2_join);
   if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
   if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
   pl->coef.release(); pl->yhat.release(); pl->ypx.release(); pl->misc.release(); pl->small.release();
@@ -167,25 +171,32 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
     pl->h_delta_t.assign(delta_t, delta_t + nt);
     pl->h_delta_z.assign(delta_z, delta_z + nz);
 
+    {
+      std::vector<double> tab(PKM_EXP_TAB);
+      pkm_fill_exp_tab(tab.data());
+      pl->d_exp_tab = upload(tab);
+    }
+
     // ---- density path tables
     pl->density_ok = desc->v0_idx >= 0 && desc->v0_idx < desc->nv && pl->nfi >= 4 && pl->nfi <= 64;
     if (pl->density_ok) {
       SplineTables sp;
       build_spline_tables(pl->nfi, nfo, sp);
       build_fold_tables(desc->nv, desc->v0_idx, desc->dv, sp, pl->fold);
-      build_wseg_tables(sp, pl->wsegs);
+      const int kt = desc->precision == 1 ? PKM_KT32 : PKM_KT;
+      build_wseg_tables(sp, kt, pl->wsegs);
       density_tables_upload(pl);
-      // S-hat' per warp segment: [nwseg][nchunk*TZC][KT], rows beyond ntz and slots beyond the
+      // S-hat' per warp segment: [nwseg][nchunk*TZC][kt], rows beyond ntz and slots beyond the
       // segment's count are zero, so every staged chunk is one full-size contiguous bulk copy
       pl->nchunk = (pl->ntz + PKM_TZC - 1) / PKM_TZC;
       const size_t rows = size_t(pl->nchunk) * PKM_TZC;
-      std::vector<double> Sw(size_t(2) * pl->wsegs.nwseg * rows * PKM_KT, 0.0);
+      std::vector<double> Sw(size_t(2) * pl->wsegs.nwseg * rows * kt, 0.0);
       for (int ws = 0; ws < pl->wsegs.nwseg; ++ws) {
         const int k0 = pl->wsegs.seg[4 * ws + 1], cnt = pl->wsegs.seg[4 * ws + 2];
         for (int t = 0; t < nt; ++t)
           for (int z = 0; z < nz; ++z) {
             const double w = delta_z[z] * delta_t[t];
-            double* row = Sw.data() + size_t(2) * ((size_t(ws) * rows + size_t(t) * nz + z) * PKM_KT);
+            double* row = Sw.data() + size_t(2) * ((size_t(ws) * rows + size_t(t) * nz + z) * kt);
             for (int r = 0; r < cnt; ++r) {
               const double* sv = FXw + size_t(2) * ((size_t(k0 + r) * nz + z) * nt + t);
               row[2 * r] = sv[0] * w;
@@ -521,6 +532,25 @@ extern "C" int32_t pkm_ybar_density_into_cube(pkm_plan* pl, const double* dens, 
                       (int64_t)cube_nx1 * nx2, (int64_t)cube_row0 * nx2, stream);
 }
 
+extern "C" int32_t pkm_host_register(void* ptr, int64_t bytes) {
+  return guarded([&] {
+    PKM_REQUIRE(ptr && bytes > 0, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible");
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type != cudaMemoryTypeUnregistered) return;  // already pinned
+    cudaGetLastError();
+    PKM_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  });
+}
+
+extern "C" int32_t pkm_host_unregister(void* ptr) {
+  return guarded([&] {
+    PKM_REQUIRE(ptr, "null argument");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();   // not registered (any more): nothing to undo
+  });
+}
+
 extern "C" int32_t pkm_device_alloc(int32_t device, int64_t bytes, void** ptr_out) {
   return guarded([&] {
     PKM_REQUIRE(ptr_out && bytes > 0, "bad argument");
@@ -739,47 +769,164 @@ extern "C" int32_t pkm_irfft_naive(pkm_plan* pl, const double* Yhat, int64_t npi
 // ----------------------------------------------------------------------------
 // statistics
 // ----------------------------------------------------------------------------
+namespace {
+
+int64_t marginal_size(const pkm_plan* pl, int64_t npix, uint32_t mask) {
+  int64_t n = 1;
+  if (mask & 1) n *= pl->d.nt;
+  if (mask & 2) n *= pl->d.nv;
+  if (mask & 4) n *= npix;
+  if (mask & 8) n *= pl->d.nz;
+  return n;
+}
+
+// device pointers to the small constants of a reduction: log dv [nv] and (optional) log light weights
+struct ReduceConsts {
+  const double* log_dv;
+  const double* log_lw;
+};
+ReduceConsts upload_reduce_consts(pkm_plan* pl, const double* log_dv, const double* light_weights,
+                                  cudaStream_t st) {
+  const int nt = pl->d.nt, nv = pl->d.nv, nz = pl->d.nz;
+  std::vector<double> h(nv + (size_t)nt * nz);
+  for (int v = 0; v < nv; ++v) h[v] = log_dv[v];
+  if (light_weights)
+    for (int i = 0; i < nt * nz; ++i) h[nv + i] = std::log(light_weights[i]);
+  pl->small.reserve(sizeof(double) * h.size());
+  PKM_CUDA(cudaMemcpyAsync(pl->small.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+  PKM_CUDA(cudaStreamSynchronize(st));   // h is a local
+  return ReduceConsts{pl->small.as<double>(), light_weights ? pl->small.as<double>() + nv : nullptr};
+}
+
+// src (device): the 5-D log density (src_mask = 0xF, weighted) or a log-probability marginal holding
+// the axes of src_mask; out (device): the marginal over keep_mask (a subset of src_mask)
+void reduce_device(pkm_plan* pl, const double* src, uint32_t src_mask, bool src_is_density, int64_t npix,
+                   const ReduceConsts& c, bool light, uint32_t keep_mask, int density, double* out,
+                   cudaStream_t st) {
+  PKM_REQUIRE((keep_mask & ~src_mask) == 0, "keep_mask 0x%x is not a subset of the source axes 0x%x", keep_mask, src_mask);
+  ReduceSrc rs;
+  rs.nt = (src_mask & 1) ? pl->d.nt : 1;
+  rs.nv = (src_mask & 2) ? pl->d.nv : 1;
+  rs.npix = (src_mask & 4) ? npix : 1;
+  rs.nz = (src_mask & 8) ? pl->d.nz : 1;
+  rs.weighted = src_is_density ? 1 : 0;
+  if (light) PKM_REQUIRE((src_mask & 9) == 9, "light weighting needs a source that keeps t and z");
+  if (keep_mask == src_mask && !src_is_density && !light) {
+    // nothing to reduce: copy, then convert to a density if asked
+    const int64_t n = marginal_size(pl, npix, keep_mask);
+    if (out != src) PKM_CUDA(cudaMemcpyAsync(out, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (density) launch_apply_log_dv(pl, out, rs, c.log_dv, keep_mask, -1.0, st);
+    return;
+  }
+  // the kernels address kept axes with the SOURCE extents: a kept axis always has its full extent
+  uint32_t km = keep_mask;
+  launch_reduce_logp(pl, src, rs, c.log_dv, light ? c.log_lw : nullptr, km, density, out, st);
+}
+
+}  // namespace
+
 extern "C" int32_t pkm_reduce_logp(pkm_plan* pl, const double* log_p_tvxz, int64_t npix,
                                    const double* log_dv, const double* light_weights,
                                    uint32_t keep_mask, int32_t density, double* out, void* stream) {
+  return pkm_reduce_logp_multi(pl, log_p_tvxz, npix, log_dv, light_weights, 1, &keep_mask, &density, &out, stream);
+}
+
+extern "C" int32_t pkm_reduce_logp_multi(pkm_plan* pl, const double* log_p_tvxz, int64_t npix,
+                                         const double* log_dv, const double* light_weights, int32_t n_out,
+                                         const uint32_t* keep_masks, const int32_t* density,
+                                         double* const* outs, void* stream) {
   return guarded([&] {
-    PKM_REQUIRE(pl && log_p_tvxz && log_dv && out && npix >= 1, "bad argument");
-    PKM_REQUIRE(keep_mask <= 0xF, "bad keep_mask");
+    PKM_REQUIRE(pl && log_p_tvxz && log_dv && keep_masks && density && outs && npix >= 1 && n_out >= 1 && n_out <= 16,
+                "bad argument");
     use_device(pl->d.device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nt = pl->d.nt, nv = pl->d.nv, nz = pl->d.nz;
     const bool host = !pkm_is_device_pointer(log_p_tvxz);
-    PKM_REQUIRE(host == !pkm_is_device_pointer(out), "input and output must be on the same side");
-    size_t nout = 1;
-    if (keep_mask & 1) nout *= nt;
-    if (keep_mask & 2) nout *= nv;
-    if (keep_mask & 4) nout *= (size_t)npix;
-    if (keep_mask & 8) nout *= nz;
-    const size_t ntot = (size_t)nt * nv * npix * nz;
-    // small constants: log_dv [nv], log light weights [nt][nz]
-    std::vector<double> h(nv + (size_t)nt * nz);
-    for (int v = 0; v < nv; ++v) h[v] = log_dv[v];
-    if (light_weights)
-      for (int i = 0; i < nt * nz; ++i) h[nv + i] = std::log(light_weights[i]);
-    pl->small.reserve(sizeof(double) * h.size());
-    PKM_CUDA(cudaMemcpyAsync(pl->small.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
-    PKM_CUDA(cudaStreamSynchronize(st));
-    const double* d_ldv = pl->small.as<double>();
-    const double* d_llw = light_weights ? d_ldv + nv : nullptr;
+    for (int i = 0; i < n_out; ++i) {
+      PKM_REQUIRE(keep_masks[i] <= 0xF, "bad keep_mask");
+      PKM_REQUIRE(outs[i] && host == !pkm_is_device_pointer(outs[i]), "input and outputs must be on the same side");
+    }
+    const ReduceConsts c = upload_reduce_consts(pl, log_dv, light_weights, st);
+    const bool light = light_weights != nullptr;
     const double* d_in = log_p_tvxz;
-    double* d_out = out;
     if (host) {
+      const size_t ntot = (size_t)nt * nv * npix * nz;
       pl->stage_in[0].reserve(sizeof(double) * ntot);
-      pl->stage_out[0].reserve(sizeof(double) * nout);
       PKM_CUDA(cudaMemcpyAsync(pl->stage_in[0].p, log_p_tvxz, sizeof(double) * ntot, cudaMemcpyHostToDevice, st));
       d_in = pl->stage_in[0].as<double>();
-      d_out = pl->stage_out[0].as<double>();
     }
-    launch_reduce_logp(pl, d_in, npix, d_ldv, d_llw, keep_mask, density, d_out, st);
+    // Largest marginals first; every output is held as a log PROBABILITY (density = 0) until the end,
+    // so that a later, smaller marginal can be reduced from the smallest already computed superset
+    // instead of the 5-D array.  (The reductions are bound by one exponential per source element,
+    // so only nested requests share work; disjoint ones each read the 5-D array once.)
+    std::vector<int> order(n_out);
+    for (int i = 0; i < n_out; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+      return marginal_size(pl, npix, keep_masks[a]) > marginal_size(pl, npix, keep_masks[b]);
+    });
+    std::vector<double*> dev(n_out, nullptr);
+    size_t stage_bytes = 0;
+    if (host)
+      for (int i = 0; i < n_out; ++i) stage_bytes += sizeof(double) * (size_t)marginal_size(pl, npix, keep_masks[i]);
+    if (host) pl->stage_out[0].reserve(stage_bytes);
+    {
+      double* cur = host ? pl->stage_out[0].as<double>() : nullptr;
+      for (int i = 0; i < n_out; ++i) {
+        dev[i] = host ? cur : outs[i];
+        if (host) cur += marginal_size(pl, npix, keep_masks[i]);
+      }
+    }
+    for (int oi = 0; oi < n_out; ++oi) {
+      const int i = order[oi];
+      int best = -1;
+      for (int oj = 0; oj < oi; ++oj) {
+        const int j = order[oj];
+        if ((keep_masks[i] & ~keep_masks[j]) != 0) continue;
+        if (best < 0 || marginal_size(pl, npix, keep_masks[j]) < marginal_size(pl, npix, keep_masks[best])) best = j;
+      }
+      if (best >= 0)   // already light-weighted (if asked): a plain log-sum-exp of the superset
+        reduce_device(pl, dev[best], keep_masks[best], false, npix, c, false, keep_masks[i], 0, dev[i], st);
+      else
+        reduce_device(pl, d_in, 0xF, true, npix, c, light, keep_masks[i], 0, dev[i], st);
+    }
+    for (int i = 0; i < n_out; ++i)
+      if (density[i]) {
+        ReduceSrc rs{nt, nv, nz, npix, 0};
+        launch_apply_log_dv(pl, dev[i], rs, c.log_dv, keep_masks[i], -1.0, st);
+      }
     if (host) {
-      PKM_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+      for (int i = 0; i < n_out; ++i)
+        PKM_CUDA(cudaMemcpyAsync(outs[i], dev[i], sizeof(double) * (size_t)marginal_size(pl, npix, keep_masks[i]),
+                                 cudaMemcpyDeviceToHost, st));
       PKM_CUDA(cudaStreamSynchronize(st));
     }
+  });
+}
+
+extern "C" int32_t pkm_reduce_logp_from(pkm_plan* pl, const double* log_P_src, uint32_t src_mask, int64_t npix,
+                                        const double* log_dv, const double* light_weights, uint32_t keep_mask,
+                                        int32_t density, double* out, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(pl && log_P_src && log_dv && out && npix >= 1, "bad argument");
+    PKM_REQUIRE(src_mask <= 0xF && keep_mask <= 0xF, "bad mask");
+    PKM_REQUIRE(pkm_is_device_pointer(log_P_src) && pkm_is_device_pointer(out), "device buffers required");
+    use_device(pl->d.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const ReduceConsts c = upload_reduce_consts(pl, log_dv, light_weights, st);
+    reduce_device(pl, log_P_src, src_mask, false, npix, c, light_weights != nullptr, keep_mask, density, out, st);
+  });
+}
+
+extern "C" int32_t pkm_moments_logp(const double* log_joint, const double* log_given, const double* values,
+                                    int64_t nouter, int64_t nvar, int64_t ninner, double* out, int32_t device,
+                                    void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(log_joint && values && out && nouter >= 1 && nvar >= 1 && ninner >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    PKM_REQUIRE(pkm_is_device_pointer(log_joint) && pkm_is_device_pointer(out) && pkm_is_device_pointer(values) &&
+                (!log_given || pkm_is_device_pointer(log_given)), "device buffers required");
+    use_device(device);
+    launch_moments_logp(log_joint, log_given, values, nouter, nvar, ninner, out, reinterpret_cast<cudaStream_t>(stream));
   });
 }
 

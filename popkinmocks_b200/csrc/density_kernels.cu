@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "exp_tab.cuh"
 #include "pkm_internal.h"
 
 // ============================================================================
@@ -318,30 +319,6 @@ k_coeff(const double* __restrict__ dens, const __grid_constant__ CUtensorMap tma
   }
 }
 
-// exp for the fold phase of the octet kernel, which ran at the FP64-pipe limit with the library
-// exp (~26 FP64 instructions): k = rint(x 256/ln 2), exp(x) = 2^(k>>8) * T[k&255] * e^r with a
-// 256-entry table of 2^(j/256) in shared memory and a degree-4 polynomial on |r| <= ln2/512
-// (truncation 4e-17) - 9 FP64 instructions, error < 2 ulp.  (A conflict-free 16-entry table with a
-// degree-8 polynomial measured slower: the fold is bound by FP64 issue, not by the lookups.)
-// Below -708 the result is flushed to 0 (the library would return a denormal < 3e-308), above
-// 709 it is +inf.
-constexpr int EXP_TAB = 256;
-__constant__ double c_exp2_tab[EXP_TAB];
-__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-  const double t = fma(x, 369.32993046757463228, 6755399441055744.0);   // 256/ln2, 1.5 * 2^52
-  const int k = __double2loint(t);
-  const double fk = t - 6755399441055744.0;
-  double r = fma(fk, -2.70760617331688990816e-03, x);                    // ln2/256 high part
-  r = fma(fk, -7.45396456746323320321e-13, r);                           // ln2/256 low part
-  double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
-  q = fma(q, r, 0.5);
-  const double p = fma(r * r, q, r);                                     // e^r - 1
-  const double T = tab[k & (EXP_TAB - 1)];
-  const double v = fma(T, p, T);                                         // in [1, 2.01)
-  const double y = __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));
-  return x < -708.0 ? 0.0 : (x > 709.0 ? INFINITY : y);
-}
-
 // ----------------------------------------------------------------------------
 // Variant used whenever the slab can be fetched as one 2-D tensor copy: one warp = (metallicity z,
 // 8 consecutive pixels), real AND imaginary part.  The 8 columns of a warp's DMMA tile are then 8
@@ -355,7 +332,8 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
 template <int TM>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap, K1Geom g,
-            const double* __restrict__ CRt, const double* __restrict__ CIt) {
+            const double* __restrict__ CRt, const double* __restrict__ CIt,
+            const double* __restrict__ exp2_tab) {
   extern __shared__ __align__(128) double smem[];
   constexpr int MB = TM;
   const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, pxb = g.pxb, v0 = g.v0;
@@ -367,14 +345,14 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   double* As_r = smem;
   double* As_i = As_r + frag_elems;
   double* Bbuf = As_i + frag_elems;
-  double* etab = Bbuf + 2 * (size_t)buf_elems;                           // [EXP_TAB] 2^(j/256)
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(etab + EXP_TAB);
+  double* etab = Bbuf + 2 * (size_t)buf_elems;                           // [PKM_EXP_TAB] 2^(j/256)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(etab + PKM_EXP_TAB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < frag_elems; i += K1_THREADS) {
     As_r[i] = CRt[i];
     As_i[i] = CIt[i];
   }
-  for (int i = tid; i < EXP_TAB; i += K1_THREADS) etab[i] = c_exp2_tab[i];
+  for (int i = tid; i < PKM_EXP_TAB; i += K1_THREADS) etab[i] = exp2_tab[i];
   const unsigned bar0 = smem_u32(bars);
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -537,9 +515,6 @@ void density_tables_upload(pkm_plan* pl) {
   pl->nfiP = nks * pl->TM * 32;  // doubles per A operand
   upload_fragments(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, nks, &pl->d_CRt);
   upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt);
-  double tab[EXP_TAB];
-  for (int j = 0; j < EXP_TAB; ++j) tab[j] = (double)exp2l((long double)j / (long double)EXP_TAB);
-  PKM_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
@@ -648,7 +623,7 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
 
 static size_t coeff_oct_smem(const pkm_plan* pl, int NC) {
   const size_t buf_elems = ((size_t)std::max(pl->d.nv, 2 * pl->nfi) * NC + 15) & ~size_t(15);
-  return ((size_t)2 * pl->nfiP + 2 * buf_elems + EXP_TAB) * sizeof(double) + 16;
+  return ((size_t)2 * pl->nfiP + 2 * buf_elems + PKM_EXP_TAB) * sizeof(double) + 16;
 }
 
 // 4-D view of the coefficient array cT[x/32][t*nz+z][m][x%32] (complex) in scalar elements:
@@ -713,7 +688,7 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   g.out_f32 = pl->d.precision == 1;
   g.use_tma = 2;
   KernelTimer tm(pl, PKM_K_COEFF, st);
-  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt);
+  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt, pl->d_exp_tab);
   PKM_CUDA(cudaGetLastError());
 #ifdef PKM_K1_PROF
   {
@@ -756,26 +731,47 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 // ============================================================================
 // kernel 2
 // ============================================================================
-// Y-hat[k,x] = sum_{tz} S'[k,tz] * sum_{q<4} w[k][q] c[i_k+q, tz, x]     (10.6 FP64 ops per (k,tz,x))
+// Y-hat[k,x] = sum_{tz} S'[k,tz] * sum_{q<4} w[k][q] c[i_k+q, tz, x]     (10.2 FP64 ops per (k,tz,x))
 //
-// The kernel is bound by the FP64 pipe, so everything else is arranged to stay out of its way:
+// The kernel is bound by the FP64 pipe, and on B200 a DFMA whose three operands all come from
+// the vector register file issues every 3 cycles instead of every 2.17 (tools/dfma_rf.cu: 24.5
+// vs 34.2 TFLOP/s).  Everything is arranged around that:
 //   * work item = one warp = (warp segment, block of 32 pixels): the lanes are 32 consecutive
-//     pixels, every lane owns the SAME KT <= 10 consecutive frequencies of one spline span,
+//     pixels, every lane owns the SAME KT <= 25 consecutive frequencies of one spline span,
 //     so the 4 coefficient rows it needs are shared by all its frequencies (4 coalesced
-//     512-byte loads per (t,z), prefetched one (t,z) ahead in registers) and the spline tap
-//     weights live in registers for the whole (t,z) loop;
+//     512-byte loads per (t,z), prefetched one (t,z) ahead in registers);
+//   * the 4 warps of a CTA work on the SAME warp segment (4 pixel blocks), so the segment index
+//     depends on blockIdx only and the 3 KT spline weights are read from the KERNEL-PARAMETER
+//     bank with a uniform index: ptxas keeps them in uniform registers (LDCU.64 + DFMA with a UR
+//     operand).  The 6 spline DFMAs of a term then read two vector registers and run at the full
+//     rate; only the 4 complex-MAC DFMAs stay register-file limited.  The parameter bank holds
+//     the weights of K2_WP_SEGS segments, so one pixel tile takes ceil(nwseg / K2_WP_SEGS) launches;
+//   * with the weights out of the vector registers KT = 25 fits (2 segments per spline span at
+//     the headline shape): the coefficient loads, the 6 DADDs forming d_q = c_q - c_3 and the
+//     loop overhead are amortised over 2.5x more DFMAs than with KT = 10;
 //   * S' is warp-uniform: it is staged in shared memory by 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx), one 1920-byte chunk = 12 (t,z) rows x KT
-//     frequencies per copy, 3 stages per warp, and read back as broadcast LDS.128;
-//   * warps are fully independent pipelines (own stages, own mbarriers, no CTA barrier):
-//     CTA = 4 warps, K2_CTAS_PER_SM CTAs per SM.
+//     (cp.async.bulk + mbarrier complete_tx), one chunk = 12 (t,z) rows x KT frequencies per
+//     copy, 3 stages per warp, and read back as broadcast LDS.128;
+//   * warps are fully independent pipelines (own stages, own mbarriers, no CTA barrier).
+// tools/contract_probe.cu is the harness the variants were measured with (one 7168-pixel tile:
+// 10.19 ms for the round-1 kernel, 8.18 ms = 28.2 TFLOP/s for this one).
 constexpr int K2_WARPS = 4;
 constexpr int K2_STAGES = 3;
-constexpr int K2_CTAS_PER_SM = 3;
+#ifndef PKM_K2_CTAS
+#define PKM_K2_CTAS 3
+#endif
+#ifndef PKM_K2_G
+#define PKM_K2_G 5
+#endif
+constexpr int K2_CTAS_PER_SM = PKM_K2_CTAS;
 constexpr int K2_PF = 12;      // L2 prefetch distance of the coefficient rows in (t,z) steps
-constexpr int K2_G = 2;        // frequencies whose FMA chains are interleaved (PKM_KT % K2_G == 0)
+constexpr int K2_G = PKM_K2_G;  // frequencies whose FMA chains are interleaved
 constexpr int K2_CHUNK_ELEMS = PKM_TZC * PKM_KT;                      // double2 per staged chunk
-constexpr unsigned K2_CHUNK_BYTES = K2_CHUNK_ELEMS * sizeof(double2);  // 1920
+constexpr unsigned K2_CHUNK_BYTES = K2_CHUNK_ELEMS * sizeof(double2);  // 4800
+constexpr int K2_WP_SEGS = 30000 / (PKM_KT * 3 * 8);                  // segments per launch (parameter bank: 32 KB)
+struct K2Weights {
+  double w[K2_WP_SEGS][PKM_KT][3];
+};
 
 __device__ __forceinline__ double2 ldg_nc_f64x2(const double2* p) {
   double2 v;
@@ -784,29 +780,25 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const double2* p) {
 }
 
 __global__ void __launch_bounds__(K2_WARPS * 32, K2_CTAS_PER_SM)
-k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
-           const int4* __restrict__ wsegs, const double2* __restrict__ cT,
-           double2* __restrict__ yhat, int nwseg, int ntz, int nchunk, int nfi, int xpad, int np,
-           int nfo, long long nitems) {
+k_contract(const __grid_constant__ K2Weights wp, int ws0, int nws, const double2* __restrict__ Sw,
+           const int4* __restrict__ wsegs, const double2* __restrict__ cT, double2* __restrict__ yhat,
+           int ntz, int nchunk, int nfi, int np, int nfo, int npg) {
   extern __shared__ __align__(128) unsigned char k2_smem[];
   double2 (*sS)[K2_STAGES][K2_CHUNK_ELEMS] = reinterpret_cast<double2 (*)[K2_STAGES][K2_CHUNK_ELEMS]>(k2_smem);
   unsigned long long (*sBar)[K2_STAGES] = reinterpret_cast<unsigned long long (*)[K2_STAGES]>(
       k2_smem + sizeof(double2) * K2_WARPS * K2_STAGES * K2_CHUNK_ELEMS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long item = (long long)blockIdx.x * K2_WARPS + warp;
-  if (item >= nitems) return;  // warps never synchronise with each other
-  const int pg = (int)(item / nwseg), ws = (int)(item - (long long)pg * nwseg);
+  const int wsl = blockIdx.x % nws;                   // uniform: warp segment within this launch
+  const int pg = (blockIdx.x / nws) * K2_WARPS + warp;
+  if (pg >= npg) return;  // warps never synchronise with each other
+  const int ws = ws0 + wsl;
   const int4 sg = __ldg(wsegs + ws);  // {first coefficient row, k0, count, -}
   const int x = pg * 32 + lane;
   const int xl = min(x, np - 1);      // lanes past the tile re-read the last pixel, never store
 
   // The 4 B-spline taps of a frequency sum to one, so P-hat = c3 + sum_{q<3} w_q (c_q - c3):
-  // three weights per frequency in registers and 3 instead of 4 FP64 ops per component.
-  double w[PKM_KT][3];
-#pragma unroll
-  for (int r = 0; r < PKM_KT; ++r)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) w[r][q] = __ldg(Ww + ((size_t)ws * PKM_KT + r) * 4 + q);
+  // three weights per frequency and 3 instead of 4 FP64 ops per component.
+  const double (&w)[PKM_KT][3] = wp.w[wsl];
   double2 acc[PKM_KT];
 #pragma unroll
   for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
@@ -828,7 +820,7 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
   __syncwarp();
 
   // coefficients are stored pixel-group major, cT[x/32][tz][m][x%32]: the ntz*nfi rows one warp
-  // walks are a single contiguous 16 MB stream (TLB and DRAM-page friendly), 512 bytes per row
+  // walks are a single contiguous stream (TLB and DRAM-page friendly), 512 bytes per row
   const size_t c_step = (size_t)nfi * 32;
   const double2* cp = cT + (((size_t)pg * ntz) * nfi + sg.x) * 32 + (xl & 31);
   double2 c[4];
@@ -850,8 +842,7 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
 #pragma unroll
       for (int q = 0; q < 3; ++q) d[q] = make_double2(c[q].x - c3.x, c[q].y - c3.y);
       cp += (tz + 1 < ntz) ? c_step : 0;  // branch-free: the last step re-reads its own rows
-      // the coefficient tile streams from HBM: each warp pulls one of the span's 4 rows a few
-      // steps ahead into L2 (the ~5 warps of a span cover all four), hiding the DRAM latency
+      // the coefficient tile streams from HBM: pull the rows a few steps ahead into L2
       if (tz + K2_PF < ntz) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -859,41 +850,27 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) c[q] = ldg_nc_f64x2(cp + q * 32);
-      // B200's FP64 pipe needs >= 4 independent DFMAs per warp to reach its issue rate (8-cycle
-      // latency, one warp instruction per ~2.2 cycles per scheduler): frequencies are processed
-      // in groups of K2_G with their chains interleaved.  Measured ceiling: a DFMA with three
-      // fresh register operands costs 3 cycles of register-file bandwidth (25.5 TFLOP/s chip-wide
-      // vs 36.9 with an immediate operand, tools/dfma_rf.cu); this loop runs at ~85 % of that.
+      const double2* srow = sbuf + j * PKM_KT;
 #pragma unroll
       for (int h = 0; h < PKM_KT; h += K2_G) {
         double pr[K2_G], pi[K2_G];
-        double2 sv[K2_G];
 #pragma unroll
-        for (int g = 0; g < K2_G; ++g) {
-          if (h + g >= PKM_KT) continue;
-          sv[g] = sbuf[j * PKM_KT + h + g];
-          pr[g] = c3.x;
-          pi[g] = c3.y;
-        }
+        for (int q = 0; q < 3; ++q) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+          for (int g = 0; g < K2_G; ++g)
+            if (h + g < PKM_KT) pr[g] = fma(w[h + g][q], d[q].x, q == 0 ? c3.x : pr[g]);
 #pragma unroll
-          for (int g = 0; g < K2_G; ++g) {
-            if (h + g >= PKM_KT) continue;
-            pr[g] = fma(w[h + g][q], d[q].x, pr[g]);
-            pi[g] = fma(w[h + g][q], d[q].y, pi[g]);
-          }
-#pragma unroll
-        for (int g = 0; g < K2_G; ++g) {
-          if (h + g >= PKM_KT) continue;
-          acc[h + g].x = fma(sv[g].x, pr[g], acc[h + g].x);
-          acc[h + g].y = fma(sv[g].x, pi[g], acc[h + g].y);
+          for (int g = 0; g < K2_G; ++g)
+            if (h + g < PKM_KT) pi[g] = fma(w[h + g][q], d[q].y, q == 0 ? c3.y : pi[g]);
         }
 #pragma unroll
         for (int g = 0; g < K2_G; ++g) {
           if (h + g >= PKM_KT) continue;
-          acc[h + g].x = fma(-sv[g].y, pi[g], acc[h + g].x);
-          acc[h + g].y = fma(sv[g].y, pr[g], acc[h + g].y);
+          const double2 s = srow[h + g];
+          acc[h + g].x = fma(s.x, pr[g], acc[h + g].x);
+          acc[h + g].y = fma(s.x, pi[g], acc[h + g].y);
+          acc[h + g].x = fma(-s.y, pi[g], acc[h + g].x);
+          acc[h + g].y = fma(s.y, pr[g], acc[h + g].y);
         }
       }
     }
@@ -922,7 +899,7 @@ k_contract(const double2* __restrict__ Sw, const double* __restrict__ Ww,
 // accumulated in float32 and then folded into float64 accumulators, so the 636-term sum does
 // not lose accuracy to float32 accumulation.  Same work decomposition and TMA staging as above.
 // ----------------------------------------------------------------------------
-constexpr int K2F_CHUNK_ELEMS = PKM_TZC * PKM_KT;                       // float2 per staged chunk
+constexpr int K2F_CHUNK_ELEMS = PKM_TZC * PKM_KT32;                       // float2 per staged chunk
 constexpr unsigned K2F_CHUNK_BYTES = K2F_CHUNK_ELEMS * sizeof(float2);   // 960
 
 __global__ void __launch_bounds__(K2_WARPS * 32, 3)
@@ -940,14 +917,14 @@ k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
   const int x = pg * 32 + lane;
   const int xl = min(x, np - 1);
 
-  float w[PKM_KT][3];
+  float w[PKM_KT32][3];
 #pragma unroll
-  for (int r = 0; r < PKM_KT; ++r)
+  for (int r = 0; r < PKM_KT32; ++r)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) w[r][q] = (float)__ldg(Ww + ((size_t)ws * PKM_KT + r) * 4 + q);
-  double2 acc[PKM_KT];
+    for (int q = 0; q < 3; ++q) w[r][q] = (float)__ldg(Ww + ((size_t)ws * PKM_KT32 + r) * 4 + q);
+  double2 acc[PKM_KT32];
 #pragma unroll
-  for (int r = 0; r < PKM_KT; ++r) acc[r] = make_double2(0.0, 0.0);
+  for (int r = 0; r < PKM_KT32; ++r) acc[r] = make_double2(0.0, 0.0);
 
   const float2* Sg = Sw + (size_t)ws * nchunk * K2F_CHUNK_ELEMS;
   const unsigned bar0 = smem_u32(&sBar[warp][0]);
@@ -978,9 +955,9 @@ k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
     mbar_wait(bar0 + 8u * stage, parity);
     const float2* sbuf = &sS[warp][stage][0];
     const int nrow = min(PKM_TZC, ntz - ci * PKM_TZC);
-    float2 a32[PKM_KT];
+    float2 a32[PKM_KT32];
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) a32[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < PKM_KT32; ++r) a32[r] = make_float2(0.f, 0.f);
     for (int j = 0; j < nrow; ++j, ++tz) {
       const float2 c3 = c[3];
       float2 d[3];
@@ -992,8 +969,8 @@ k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
 #pragma unroll
       for (int q = 0; q < 4; ++q) c[q] = __ldg(cp + q * 32);
 #pragma unroll
-      for (int r = 0; r < PKM_KT; ++r) {
-        const float2 s = sbuf[j * PKM_KT + r];
+      for (int r = 0; r < PKM_KT32; ++r) {
+        const float2 s = sbuf[j * PKM_KT32 + r];
         float pr = c3.x, pi = c3.y;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -1007,7 +984,7 @@ k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
       }
     }
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r) {
+    for (int r = 0; r < PKM_KT32; ++r) {
       acc[r].x += (double)a32[r].x;
       acc[r].y += (double)a32[r].y;
     }
@@ -1025,9 +1002,19 @@ k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
   if (x < np) {
     double2* yo = yhat + (size_t)x * nfo + sg.y;
 #pragma unroll
-    for (int r = 0; r < PKM_KT; ++r)
+    for (int r = 0; r < PKM_KT32; ++r)
       if (r < sg.z) yo[r] = acc[r];
   }
+}
+
+// side stream (+ fork / join events) for the alternate launches of one tile, created on first use
+static bool contract_side_stream(pkm_plan* pl) {
+  if (pl->s_k2) return true;
+  if (getenv("PKM_CONTRACT_NO_FORK")) return false;
+  PKM_CUDA(cudaStreamCreateWithFlags(&pl->s_k2, cudaStreamNonBlocking));
+  PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_k2_fork, cudaEventDisableTiming));
+  PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_k2_join, cudaEventDisableTiming));
+  return true;
 }
 
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
@@ -1044,16 +1031,37 @@ void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, d
     pl->launches++;
     return;
   }
-  const long long npg = (npix_tile + 31) / 32;
-  const long long nitems = npg * pl->wsegs.nwseg;
-  const unsigned grid = (unsigned)((nitems + K2_WARPS - 1) / K2_WARPS);
+  (void)xpad;
+  const int npg = (npix_tile + 31) / 32;
   const size_t smem = sizeof(double2) * K2_WARPS * K2_STAGES * K2_CHUNK_ELEMS +
                       sizeof(unsigned long long) * K2_WARPS * K2_STAGES;
   PKM_CUDA(cudaFuncSetAttribute(k_contract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KernelTimer tm(pl, PKM_K_CONTRACT, st);
-  k_contract<<<grid, K2_WARPS * 32, smem, st>>>(pl->d_Sw, pl->d_wseg_w, reinterpret_cast<const int4*>(pl->d_wseg),
-                                            cT, yhat, pl->wsegs.nwseg, pl->ntz, pl->nchunk, pl->nfi, xpad,
-                                            npix_tile, pl->nfo, nitems);
-  PKM_CUDA(cudaGetLastError());
-  pl->launches++;
+  static_assert(sizeof(K2Weights) <= 30000, "the spline weights of one launch must fit the parameter bank");
+  // The launches of one tile are independent: every other one goes to a side stream so that the
+  // CTAs of the next launch fill the SMs while the last wave of the previous one drains.
+  const int nlaunch = (pl->wsegs.nwseg + K2_WP_SEGS - 1) / K2_WP_SEGS;
+  const bool fork = nlaunch > 1 && contract_side_stream(pl);
+  if (fork) {
+    PKM_CUDA(cudaEventRecord(pl->ev_k2_fork, st));
+    PKM_CUDA(cudaStreamWaitEvent(pl->s_k2, pl->ev_k2_fork, 0));
+  }
+  K2Weights wp;
+  int li = 0;
+  for (int ws0 = 0; ws0 < pl->wsegs.nwseg; ws0 += K2_WP_SEGS, ++li) {
+    const int nws = std::min(K2_WP_SEGS, pl->wsegs.nwseg - ws0);
+    for (int i = 0; i < nws; ++i)
+      for (int r = 0; r < PKM_KT; ++r)
+        for (int q = 0; q < 3; ++q) wp.w[i][r][q] = pl->wsegs.w[((size_t)(ws0 + i) * PKM_KT + r) * 4 + q];
+    const unsigned grid = (unsigned)(((npg + K2_WARPS - 1) / K2_WARPS) * nws);
+    cudaStream_t ls = (fork && (li & 1)) ? pl->s_k2 : st;
+    k_contract<<<grid, K2_WARPS * 32, smem, ls>>>(wp, ws0, nws, pl->d_Sw, reinterpret_cast<const int4*>(pl->d_wseg), cT,
+                                              yhat, pl->ntz, pl->nchunk, pl->nfi, npix_tile, pl->nfo, npg);
+    PKM_CUDA(cudaGetLastError());
+    pl->launches++;
+  }
+  if (fork) {
+    PKM_CUDA(cudaEventRecord(pl->ev_k2_join, pl->s_k2));
+    PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_k2_join, 0));
+  }
 }

@@ -72,14 +72,15 @@ void build_fold_tables(int nv, int v0_idx, double dv, const SplineTables& sp, Fo
 
 // Work items of the contraction kernel: a "warp segment" is a run of at most PKM_KT consecutive
 // output frequencies that share one 4-tap coefficient window (one spline span).
-constexpr int PKM_KT = 10;      // frequencies per thread of the contraction kernels
+constexpr int PKM_KT = 25;      // frequencies per thread of the float64 contraction kernel
+constexpr int PKM_KT32 = 10;    // ... of the float32 contraction kernel (weights in vector registers)
 constexpr int PKM_TZC = 12;     // (t,z) rows per staged S-hat' chunk (one bulk copy)
 struct WsegTables {
-  int nwseg = 0;
+  int nwseg = 0, kt = 0;
   std::vector<int32_t> seg;     // [nwseg][4] = {first coefficient row, first frequency k0, count, 0}
-  std::vector<double> w;        // [nwseg][PKM_KT][4] spline tap weights (zero for padding slots)
+  std::vector<double> w;        // [nwseg][kt][4] spline tap weights (zero for padding slots)
 };
-void build_wseg_tables(const SplineTables& sp, WsegTables& out);
+void build_wseg_tables(const SplineTables& sp, int kt, WsegTables& out);
 
 // chirp-z tables for the arbitrary-length inverse real FFT
 struct CztTables {
@@ -139,6 +140,8 @@ struct pkm_plan {
   double2* d_Bhat = nullptr;    // [M] forward transform of bfilt, in the kernel's permuted order
   double2* d_wn = nullptr;      // [n] exp(+2 pi i r / n) for the naive cross-check transform
 
+  double* d_exp_tab = nullptr;  // [256] 2^(j/256) for exp_tab()
+
   // statistics
   double* d_log_dt = nullptr;   // [nt]
   double* d_log_dz = nullptr;   // [nz]
@@ -149,6 +152,8 @@ struct pkm_plan {
   // host-buffer pipeline: s_copy = H2D stream, s_comp = D2H stream; per staging slot:
   // ev_in (H2D landed), ev_done (kernel 1 consumed it), ev_ready (output staged), ev_out (D2H done)
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaStream_t s_k2 = nullptr;           // side stream of the contraction's alternate launches
+  cudaEvent_t ev_k2_fork = nullptr, ev_k2_join = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr}, ev_ready[2] = {nullptr, nullptr};
 };
@@ -183,9 +188,21 @@ void launch_logsumexp_cubes(int n_cmps, const double* const* d_ptrs_dev, const d
                             double* out, cudaStream_t st);
 
 // statistics kernels (stats.cu)
-void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const double* d_log_dv,
+// Source of a log-sum-exp reduction: the 5-D log density (weighted = 1: the log volume elements
+// are added on the fly) or an already volume-weighted log-probability marginal of it (weighted = 0),
+// whose summed-out axes have extent 1.
+struct ReduceSrc {
+  int nt, nv, nz;
+  int64_t npix;
+  int weighted;
+};
+void launch_reduce_logp(pkm_plan* pl, const double* logp, const ReduceSrc& src, const double* d_log_dv,
                         const double* d_log_lw, uint32_t keep_mask, int density, double* out,
                         cudaStream_t st);
+void launch_apply_log_dv(pkm_plan* pl, double* out, const ReduceSrc& src, const double* d_log_dv,
+                         uint32_t keep_mask, double sign, cudaStream_t st);
+void launch_moments_logp(const double* log_joint, const double* log_given, const double* values,
+                         int64_t nouter, int64_t nvar, int64_t ninner, double* out, cudaStream_t st);
 void density_tables_upload(pkm_plan* pl);
 int coeff_choose_pxb(const pkm_plan* pl, int* ngroup_out = nullptr);
 void launch_moments(const double* P, const double* values, int64_t nvar, int64_t ncond,

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "exp_tab.cuh"
 #include "pkm_internal.h"
 
 namespace {
@@ -30,7 +31,9 @@ struct ReduceGeom {
   int nt, nv, nz;
   long long npix;
   int kt, kv, kx, kz;  // 1 = axis kept
-  double log_dxdy;
+  double log_dxdy;     // 0 when the source already holds volume-weighted log probabilities
+  int wt;              // 1 = add the log volume elements of (t, v, z) to the source (a log DENSITY)
+  double out_log_dxdy; // log(dx dy): what a density OUTPUT divides by when x is kept
 };
 
 __device__ __forceinline__ long long out_index(const ReduceGeom& g, int t, int v, long long x, int z) {
@@ -47,7 +50,7 @@ struct Lse {
 };
 __device__ __forceinline__ Lse lse_merge(Lse a, Lse b) {
   const double M = fmax(a.m, b.m);
-  if (!(M > -INFINITY)) return Lse{-INFINITY, 0.0};
+  if (!(M > -INFINITY)) return Lse{-INFINITY, a.s + b.s};   // 0, or NaN if either side carries one
   return Lse{M, a.s * exp(a.m - M) + b.s * exp(b.m - M)};
 }
 
@@ -64,10 +67,12 @@ constexpr int RED_U = 8;
 __global__ void __launch_bounds__(256)
 k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
                 const double* __restrict__ log_dv, const double* __restrict__ log_dz,
-                const double* __restrict__ log_lw, double* __restrict__ mx, double* __restrict__ out,
-                double* __restrict__ gmax, int PB, long long nchunk) {
+                const double* __restrict__ log_lw, const double* __restrict__ exp2_tab,
+                double* __restrict__ mx, double* __restrict__ out, double* __restrict__ gmax, int PB,
+                long long nchunk) {
   extern __shared__ double s_tab[];          // this CTA's log_dt [t0,t1) | log_dv [v0,v1) | log_lw rows
   __shared__ double red_m[256], red_s[256];
+  __shared__ double s_exp[PKM_EXP_TAB];      // 2^(j/256) for exp_tab()
   const int tid = threadIdx.x;
   int t0 = 0, t1 = g.nt, v0 = 0, v1 = g.nv;
   if (g.kt) { t0 = blockIdx.y; t1 = t0 + 1; }
@@ -75,9 +80,10 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
   double* s_dt = s_tab;
   double* s_dv = s_tab + (t1 - t0);
   double* s_lw = s_dv + (v1 - v0);
-  for (int i = tid; i < t1 - t0; i += blockDim.x) s_dt[i] = log_dt[t0 + i];
-  for (int i = tid; i < v1 - v0; i += blockDim.x) s_dv[i] = log_dv[v0 + i];
+  for (int i = tid; i < t1 - t0; i += blockDim.x) s_dt[i] = g.wt ? log_dt[t0 + i] : 0.0;
+  for (int i = tid; i < v1 - v0; i += blockDim.x) s_dv[i] = g.wt ? log_dv[v0 + i] : 0.0;
   if (log_lw) for (int i = tid; i < (t1 - t0) * g.nz; i += blockDim.x) s_lw[i] = log_lw[t0 * g.nz + i];
+  for (int i = tid; i < PKM_EXP_TAB; i += blockDim.x) s_exp[i] = exp2_tab[i];
   __syncthreads();
 
   const int nact = PB * g.nz;
@@ -87,21 +93,29 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
 
   Lse acc{-INFINITY, 0.0};
   // consume a batch: one maximum, then RED_U + 1 independent exps
+  // (table exp, exp_tab.cuh: 9 FP64 instructions instead of the library's ~26 - the exponentials,
+  // not HBM, bound this kernel.  fmax ignores NaN, exp_tab propagates it: a NaN element makes the
+  // sum NaN, as scipy's logsumexp does; a batch holding only -inf / NaN is checked separately)
   auto flush = [&acc](const double (&a)[RED_U]) {
     double bm = a[0];
 #pragma unroll
     for (int k = 1; k < RED_U; ++k) bm = fmax(bm, a[k]);
     if (bm > -INFINITY) {
       const double M = fmax(acc.m, bm);
-      double sum = acc.s * exp(acc.m - M);
+      double sum = acc.s * exp_tab(acc.m - M, s_exp);
 #pragma unroll
-      for (int k = 0; k < RED_U; ++k) sum += exp(a[k] - M);
+      for (int k = 0; k < RED_U; ++k) sum += exp_tab(a[k] - M, s_exp);
       acc.m = M;
       acc.s = sum;
+    } else {
+      bool nan = false;
+#pragma unroll
+      for (int k = 0; k < RED_U; ++k) nan = nan || a[k] != a[k];
+      if (nan) acc.s = NAN;
     }
   };
   if (tid < nact) {
-    const double cz = log_dz[z] + g.log_dxdy;
+    const double cz = (g.wt ? log_dz[z] : 0.0) + g.log_dxdy;
     const int nT = t1 - t0, nV = v1 - v0;
     const long long cstep = g.kx ? nchunk : G;          // x kept: exactly one chunk per CTA
     if (nV > 1) {
@@ -262,13 +276,14 @@ __global__ void k_reduce_finalize(double* __restrict__ out, const double* __rest
     if (g.kv) { v = (int)(r % g.nv); r /= g.nv; }
     if (g.kt) { t = (int)r; }
     double m = mx[i];
-    double val = (m > -INFINITY) ? m + log(out[i]) : -INFINITY;
+    const double sm = out[i];
+    double val = (m > -INFINITY || sm != sm) ? m + log(sm) : -INFINITY;
     val -= lognorm;
     if (density) {
       double ldv = 0.0;
       if (g.kt) ldv += log_dt[t];
       if (g.kv) ldv += log_dv[v];
-      if (g.kx) ldv += g.log_dxdy;
+      if (g.kx) ldv += g.out_log_dxdy;
       if (g.kz) ldv += log_dz[z];
       val -= ldv;
     }
@@ -288,7 +303,8 @@ __global__ void k_reduce_identity(const double* __restrict__ logp, ReduceGeom g,
     r /= g.npix;
     int v = (int)(r % g.nv); r /= g.nv;
     int t = (int)r;
-    out[i] = logp[i] + log_dt[t] + log_dv[v] + g.log_dxdy + log_dz[z] + (log_lw ? log_lw[t * g.nz + z] : 0.0);
+    const double ldV = g.wt ? log_dt[t] + log_dv[v] + g.log_dxdy + log_dz[z] : 0.0;
+    out[i] = logp[i] + ldV + (log_lw ? log_lw[t * g.nz + z] : 0.0);
   }
 }
 
@@ -305,7 +321,7 @@ __global__ void k_sub_density(double* __restrict__ out, long long ntot, ReduceGe
     int v = (int)(r % g.nv); r /= g.nv;
     int t = (int)r;
     double val = out[i] - ln;
-    if (density) val -= log_dt[t] + log_dv[v] + g.log_dxdy + log_dz[z];
+    if (density) val -= log_dt[t] + log_dv[v] + g.out_log_dxdy + log_dz[z];
     out[i] = val;
   }
 }
@@ -333,6 +349,56 @@ __global__ void k_moments(const double* __restrict__ P, const double* __restrict
   out[ncond + c] = m2;
   out[2 * ncond + c] = m3;
   out[3 * ncond + c] = m4;
+}
+
+// Moments of a conditional distribution straight from the log-probability marginals
+// (base.py:130-177, 208-260): P_i = exp(log_joint[a][i][b] - log_given[a][b]), i = variable index,
+// (a, b) = conditioner index c = a * ninner + b.  log_given may be NULL (unconditional, P = exp(joint)).
+// out[0][c] = mean, out[1..3][c] = central moments 2..4.  NaN where P(given) = 0, as in the reference.
+__global__ void k_moments_logp(const double* __restrict__ lj, const double* __restrict__ lg,
+                               const double* __restrict__ values, long long nouter, long long nvar,
+                               long long ninner, double* __restrict__ out) {
+  const long long ncond = nouter * ninner;
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncond) return;
+  const long long a = c / ninner, b = c - a * ninner;
+  const double* col = lj + a * nvar * ninner + b;
+  const double g = lg ? lg[c] : 0.0;
+  double mean = 0.0;
+  for (long long i = 0; i < nvar; ++i) mean += values[i] * exp(col[i * ninner] - g);
+  double m2 = 0.0, m3 = 0.0, m4 = 0.0;
+  for (long long i = 0; i < nvar; ++i) {
+    const double d = values[i] - mean, p = exp(col[i * ninner] - g);
+    const double d2 = d * d;
+    m2 += d2 * p;
+    m3 += d2 * d * p;
+    m4 += d2 * d2 * p;
+  }
+  out[c] = mean;
+  out[ncond + c] = m2;
+  out[2 * ncond + c] = m3;
+  out[3 * ncond + c] = m4;
+}
+
+// out[i] += sign * log dV(kept axes of i)   (log probability <-> log density of a marginal)
+__global__ void k_apply_log_dv(double* __restrict__ out, long long nout, ReduceGeom g,
+                               const double* __restrict__ log_dt, const double* __restrict__ log_dv,
+                               const double* __restrict__ log_dz, double sign) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nout;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    int z = 0, t = 0, v = 0;
+    if (g.kz) { z = (int)(r % g.nz); r /= g.nz; }
+    if (g.kx) { r /= g.npix; }
+    if (g.kv) { v = (int)(r % g.nv); r /= g.nv; }
+    if (g.kt) { t = (int)r; }
+    double ldv = 0.0;
+    if (g.kt) ldv += log_dt[t];
+    if (g.kv) ldv += log_dv[v];
+    if (g.kx) ldv += g.out_log_dxdy;
+    if (g.kz) ldv += log_dz[z];
+    out[i] += sign * ldv;
+  }
 }
 
 // numpy.max semantics: NaN if any element is NaN
@@ -415,7 +481,7 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
   if (g.kx) {
     dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
     k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
-                                            d_mx, d_sum, d_gmax, PB, nchunk);
+                                            pl->d_exp_tab, d_mx, d_sum, d_gmax, PB, nchunk);
     return 1;
   }
   const int G = reduce_groups(pl, g, nchunk);
@@ -423,18 +489,21 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
   double* ps = d_part + nout * G;
   dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
   k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
-                                          pm, ps, d_gmax, PB, nchunk);
+                                          pl->d_exp_tab, pm, ps, d_gmax, PB, nchunk);
   k_reduce_combine<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(pm, ps, nout, G, d_mx, d_sum);
   return 2;
 }
 
-void launch_reduce_logp(pkm_plan* pl, const double* logp, int64_t npix, const double* d_log_dv,
+void launch_reduce_logp(pkm_plan* pl, const double* logp, const ReduceSrc& src, const double* d_log_dv,
                         const double* d_log_lw, uint32_t keep_mask, int density, double* out,
                         cudaStream_t st) {
+  const int64_t npix = src.npix;
   ReduceGeom g;
-  g.nt = pl->d.nt; g.nv = pl->d.nv; g.nz = pl->d.nz; g.npix = npix;
+  g.nt = src.nt; g.nv = src.nv; g.nz = src.nz; g.npix = npix;
   g.kt = keep_mask & 1; g.kv = (keep_mask >> 1) & 1; g.kx = (keep_mask >> 2) & 1; g.kz = (keep_mask >> 3) & 1;
-  g.log_dxdy = std::log(pl->d.dx) + std::log(pl->d.dy);
+  g.wt = src.weighted ? 1 : 0;
+  g.log_dxdy = g.wt ? std::log(pl->d.dx) + std::log(pl->d.dy) : 0.0;
+  g.out_log_dxdy = std::log(pl->d.dx) + std::log(pl->d.dy);
   PKM_REQUIRE(g.nz <= 256, "nz=%d > 256 unsupported by the reduction kernel", g.nz);
   const long long ntot = (long long)g.nt * g.nv * npix * g.nz;
   long long nout = 1;
@@ -498,6 +567,34 @@ void launch_moments(const double* P, const double* values, int64_t nvar, int64_t
   if (ncond <= 0) return;
   k_moments<<<(unsigned)((ncond + 127) / 128), 128, 0, st>>>(P, values, nvar, ncond, out);
   PKM_CUDA(cudaGetLastError());
+}
+
+void launch_moments_logp(const double* log_joint, const double* log_given, const double* values,
+                         int64_t nouter, int64_t nvar, int64_t ninner, double* out, cudaStream_t st) {
+  const int64_t ncond = nouter * ninner;
+  if (ncond <= 0) return;
+  k_moments_logp<<<(unsigned)((ncond + 127) / 128), 128, 0, st>>>(log_joint, log_given, values, nouter, nvar,
+                                                                 ninner, out);
+  PKM_CUDA(cudaGetLastError());
+}
+
+// out (a marginal with the axes of keep_mask, extents taken from src) += sign * log dV
+void launch_apply_log_dv(pkm_plan* pl, double* out, const ReduceSrc& src, const double* d_log_dv,
+                         uint32_t keep_mask, double sign, cudaStream_t st) {
+  ReduceGeom g;
+  g.nt = src.nt; g.nv = src.nv; g.nz = src.nz; g.npix = src.npix;
+  g.kt = keep_mask & 1; g.kv = (keep_mask >> 1) & 1; g.kx = (keep_mask >> 2) & 1; g.kz = (keep_mask >> 3) & 1;
+  g.wt = 0; g.log_dxdy = 0.0;
+  g.out_log_dxdy = std::log(pl->d.dx) + std::log(pl->d.dy);
+  long long nout = 1;
+  if (g.kt) nout *= g.nt;
+  if (g.kv) nout *= g.nv;
+  if (g.kx) nout *= g.npix;
+  if (g.kz) nout *= g.nz;
+  const int grid = (int)std::min<long long>((nout + 255) / 256, (long long)pl->num_sms * 16);
+  k_apply_log_dv<<<grid, 256, 0, st>>>(out, nout, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, sign);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches += 1;
 }
 
 // d_result: 2 doubles of device scratch (value, then an int flag in the second slot)

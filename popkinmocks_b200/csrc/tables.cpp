@@ -177,20 +177,21 @@ void build_fold_tables(int nv, int v0_idx, double dv, const SplineTables& sp, Fo
   }
 }
 
-void build_wseg_tables(const SplineTables& sp, WsegTables& out) {
+void build_wseg_tables(const SplineTables& sp, int kt, WsegTables& out) {
   const int nfo = sp.nfo;
+  out.kt = kt;
   out.seg.clear();
   out.w.clear();
   int k = 0;
   while (k < nfo) {
     const int span = sp.tap_idx[k];
     int cnt = 1;
-    while (cnt < PKM_KT && k + cnt < nfo && sp.tap_idx[k + cnt] == span) ++cnt;
+    while (cnt < kt && k + cnt < nfo && sp.tap_idx[k + cnt] == span) ++cnt;
     out.seg.push_back(span);
     out.seg.push_back(k);
     out.seg.push_back(cnt);
     out.seg.push_back(0);
-    for (int r = 0; r < PKM_KT; ++r)
+    for (int r = 0; r < kt; ++r)
       for (int q = 0; q < 4; ++q) out.w.push_back(r < cnt ? sp.tap_w[size_t(k + r) * 4 + q] : 0.0);
     k += cnt;
   }

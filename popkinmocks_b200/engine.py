@@ -201,6 +201,121 @@ class Plan:
                                                None))
         return out
 
+    @staticmethod
+    def _mask(keep):
+        return sum(bit for ax, bit in zip("tvxz", (1, 2, 4, 8)) if ax in keep)
+
+    def _marginal_shape(self, keep, nx1, nx2):
+        shape = []
+        for ax in "tvxz":
+            if ax in keep:
+                shape += {"t": [self.nt], "v": [self.nv], "x": [nx1, nx2], "z": [self.nz]}[ax]
+        return tuple(shape)
+
+    def reduce_logp_multi(self, log_p_tvxz, log_dv, keeps, densities, light_weights=None):
+        """Several log-marginals in one call (pkm_reduce_logp_multi): nested requests are reduced
+        from each other, so e.g. keeps=("vx", "x") reads the 5-D array once.  Returns a list."""
+        on_dev = _is_cuda_tensor(log_p_tvxz)
+        if not on_dev:
+            log_p_tvxz = _lib.as_f64(log_p_tvxz)
+        nt, nv, nx1, nx2, nz = [int(s) for s in log_p_tvxz.shape]
+        n = len(keeps)
+        outs = []
+        for keep in keeps:
+            shape = self._marginal_shape(keep, nx1, nx2)
+            if on_dev:
+                import torch
+                outs.append(torch.empty(shape, dtype=torch.float64, device=log_p_tvxz.device))
+            else:
+                outs.append(np.empty(shape, dtype=np.float64))
+        masks = (C.c_uint32 * n)(*[self._mask(k) for k in keeps])
+        dens = (C.c_int32 * n)(*[int(bool(d)) for d in densities])
+        ptrs = (C.c_void_p * n)(*[_lib.ptr(o) for o in outs])
+        lw = None if light_weights is None else _lib.as_f64(light_weights)
+        ldv = _lib.as_f64(log_dv)
+        _lib.check(_lib.load().pkm_reduce_logp_multi(self._h, _lib.ptr(log_p_tvxz), nx1 * nx2, _lib.ptr(ldv),
+                                                     _lib.ptr(lw), n, masks, dens, ptrs, None))
+        return outs
+
+    def reduce_logp_from(self, src, src_keep, npix, log_dv, keep, density, light_weights=None):
+        """A log-marginal reduced from the device-resident log-PROBABILITY marginal `src` over the
+        axes `src_keep` (pkm_reduce_logp_from); `light_weights` re-weights a mass-weighted source
+        that keeps t and z.  Returns a CUDA tensor with the axes of `keep`."""
+        import torch
+        dims = {"t": [self.nt], "v": [self.nv], "z": [self.nz]}
+        xshape = None
+        if "x" in src_keep:
+            xi = src_keep.index("x")
+            xshape = list(src.shape[xi:xi + 2])
+        shape = []
+        for ax in "tvxz":
+            if ax in keep:
+                shape += xshape if ax == "x" else dims[ax]
+        out = torch.empty(tuple(shape), dtype=torch.float64, device=src.device)
+        lw = None if light_weights is None else _lib.as_f64(light_weights)
+        ldv = _lib.as_f64(log_dv)
+        _lib.check(_lib.load().pkm_reduce_logp_from(self._h, _lib.ptr(src.contiguous()), self._mask(src_keep),
+                                                    int(npix), _lib.ptr(ldv), _lib.ptr(lw), self._mask(keep),
+                                                    int(bool(density)), _lib.ptr(out), None))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# host buffers: page-locked in place on first use, released when the array is garbage collected
+# ----------------------------------------------------------------------------------------------
+_PINNED = {}
+
+
+def pin_host_array(arr):
+    """Page-lock a C-contiguous NumPy array in place (pkm_host_register) so that the library's
+    pipelined staging and `to_device` read it at PCIe rate.  Idempotent; the registration is
+    undone when the array is collected.  Returns True if the array is (now) pinned."""
+    if not isinstance(arr, np.ndarray) or not arr.flags.c_contiguous or arr.nbytes < (1 << 20):
+        return False
+    addr = arr.ctypes.data
+    if addr in _PINNED:
+        return True
+    base = arr
+    while isinstance(base.base, np.ndarray):
+        base = base.base
+    try:
+        _lib.check(_lib.load().pkm_host_register(C.c_void_p(addr), int(arr.nbytes)))
+    except _lib.PkmError:
+        return False                         # e.g. read-only mapping: the pageable path still works
+    _PINNED[addr] = True
+
+    def _release(a=addr):
+        if _PINNED.pop(a, None):
+            try:
+                _lib.load().pkm_host_unregister(C.c_void_p(a))
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+    import weakref
+    try:
+        weakref.finalize(base, _release)
+    except TypeError:
+        pass
+    return True
+
+
+def to_device(arr, device=0):
+    """float64 CUDA tensor copy of a host array: the source is page-locked in place and copied by
+    one asynchronous DMA (no pageable staging of the whole array)."""
+    import torch
+    host = np.ascontiguousarray(arr, dtype=np.float64)
+    pin_host_array(host)
+    out = torch.empty(host.shape, dtype=torch.float64, device=f"cuda:{device}")
+    out.copy_(torch.from_numpy(host), non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    return out
+
+
+def pinned_empty(shape):
+    """(tensor, ndarray view) of a page-locked float64 host buffer from torch's caching allocator."""
+    import torch
+    t = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+    return t, t.numpy()
+
 
 def get_plan(cube, device=0, precision="float64"):
     """The cube's plan for (`device`, `precision`), created on first use.
@@ -264,6 +379,22 @@ def moments(P, values, device=0):
     _lib.check(_lib.load().pkm_moments(_lib.ptr(P), _lib.ptr(values), nvar, ncond, _lib.ptr(out),
                                        int(device), None))
     return out
+
+
+def moments_logp(log_joint, log_given, values, nouter, nvar, ninner):
+    """Mean and central moments 2..4 of P = exp(log_joint - log_given) along the middle axis of
+    log_joint [nouter, nvar, ninner] (CUDA tensors; pkm_moments_logp).  Returns a NumPy array
+    [4, nouter * ninner]."""
+    import torch
+    _lib.require_gpu()
+    dev = log_joint.device
+    vals = torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64), device=dev)
+    out = torch.empty((4, int(nouter) * int(ninner)), dtype=torch.float64, device=dev)
+    lg = None if log_given is None else log_given.contiguous()
+    _lib.check(_lib.load().pkm_moments_logp(_lib.ptr(log_joint.contiguous()), _lib.ptr(lg), _lib.ptr(vals),
+                                            int(nouter), int(nvar), int(ninner), _lib.ptr(out),
+                                            int(dev.index or 0), None))
+    return out.cpu().numpy()
 
 
 def noise(ybar, snr, mode, seed=0, offset=0, ybar_max=-1.0, want_sigma=True, want_sample=True,

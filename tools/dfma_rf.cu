@@ -44,7 +44,16 @@ void run(int warps, int ctas) {
   cudaFree(out);
 }
 int main() {
-  run<1>(4, 3); run<2>(4, 3); run<3>(4, 3); run<4>(4, 3);
-  run<1>(8, 4); run<2>(8, 4); run<3>(8, 4); run<4>(8, 4); run<5>(4, 3); run<6>(4, 3); run<5>(8, 4); run<6>(8, 4); run<5>(1, 1); run<3>(1, 1); run<7>(4, 3); run<8>(4, 3); run<7>(1, 12); run<8>(1, 12);
+  // warps per SM sweep: (warps per CTA, CTAs per SM)
+  printf("-- 4 warps/SM (1 per scheduler)\n");
+  run<1>(4, 1); run<2>(4, 1); run<3>(4, 1); run<6>(4, 1); run<5>(4, 1);
+  printf("-- 8 warps/SM\n");
+  run<1>(4, 2); run<2>(4, 2); run<3>(4, 2); run<6>(4, 2); run<5>(4, 2);
+  printf("-- 12 warps/SM\n");
+  run<1>(4, 3); run<2>(4, 3); run<3>(4, 3); run<4>(4, 3); run<6>(4, 3); run<5>(4, 3); run<7>(4, 3); run<8>(4, 3);
+  printf("-- 16 warps/SM\n");
+  run<1>(4, 4); run<2>(4, 4); run<3>(4, 4); run<6>(4, 4); run<5>(4, 4);
+  printf("-- 32 warps/SM\n");
+  run<1>(8, 4); run<2>(8, 4); run<3>(8, 4); run<6>(8, 4); run<5>(8, 4);
   return 0;
 }
