@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C4", choices=["C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configuration (SURVEY.md 8d): C4 = the headline 201x201 synthetic cube "
+                         "(default, the driver's bench line); C2 GrowingDisk 51x51 (path A), C3 Mixture 101x101 + "
+                         "marginals + moments, C5 evaluate_ybar + ShotNoise 101x101 (bench_workloads.py)")
     ap.add_argument("--nx", type=int, default=201, help="pixels per side of one cube")
     ap.add_argument("--nv", type=int, default=101)
     ap.add_argument("--lmd", type=float, nargs=2, default=(4700.0, 6500.0))
@@ -73,14 +77,15 @@ def parse_args():
 # ----------------------------------------------------------------------------------------------
 # workload description shared by both arms
 # ----------------------------------------------------------------------------------------------
-def build_cube(args, nx1=None):
+def build_cube(args, nx1=None, nx2=None):
     import popkinmocks_b200 as pkm
     ssps = pkm.milesSSPs(lmd_min=args.lmd[0], lmd_max=args.lmd[1])
-    # x1 extent scales with the number of rows so dx (and the result per pixel) is unchanged
+    # the spatial extents scale with the pixel counts so dx, dy (and the result per pixel) are unchanged
     nx1 = nx1 or args.nx
-    return pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx1, nx2=args.nx, nv=args.nv,
+    nx2 = nx2 or args.nx
+    return pkm.ifu_cube.IFUCube(ssps=ssps, nx1=nx1, nx2=nx2, nv=args.nv,
                                 x1rng=(-1.0 * nx1 / args.nx, 1.0 * nx1 / args.nx),
-                                x2rng=(-1.0, 1.0), vrng=(-1000.0, 1000.0))
+                                x2rng=(-1.0 * nx2 / args.nx, 1.0 * nx2 / args.nx), vrng=(-1000.0, 1000.0))
 
 
 def workload_config(args, cube):
@@ -117,6 +122,20 @@ def _cpu_task(seed):
     return time.perf_counter() - t0, float(y.sum())
 
 
+def _cpu_task_gaussian(seed):
+    """One tile of `px` pixels through the oracle's path A (parametric.py:355-373)."""
+    from oracle import restatement as R
+    c = _CPU
+    rng = np.random.default_rng(seed)
+    P = rng.random((c["nt"], 1, c["px"], c["nz"]))
+    P /= P.sum()
+    mu = 400.0 * (rng.random((c["nt"], 1, c["px"])) - 0.5)
+    sg = 20.0 + 200.0 * rng.random((c["nt"], 1, c["px"]))
+    t0 = time.perf_counter()
+    y = R.ybar_gaussian(P, mu, sg, c["FXw"], c["par_dims"], c["n_fft"], c["dv"])
+    return time.perf_counter() - t0, float(y.sum())
+
+
 def cpu_consts(cube, px):
     s = cube.ssps
     nz, nt = s.par_dims
@@ -137,8 +156,9 @@ def cpu_procs(args):
 class CpuArm:
     """A fork pool of host workers, created BEFORE CUDA is initialised in this process."""
 
-    def __init__(self, args, cube):
+    def __init__(self, args, cube, task=None):
         import multiprocessing as mp
+        self.task = task or _cpu_task
         self.nproc = cpu_procs(args)
         self.px = args.cpu_px
         self.n_fft = cube.ssps.n_fft
@@ -151,7 +171,7 @@ class CpuArm:
         seeds = list(range(self.seed, self.seed + self.nproc))
         self.seed += self.nproc
         t0 = time.perf_counter()
-        self.pool.map(_cpu_task, seeds, chunksize=1)
+        self.pool.map(self.task, seeds, chunksize=1)
         dt = time.perf_counter() - t0
         return dt, self.nproc * self.px * self.n_fft
 
@@ -426,6 +446,10 @@ def run_b200(args):
     verify = None
     if rank == 0 and not args.no_verify:
         verify = verify_cube(out.reshape(n_fft, total_pix), cube, synth, total_pix)
+    spot_px, spot_ref = [], None
+    if rank == 0 and verify is not None:         # kept for the class-API leg below (`out` is reused)
+        spot_px = [p for p in verify["pixel_index"] if r0 <= p < r1][:4]
+        spot_ref = out.reshape(n_fft, total_pix)[:, spot_px].cpu().numpy()
     if world > 1:
         bad = torch.tensor([1.0 if (verify and not verify["ok"]) else 0.0], device=dev)
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
@@ -511,18 +535,27 @@ def run_b200(args):
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": f"skipped: pinned host buffers of all ranks ({host_bytes / 1e9:.0f} GB) exceed 60% of host RAM"}
     elif not args.no_e2e:
+        # the call a user of the reference makes: Component(cube, log_p_tvxz).evaluate_ybar() on a
+        # HOST array (page-locked in place by the class on first use), result = a host NumPy cube
+        import popkinmocks_b200 as pkm
         h_in = torch.empty(logp.shape, dtype=torch.float64, pin_memory=True)
         h_in.copy_(logp)
-        h_out = torch.empty((n_fft, rows, nxl), dtype=torch.float64, pin_memory=True)
-        np_in, np_out = h_in.numpy(), h_out.numpy()
+        np_in = h_in.numpy()
         del logp
         torch.cuda.empty_cache()
+        cube_e2e = cube if world == 1 else build_cube(args, nx1=rows, nx2=nxl)
+        cmp = pkm.components.Component(cube=cube_e2e, log_p_tvxz=np_in)
 
         def step_e2e():
-            plan.ybar_density(np_in, is_log=True, out=np_out)
+            cmp.evaluate_ybar(device=local)
 
         step_e2e()
         barrier()
+        e2e_err = None
+        if spot_ref is not None and spot_px:
+            # the class-API cube must be the cube verified above (rank 0's pixel range of it)
+            got = cmp.ybar.reshape(n_fft, -1)[:, [p - r0 for p in spot_px]]
+            e2e_err = float(np.max(np.abs(got - spot_ref)) / np.max(np.abs(spot_ref)))
         w2 = sampler.mark() if sampler else 0
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -536,10 +569,13 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": voxels_per_step * args.e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
+               "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(cmp.ybar.size * 8),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "note": "per rank: pinned host log_p_tvxz -> pkm_ybar_density -> pinned host cube; "
-                       "multi-GPU ranks leave their row blocks on their own host buffers"}
+               "api": "popkinmocks_b200.components.Component(cube, log_p_tvxz).evaluate_ybar()",
+               "max_rel_diff_vs_device_cube": e2e_err,
+               "note": "per rank: host log_p_tvxz (page-locked in place) -> Component.evaluate_ybar -> host "
+                       "NumPy cube; H2D of tile i+1, kernels of tile i and D2H of tile i-1 overlap inside "
+                       "pkm_ybar_density; multi-GPU ranks leave their pixel ranges on their own host buffers"}
 
     clocks = sampler.stop(windows) if sampler else None
 
@@ -656,9 +692,79 @@ def ncu_traffic(kernel, npix):
     return None
 
 
+def run_config(args):
+    """--config C2|C3|C5: the other BASELINE.json configurations through bench_workloads.py, reported
+    with the same JSON contract.  N > 1 runs one independent replica per GPU (these configurations
+    fit one GPU; the sharded multi-GPU path is the C4 line)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import bench_workloads as W
+    nx = {"C2": 51, "C3": 101, "C5": 101}[args.config] if args.nx == 201 else args.nx
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cube = W.make_cube(nx, args.nv)
+        if args.config == "C2":
+            arm = CpuArm(args, cube, task=_cpu_task_gaussian)
+            kind = ("oracle/restatement.py ybar_gaussian (parametric.py:355-373) on random maps of the same shape")
+        else:
+            arm = CpuArm(args, cube)
+            kind = ("oracle/restatement.py ybar_density_literal (base.py:836-859) on random densities of the same "
+                    "shape - the cube evaluation, which dominates the reference's time for this configuration")
+        arm.step()
+        tot_s, tot_v = 0.0, 0
+        while tot_s < 6.0:
+            sec, vox = arm.step()
+            tot_s += sec
+            tot_v += vox
+        arm.close()
+        cpu = {"value": tot_v / tot_s, "unit": UNIT, "cores": arm.nproc, "kind": "port",
+               "sample": f"{tot_v // cube.ssps.n_fft} pixels in {tot_s:.1f} s wall, {arm.nproc} workers: {kind}"}
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid).replace("GPU-", "")
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    w0 = sampler.mark() if sampler else 0
+    if world > 1:
+        dist.barrier()
+    r = W.RUNNERS[args.config](nx=nx, nv=args.nv, steps=args.steps, warmup=max(args.warmup, 3), device=local,
+                               e2e_steps=args.e2e_steps)
+    w1 = sampler.mark() if sampler else 0
+    ms, e2e_ms, ok = r["ms_per_step"], r["e2e"]["ms_per_step"], 1.0 if r["verify"]["ok"] else 0.0
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, -ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, ok = float(t[0]), float(t[1]), -float(t[2])
+    clocks = sampler.stop([(w0, w1)]) if sampler else None
+    if rank == 0:
+        cfg = dict(r["config"])
+        cfg["workload"] = r["workload"]
+        e2e = dict(r["e2e"])
+        e2e.update({"value": world * r["voxels"] / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms})
+        line = {"metric": METRIC, "value": world * r["voxels"] / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg, "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": r["roofline"],
+                "verify": r["verify"], "kernels": r["kernels"], "other_paths": r["other_paths"],
+                "cpu_baseline": cpu, "clocks": clocks,
+                "replicas": ("one independent replica per GPU" if world > 1 else None)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if ok < 0.5:
+        raise SystemExit(f"bench.py --config {args.config}: verification against the oracle failed")
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config != "C4":
+        run_config(a)
     else:
         run_b200(a)

@@ -613,16 +613,14 @@ extern "C" int32_t pkm_ybar_gaussian(pkm_plan* pl, const double* P_txz, const do
     const int64_t npix = (int64_t)(row_end - row_begin) * nx2;
     if (npix == 0) return;
 
-    // omega is tiny: stage it through the stream (ordered with earlier kernels using it)
-    PKM_CUDA(cudaMemcpyAsync(pl->d_omega, omega, sizeof(double) * pl->nfo, cudaMemcpyDefault, st));
-    PKM_CUDA(cudaStreamSynchronize(st));  // omega may be a pageable temporary of the caller
-    double omega_step4 = 0.0;             // frequency stride of one lane of the kernel: omega[4] - omega[0]
-    {
-      double o[5] = {0, 0, 0, 0, 0};
-      const int cnt = std::min(pl->nfo, 5);
-      PKM_CUDA(cudaMemcpy(o, pl->d_omega, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
-      omega_step4 = cnt >= 2 ? 4.0 * (o[1] - o[0]) : 0.0;
+    // omega is a plan constant in practice (linspace(0, pi, nfo)/dv): it is uploaded when it first
+    // appears or changes, from a plan-owned copy, without blocking the stream or the host
+    if (pl->h_omega.size() != (size_t)pl->nfo || memcmp(pl->h_omega.data(), omega, sizeof(double) * pl->nfo) != 0) {
+      pl->h_omega.assign(omega, omega + pl->nfo);
+      PKM_CUDA(cudaMemcpyAsync(pl->d_omega, pl->h_omega.data(), sizeof(double) * pl->nfo, cudaMemcpyHostToDevice, st));
     }
+    // frequency stride of one lane of the kernel: omega[4] - omega[0]
+    const double omega_step4 = pl->nfo >= 2 ? 4.0 * (omega[1] - omega[0]) : 0.0;
 
     size_t per_px = sizeof(double2) * pl->nfo + sizeof(double) * n;
     if (in_host) per_px += sizeof(double) * (size_t)nt * (nz + 2);

@@ -379,3 +379,94 @@ def test_mixture_pixelation_matches_reference(galaxy, base_component):
     assert rel_err(twin.ybar, base_component.ybar) < 1e-12
     for dist in ("tz", "v_x"):
         assert rel_err(twin.get_p(dist), np.exp(g[f"b_logp|{dist}|0|1"])) < TOL
+
+
+# ----------------------------------------------------------------------------- part 3: this round
+def test_multi_output_reduction_and_derivation_from_cached_marginals(gpu_ok):
+    """pkm_reduce_logp_multi / pkm_reduce_logp_from: nested requests are reduced from each other;
+    every result must agree with the single-output pass over the 5-D array (and so with the
+    reference goldens the single-output pass is pinned to)."""
+    import torch
+    from popkinmocks_b200 import engine
+    name = "g2_rebin_nv21_prime"
+    g = load_golden(name)
+    cube = golden_cube(name)
+    plan = engine.get_plan(cube)
+    logp = torch.from_numpy(g["b_log_p_tvxz"]).cuda()
+    log_dv = np.log(np.diff(cube.v_edg))
+    keeps = ("vx", "txz", "x", "v", "tz", "z", "t", "tvxz")
+    for lw in (None, cube.ssps.light_weights):
+        dens = [i % 2 == 0 for i in range(len(keeps))]
+        outs = plan.reduce_logp_multi(logp, log_dv, keeps, dens, light_weights=lw)
+        for keep, d, out in zip(keeps, dens, outs):
+            ref = plan.reduce_logp(logp, log_dv, keep, d, light_weights=lw).cpu().numpy()
+            got = out.cpu().numpy()
+            assert got.shape == ref.shape, keep
+            assert np.array_equal(np.isneginf(got), np.isneginf(ref)), keep
+            ok = np.isfinite(ref)
+            assert np.allclose(got[ok], ref[ok], rtol=0, atol=1e-12), (keep, lw is not None)
+    # light-weighted marginals without v follow from the MASS-weighted p(t,x,z)
+    txz = plan.reduce_logp(logp, log_dv, "txz", False)
+    npix = cube.nx * cube.ny
+    for keep in ("tz", "x", "xz", "t"):
+        got = plan.reduce_logp_from(txz, "txz", npix, log_dv, keep, True, light_weights=cube.ssps.light_weights)
+        ref = plan.reduce_logp(logp, log_dv, keep, True, light_weights=cube.ssps.light_weights)
+        ok = torch.isfinite(ref)
+        assert torch.allclose(got[ok], ref[ok], rtol=0, atol=1e-12), keep
+    # host arrays go through the same entry point
+    outs = plan.reduce_logp_multi(g["b_log_p_tvxz"], log_dv, ("vx", "x"), (False, False))
+    assert isinstance(outs[0], np.ndarray)
+    assert np.allclose(outs[1], plan.reduce_logp(logp, log_dv, "x", False).cpu().numpy(), rtol=0, atol=1e-12)
+
+
+def test_marginal_cache_is_dropped_with_the_array(gpu_ok):
+    name = "g2_rebin_nv21_prime"
+    g = load_golden(name)
+    comp = pkm.components.Component(cube=golden_cube(name), log_p_tvxz=g["b_log_p_tvxz"].copy())
+    p1 = comp.get_p("v_x", density=False)
+    s1 = comp.get_skewness("v_x")
+    assert ("vx", False, 0) in comp.__dict__["_pkm_marg"] and ("x", False, 0) in comp.__dict__["_pkm_marg"]
+    shifted = g["b_log_p_tvxz"].copy()
+    shifted[:, :5] = -np.inf                     # remove the five lowest velocity bins
+    comp.log_p_tvxz = shifted                    # rebinding drops the device copy and every cache
+    assert "_pkm_marg" not in comp.__dict__ and "_pkm_mom" not in comp.__dict__
+    p2 = comp.get_p("v_x", density=False)
+    assert np.all(p2[:5] == 0.0) and not np.allclose(p1, p2, equal_nan=True)
+    comp.log_p_tvxz[:, 5:8] = -np.inf            # in-place edit: needs an explicit invalidation
+    comp.invalidate_cache()
+    p3 = comp.get_p("v_x", density=False)
+    assert np.all(p3[:8] == 0.0)
+    with np.errstate(invalid="ignore"):
+        assert not np.allclose(comp.get_skewness("v_x"), s1, equal_nan=True)
+
+
+def test_nan_and_empty_densities_through_both_coefficient_kernels(gpu_ok, monkeypatch):
+    """-inf log densities are exact zeros and a NaN poisons its own pixel only (np.exp semantics);
+    the TMA/tensor-core coefficient kernel and the staged fallback agree."""
+    from popkinmocks_b200 import engine
+    name = "g3_full_nv101_odd"
+    g = load_golden(name)
+    cube = build_cube(name)
+    logp = np.repeat(g["wn_log_p_tvxz"], 20, axis=3)           # 1 x 40 pixels
+    cube = pkm.ifu_cube.IFUCube(ssps=cube.ssps, nx1=1, nx2=40, nv=cube.nv, vrng=(-1000.0, 1000.0))
+    logp[:, :, 0, 3, :] = -np.inf                              # an empty pixel
+    logp[7, 50, 0, 11, 2] = np.nan
+    logp[:, 10:20, 0, 17, :] = -np.inf
+    res = {}
+    for kern in ("1", "0"):
+        monkeypatch.setenv("PKM_COEFF_KERNEL", kern)
+        plan = engine.Plan(cube)
+        res[kern] = plan.ybar_density(logp, is_log=True)
+        plan.close()
+    for y in res.values():
+        assert np.all(y[:, 0, 3] == 0.0)
+        assert np.all(np.isnan(y[:, 0, 11]))
+        assert np.isfinite(np.delete(y, 11, axis=2)).all()
+    ok = np.delete(np.arange(40), 11)
+    assert rel_err(res["1"][:, :, ok], res["0"][:, :, ok]) < 1e-13
+    from oracle import restatement as R
+    s = cube.ssps
+    with np.errstate(invalid="ignore"):
+        ref = R.ybar_density_literal(np.exp(logp[:, :, :, 16:19]), cube.v_edg, s.FXw, s.par_dims, s.n_fft, s.dv,
+                                     s.delta_t, s.delta_z, cube.dx, cube.dy)
+    assert rel_err(res["1"][:, :, 16:19], ref) < TOL
