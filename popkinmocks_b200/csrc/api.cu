@@ -782,6 +782,7 @@ int64_t marginal_size(const pkm_plan* pl, int64_t npix, uint32_t mask) {
 struct ReduceConsts {
   const double* log_dv;
   const double* log_lw;
+  int uniform_dv;
 };
 ReduceConsts upload_reduce_consts(pkm_plan* pl, const double* log_dv, const double* light_weights,
                                   cudaStream_t st) {
@@ -793,7 +794,12 @@ ReduceConsts upload_reduce_consts(pkm_plan* pl, const double* log_dv, const doub
   pl->small.reserve(sizeof(double) * h.size());
   PKM_CUDA(cudaMemcpyAsync(pl->small.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
   PKM_CUDA(cudaStreamSynchronize(st));   // h is a local
-  return ReduceConsts{pl->small.as<double>(), light_weights ? pl->small.as<double>() + nv : nullptr};
+  // equal bins up to the rounding of diff(v_edg) (a few ulp): the reductions then fold log dv into a
+  // per-thread constant instead of adding it to every element (differences <= 1e-15 in log p)
+  int uniform = 1;
+  for (int v = 1; v < nv; ++v)
+    uniform = uniform && std::fabs(log_dv[v] - log_dv[0]) <= 1e-14 * (std::fabs(log_dv[0]) + 1.0);
+  return ReduceConsts{pl->small.as<double>(), light_weights ? pl->small.as<double>() + nv : nullptr, uniform};
 }
 
 // src (device): the 5-D log density (src_mask = 0xF, weighted) or a log-probability marginal holding
@@ -808,6 +814,7 @@ void reduce_device(pkm_plan* pl, const double* src, uint32_t src_mask, bool src_
   rs.npix = (src_mask & 4) ? npix : 1;
   rs.nz = (src_mask & 8) ? pl->d.nz : 1;
   rs.weighted = src_is_density ? 1 : 0;
+  rs.uniform_dv = c.uniform_dv;
   if (light) PKM_REQUIRE((src_mask & 9) == 9, "light weighting needs a source that keeps t and z");
   if (keep_mask == src_mask && !src_is_density && !light) {
     // nothing to reduce: copy, then convert to a density if asked

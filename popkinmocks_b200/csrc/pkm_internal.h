@@ -196,6 +196,7 @@ struct ReduceSrc {
   int nt, nv, nz;
   int64_t npix;
   int weighted;
+  int uniform_dv = 0;   // all velocity bins have the same width (log dv folded into the per-thread constant)
 };
 void launch_reduce_logp(pkm_plan* pl, const double* logp, const ReduceSrc& src, const double* d_log_dv,
                         const double* d_log_lw, uint32_t keep_mask, int density, double* out,

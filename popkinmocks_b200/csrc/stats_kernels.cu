@@ -54,177 +54,278 @@ __device__ __forceinline__ Lse lse_merge(Lse a, Lse b) {
   return Lse{M, a.s * exp(a.m - M) + b.s * exp(b.m - M)};
 }
 
+// exp(x) for -708 <= x <= 0 (or NaN) with the shared 256-entry table (exp_tab.cuh), WITHOUT a range
+// test: the caller skips the term when x < -708.  NaN propagates through the polynomial and the
+// exponent patch (the low word of a NaN `t` is 0).  9 FP64 + 6 integer instructions.
+__device__ __forceinline__ double exp_core_tab(double x, const double* __restrict__ tab) {
+  const double t = fma(x, 369.32993046757463228, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double fk = t - 6755399441055744.0;
+  double r = fma(fk, -2.70760617331688990816e-03, x);
+  r = fma(fk, -7.45396456746323320321e-13, r);
+  double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  const double p = fma(r * r, q, r);
+  const double T = tab[k & (PKM_EXP_TAB - 1)];
+  const double v = fma(T, p, T);
+  return __hiloint2double(__double2hiint(v) + ((k >> 8) << 20), __double2loint(v));
+}
+__device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict__ tab) {
+  return x < -708.0 ? 0.0 : exp_core_tab(x, tab);
+}
+
 // ONE streaming pass over the 5-D array ("online" log-sum-exp).
-// CTA = one kept (t, v) index (or the full range of a dropped axis) x pixel chunks of PB whole
-// pixels; thread = one (pixel-in-chunk, z) element, contiguous in memory for fixed (t, v).
+// Thread = one (pixel-in-chunk, z) element of a chunk of PB whole pixels, contiguous in memory for
+// fixed (t, v).  CTA = (chunk or chunk group, kept t, block of VPC kept v's); for every kept v of
+// its block the CTA runs the reduction over the dropped axes and stores one result, so the
+// per-CTA set-up (tables, barriers) is shared by VPC outputs.
 // x kept:    gridDim.x = number of chunks, every output cell has exactly one owner -> the pair is
 //            stored straight into (mx, out).
 // x dropped: gridDim.x = G chunk groups, CTA c walks chunks c, c+G, ...; the per-CTA pairs go to
 //            (mx, out)[o * G + c] and k_reduce_combine folds the G partials of every output.
-// Elements are consumed in batches of U: one maximum, then U+1 independent exps - the exp work
-// (not HBM) bounds this kernel, so nothing in the batch may sit on a dependent chain.
+// Elements are consumed in batches of U (one maximum, then U+1 independent table exponentials) with
+// TWO batches of loads in flight.  The kernel was bound by instruction issue (65 instructions per
+// element, ncu profiles/r2_*): full batches take an unpredicated path with pointer increments,
+// equal velocity bins are folded into the per-(t,z) constant, the exponential has one range test.
 constexpr int RED_U = 8;
-__global__ void __launch_bounds__(256)
+constexpr int RED_VPC = 16;    // kept velocity bins per CTA
+#ifndef PKM_RED_MINB
+#define PKM_RED_MINB 4
+#endif
+__global__ void __launch_bounds__(256, PKM_RED_MINB)
 k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
                 const double* __restrict__ log_dv, const double* __restrict__ log_dz,
                 const double* __restrict__ log_lw, const double* __restrict__ exp2_tab,
                 double* __restrict__ mx, double* __restrict__ out, double* __restrict__ gmax, int PB,
-                long long nchunk) {
-  extern __shared__ double s_tab[];          // this CTA's log_dt [t0,t1) | log_dv [v0,v1) | log_lw rows
+                long long nchunk, int uniform_dv) {
+  extern __shared__ double s_tab[];          // log_dt [nt] | log_dv [nv] | log_lw [nt][nz]
   __shared__ double red_m[256], red_s[256];
-  __shared__ double s_exp[PKM_EXP_TAB];      // 2^(j/256) for exp_tab()
+  __shared__ double s_exp[PKM_EXP_TAB];      // 2^(j/256) for exp_neg_tab()
   const int tid = threadIdx.x;
-  int t0 = 0, t1 = g.nt, v0 = 0, v1 = g.nv;
-  if (g.kt) { t0 = blockIdx.y; t1 = t0 + 1; }
-  if (g.kv) { v0 = blockIdx.z; v1 = v0 + 1; }
+  const int nz_ = g.nz;
   double* s_dt = s_tab;
-  double* s_dv = s_tab + (t1 - t0);
-  double* s_lw = s_dv + (v1 - v0);
-  for (int i = tid; i < t1 - t0; i += blockDim.x) s_dt[i] = g.wt ? log_dt[t0 + i] : 0.0;
-  for (int i = tid; i < v1 - v0; i += blockDim.x) s_dv[i] = g.wt ? log_dv[v0 + i] : 0.0;
-  if (log_lw) for (int i = tid; i < (t1 - t0) * g.nz; i += blockDim.x) s_lw[i] = log_lw[t0 * g.nz + i];
+  double* s_dv = s_tab + g.nt;
+  double* s_lw = s_dv + g.nv;
+  // with equal velocity bins log dv is part of the per-thread constant, not of every element
+  const double dv_all = (g.wt && uniform_dv) ? log_dv[0] : 0.0;
+  for (int i = tid; i < g.nt; i += blockDim.x) s_dt[i] = g.wt ? log_dt[i] : 0.0;
+  for (int i = tid; i < g.nv; i += blockDim.x) s_dv[i] = (g.wt && !uniform_dv) ? log_dv[i] : 0.0;
+  if (log_lw) for (int i = tid; i < g.nt * nz_; i += blockDim.x) s_lw[i] = log_lw[i];
   for (int i = tid; i < PKM_EXP_TAB; i += blockDim.x) s_exp[i] = exp2_tab[i];
   __syncthreads();
 
-  const int nact = PB * g.nz;
-  const int xl = tid / g.nz, z = tid - xl * g.nz;
+  const int nact = PB * nz_;
+  const int xl = tid / nz_, z = tid - xl * nz_;
   const long long G = gridDim.x;
-  const long long row = g.npix * g.nz;       // elements per (t, v)
+  const long long row = g.npix * nz_;        // elements per (t, v)
+  const bool active = tid < nact;
+  int t0 = 0, t1 = g.nt;
+  if (g.kt) { t0 = blockIdx.y; t1 = t0 + 1; }
+  const int vblk0 = g.kv ? blockIdx.z * RED_VPC : 0;
+  const int vblk1 = g.kv ? min(g.nv, vblk0 + RED_VPC) : 1;
+  const double cz = (g.wt ? log_dz[min(z, nz_ - 1)] : 0.0) + g.log_dxdy + dv_all;
+  const long long cstep = g.kx ? nchunk : G;            // x kept: exactly one chunk per CTA
+  const long long part = g.kx ? 1 : G, pidx = g.kx ? 0 : blockIdx.x;
+  const bool per_v = !uniform_dv && g.wt;               // per-element log dv
 
-  Lse acc{-INFINITY, 0.0};
-  // consume a batch: one maximum, then RED_U + 1 independent exps
-  // (table exp, exp_tab.cuh: 9 FP64 instructions instead of the library's ~26 - the exponentials,
-  // not HBM, bound this kernel.  fmax ignores NaN, exp_tab propagates it: a NaN element makes the
-  // sum NaN, as scipy's logsumexp does; a batch holding only -inf / NaN is checked separately)
-  auto flush = [&acc](const double (&a)[RED_U]) {
-    double bm = a[0];
-#pragma unroll
-    for (int k = 1; k < RED_U; ++k) bm = fmax(bm, a[k]);
-    if (bm > -INFINITY) {
-      const double M = fmax(acc.m, bm);
-      double sum = acc.s * exp_tab(acc.m - M, s_exp);
-#pragma unroll
-      for (int k = 0; k < RED_U; ++k) sum += exp_tab(a[k] - M, s_exp);
-      acc.m = M;
-      acc.s = sum;
-    } else {
-      bool nan = false;
-#pragma unroll
-      for (int k = 0; k < RED_U; ++k) nan = nan || a[k] != a[k];
-      if (nan) acc.s = NAN;
-    }
-  };
-  if (tid < nact) {
-    const double cz = (g.wt ? log_dz[z] : 0.0) + g.log_dxdy;
+  for (int vo = vblk0; vo < vblk1; ++vo) {
+    int v0 = 0, v1 = g.nv;
+    if (g.kv) { v0 = vo; v1 = vo + 1; }
     const int nT = t1 - t0, nV = v1 - v0;
-    const long long cstep = g.kx ? nchunk : G;          // x kept: exactly one chunk per CTA
-    if (nV > 1) {
-      // batches along v (stride = one (t,v) row)
-      for (long long chunk = blockIdx.x; chunk < nchunk; chunk += cstep) {
-        if (chunk * PB + xl >= g.npix) continue;
-        for (int t = t0; t < t1; ++t) {
-          const double ct = cz + s_dt[t - t0] + (log_lw ? s_lw[(t - t0) * g.nz + z] : 0.0);
-          const double* p = logp + ((long long)t * g.nv + v0) * row + chunk * nact + tid;
-          for (int vb = 0; vb < nV; vb += RED_U) {
-            double a[RED_U];
+    Lse acc{-INFINITY, 0.0};
+    // Consume a batch.  The running maximum M only ever grows, so the common case is "no element
+    // exceeds M": one compare per element (no selects), then RED_U independent table exponentials
+    // of a - M <= 0, each added unless it underflows (a predicated add instead of a select).  A
+    // batch that raises M takes the slow path once (rescale the sum).  NaN compares false, passes
+    // the underflow test and poisons the sum - scipy's logsumexp gives NaN as well.
+    auto flush = [&acc](const double (&a)[RED_U], const double* tab) {
+      bool grow = false;
 #pragma unroll
-            for (int k = 0; k < RED_U; ++k) {
-              const bool ok = vb + k < nV;
-              const double ld = ok ? __ldg(p + (long long)(vb + k) * row) : -INFINITY;
-              a[k] = ld + ct + s_dv[ok ? vb + k : 0];
-            }
-            flush(a);
-          }
-        }
-      }
-    } else if (nT > 1) {
-      // v kept, t summed: batches along t (stride = nv rows)
-      const double cv = s_dv[0];
-      for (long long chunk = blockIdx.x; chunk < nchunk; chunk += cstep) {
-        if (chunk * PB + xl >= g.npix) continue;
-        const double* p = logp + (long long)v0 * row + chunk * nact + tid;
-        for (int tb = 0; tb < nT; tb += RED_U) {
-          double a[RED_U];
+      for (int k = 0; k < RED_U; ++k) grow = grow || a[k] > acc.m;
+      if (grow) {
+        double bm = a[0];
 #pragma unroll
-          for (int k = 0; k < RED_U; ++k) {
-            const bool ok = tb + k < nT;
-            const int tt = ok ? tb + k : 0;
-            const double ld = ok ? __ldg(p + (long long)tt * g.nv * row) : -INFINITY;
-            a[k] = ld + (cz + s_dt[tt] + (log_lw ? s_lw[tt * g.nz + z] : 0.0)) + cv;
-          }
-          flush(a);
-        }
+        for (int k = 1; k < RED_U; ++k) bm = fmax(bm, a[k]);
+        acc.s = acc.m > -INFINITY ? acc.s * exp_neg_tab(acc.m - bm, tab) : acc.s;   // bm > acc.m
+        acc.m = bm;
       }
-    } else {
-      // t and v kept: batches along this CTA's pixel chunks (a single element when x is kept too)
-      const double c = cz + s_dt[0] + (log_lw ? s_lw[z] : 0.0);
-      const double cv = s_dv[0];
-      const double* p = logp + ((long long)t0 * g.nv + v0) * row + tid;
-      for (long long cb = blockIdx.x; cb < nchunk; cb += cstep * RED_U) {
-        double a[RED_U];
+      if (acc.m > -INFINITY) {
+        double sum = acc.s;
 #pragma unroll
         for (int k = 0; k < RED_U; ++k) {
-          const long long chunk = cb + k * cstep;
-          const bool ok = chunk < nchunk && chunk * PB + xl < g.npix;
-          const double ld = ok ? __ldg(p + chunk * nact) : -INFINITY;
-          a[k] = ld + c + cv;
+          const double x = a[k] - acc.m;
+          const double y = exp_core_tab(x, tab);
+          if (!(x < -708.0)) sum += y;
         }
-        flush(a);
+        acc.s = sum;
+      } else {                      // nothing finite seen so far: -inf elements add nothing, NaN poisons
+        bool nan = false;
+#pragma unroll
+        for (int k = 0; k < RED_U; ++k) nan = nan || a[k] != a[k];
+        if (nan) acc.s = NAN;
+      }
+    };
+    if (active) {
+      if (nV > 1) {
+        // batches along v (stride = one (t,v) row)
+        for (long long chunk = blockIdx.x; chunk < nchunk; chunk += cstep) {
+          if (chunk * PB + xl >= g.npix) continue;
+          for (int t = t0; t < t1; ++t) {
+            const double ct = cz + s_dt[t] + (log_lw ? s_lw[t * nz_ + z] : 0.0);
+            const double* p = logp + ((long long)t * g.nv + v0) * row + chunk * nact + tid;
+            auto load = [&](double (&a)[RED_U], int vb) {
+              const double* q = p + (long long)vb * row;
+              if (vb + RED_U <= nV) {
+#pragma unroll
+                for (int k = 0; k < RED_U; ++k) a[k] = __ldg(q + k * row) + (per_v ? ct + s_dv[v0 + vb + k] : ct);
+              } else {
+#pragma unroll
+                for (int k = 0; k < RED_U; ++k) {
+                  const bool ok = vb + k < nV;
+                  a[k] = ok ? __ldg(q + k * row) + ct + s_dv[v0 + vb + k] : -INFINITY;
+                }
+              }
+            };
+            double a[RED_U], b[RED_U];
+            load(a, 0);
+            for (int vb = 0; vb < nV; vb += 2 * RED_U) {
+              load(b, vb + RED_U);
+              flush(a, s_exp);
+              load(a, vb + 2 * RED_U);
+              flush(b, s_exp);
+            }
+          }
+        }
+      } else if (nT > 1) {
+        // v kept, t summed: batches along t (stride = nv rows)
+        const double cv = cz + s_dv[v0];
+        const long long tstride = (long long)g.nv * row;
+        for (long long chunk = blockIdx.x; chunk < nchunk; chunk += cstep) {
+          if (chunk * PB + xl >= g.npix) continue;
+          const double* p = logp + (long long)v0 * row + chunk * nact + tid;
+          auto load = [&](double (&a)[RED_U], int tb) {
+            const double* q = p + (long long)tb * tstride;
+            if (tb + RED_U <= nT) {
+#pragma unroll
+              for (int k = 0; k < RED_U; ++k)
+                a[k] = __ldg(q + k * tstride) + (cv + s_dt[tb + k] + (log_lw ? s_lw[(tb + k) * nz_ + z] : 0.0));
+            } else {
+#pragma unroll
+              for (int k = 0; k < RED_U; ++k) {
+                const bool ok = tb + k < nT;
+                const int tt = ok ? tb + k : 0;
+                a[k] = ok ? __ldg(q + k * tstride) + (cv + s_dt[tt] + (log_lw ? s_lw[tt * nz_ + z] : 0.0)) : -INFINITY;
+              }
+            }
+          };
+          double a[RED_U], b[RED_U];
+          load(a, 0);
+          for (int tb = 0; tb < nT; tb += 2 * RED_U) {
+            load(b, tb + RED_U);
+            flush(a, s_exp);
+            load(a, tb + 2 * RED_U);
+            flush(b, s_exp);
+          }
+        }
+      } else {
+        // t and v kept: batches along this CTA's pixel chunks (a single element when x is kept too)
+        const double c = cz + s_dt[t0] + (log_lw ? s_lw[t0 * nz_ + z] : 0.0) + s_dv[v0];
+        const double* p = logp + ((long long)t0 * g.nv + v0) * row + tid;
+        if (g.kx) {
+          const long long chunk = blockIdx.x;
+          if (chunk * PB + xl < g.npix) {
+            const double a0 = __ldg(p + chunk * nact) + c;
+            acc.m = a0 > -INFINITY ? a0 : -INFINITY;
+            acc.s = a0 > -INFINITY ? 1.0 : (a0 != a0 ? NAN : 0.0);
+          }
+        } else {
+          auto load = [&](double (&a)[RED_U], long long cb) {
+#pragma unroll
+            for (int k = 0; k < RED_U; ++k) {
+              const long long chunk = cb + k * cstep;
+              const bool ok = chunk < nchunk && chunk * PB + xl < g.npix;
+              a[k] = ok ? __ldg(p + chunk * nact) + c : -INFINITY;
+            }
+          };
+          double a[RED_U], b[RED_U];
+          load(a, blockIdx.x);
+          for (long long cb = blockIdx.x; cb < nchunk; cb += 2 * cstep * RED_U) {
+            load(b, cb + cstep * RED_U);
+            flush(a, s_exp);
+            load(a, cb + 2 * cstep * RED_U);
+            flush(b, s_exp);
+          }
+        }
       }
     }
-  }
 
-  if (gmax) {                                 // global maximum (light-weighted normalisation)
-    double r = acc.m;
-    for (int off = 16; off > 0; off >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, off));
-    if ((tid & 31) == 0 && r > -INFINITY) atomic_max_double(gmax, r);
-  }
+    if (gmax) {                                 // global maximum (light-weighted normalisation)
+      double r = acc.m;
+      for (int off = 16; off > 0; off >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, off));
+      if ((tid & 31) == 0 && r > -INFINITY) atomic_max_double(gmax, r);
+    }
 
-  // combine over the dropped in-CTA axes and store the pair(s)
-  const long long part = g.kx ? 1 : G, pidx = g.kx ? 0 : blockIdx.x;
-  if (g.kx && g.kz) {
-    const long long x = (long long)blockIdx.x * PB + xl;
-    if (tid < nact && x < g.npix) {
-      const long long o = out_index(g, t0, v0, x, z);
-      mx[o] = acc.m;
-      out[o] = acc.s;
-    }
-    return;
-  }
-  red_m[tid] = tid < nact ? acc.m : -INFINITY;
-  red_s[tid] = tid < nact ? acc.s : 0.0;
-  __syncthreads();
-  if (g.kx) {            // reduce over z, one thread per pixel
-    const long long x = (long long)blockIdx.x * PB + tid;
-    if (tid < PB && x < g.npix) {
-      Lse r{-INFINITY, 0.0};
-      for (int zz = 0; zz < g.nz; ++zz) r = lse_merge(r, Lse{red_m[tid * g.nz + zz], red_s[tid * g.nz + zz]});
-      const long long o = out_index(g, t0, v0, x, 0);
-      mx[o] = r.m;
-      out[o] = r.s;
-    }
-  } else if (g.kz) {     // reduce over the chunk's pixels, one thread per z
-    if (tid < g.nz) {
-      Lse r{-INFINITY, 0.0};
-      for (int xx = 0; xx < PB; ++xx) r = lse_merge(r, Lse{red_m[xx * g.nz + tid], red_s[xx * g.nz + tid]});
-      const long long o = out_index(g, t0, v0, 0, tid) * part + pidx;
-      mx[o] = r.m;
-      out[o] = r.s;
-    }
-  } else {               // reduce everything in the CTA
-    for (int st = 128; st > 0; st >>= 1) {
-      if (tid < st) {
-        const Lse r = lse_merge(Lse{red_m[tid], red_s[tid]}, Lse{red_m[tid + st], red_s[tid + st]});
-        red_m[tid] = r.m;
-        red_s[tid] = r.s;
+    // combine over the dropped in-CTA axes and store the pair(s)
+    if (g.kx && g.kz) {
+      const long long x = (long long)blockIdx.x * PB + xl;
+      if (active && x < g.npix) {
+        const long long o = out_index(g, t0, v0, x, z);
+        mx[o] = acc.m;
+        out[o] = acc.s;
       }
+      continue;
+    }
+    // Two-phase so that every thread evaluates ONE table exponential: (1) group maximum M from
+    // shared memory, (2) s * exp(m - M) summed per group.  (A serial chain of pair merges by one
+    // thread per group cost as much as the streaming loop.)  NaN sums are kept: 0 * NaN = NaN.
+    red_m[tid] = active ? acc.m : -INFINITY;
+    __syncthreads();
+    if (g.kx) {            // groups = pixels: the nz elements of pixel xl are contiguous
+      double M = -INFINITY;
+      if (active)
+        for (int zz = 0; zz < nz_; ++zz) M = fmax(M, red_m[xl * nz_ + zz]);
+      red_s[tid] = active ? (M > -INFINITY ? acc.s * exp_neg_tab(acc.m - M, s_exp) : acc.s) : 0.0;
       __syncthreads();
+      const long long x = (long long)blockIdx.x * PB + xl;
+      if (active && z == 0 && x < g.npix) {
+        double sum = 0.0;
+        for (int zz = 0; zz < nz_; ++zz) sum += red_s[xl * nz_ + zz];
+        const long long o = out_index(g, t0, v0, x, 0);
+        mx[o] = M;
+        out[o] = sum;
+      }
+    } else if (g.kz) {     // groups = metallicities: the PB pixels of z are strided by nz
+      double M = -INFINITY;
+      if (active)
+        for (int xx = 0; xx < PB; ++xx) M = fmax(M, red_m[xx * nz_ + z]);
+      red_s[tid] = active ? (M > -INFINITY ? acc.s * exp_neg_tab(acc.m - M, s_exp) : acc.s) : 0.0;
+      __syncthreads();
+      if (active && xl == 0) {
+        double sum = 0.0;
+        for (int xx = 0; xx < PB; ++xx) sum += red_s[xx * nz_ + z];
+        const long long o = out_index(g, t0, v0, 0, z) * part + pidx;
+        mx[o] = M;
+        out[o] = sum;
+      }
+    } else {               // one group: the whole CTA
+      for (int st = 128; st > 0; st >>= 1) {
+        if (tid < st) red_m[tid] = fmax(red_m[tid], red_m[tid + st]);
+        __syncthreads();
+      }
+      const double M = red_m[0];
+      red_s[tid] = active ? (M > -INFINITY ? acc.s * exp_neg_tab(acc.m - M, s_exp) : acc.s) : 0.0;
+      __syncthreads();
+      for (int st = 128; st > 0; st >>= 1) {
+        if (tid < st) red_s[tid] += red_s[tid + st];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const long long o = out_index(g, t0, v0, 0, 0) * part + pidx;
+        mx[o] = M;
+        out[o] = red_s[0];
+      }
     }
-    if (tid == 0) {
-      const long long o = out_index(g, t0, v0, 0, 0) * part + pidx;
-      mx[o] = red_m[0];
-      out[o] = red_s[0];
-    }
+    __syncthreads();       // red_m / red_s are reused by the next kept velocity bin
   }
 }
 
@@ -464,7 +565,7 @@ __global__ void k_noise(const double* __restrict__ ybar, long long n, double snr
 // number of pixel-chunk groups (CTAs along x) when x is summed over: enough CTAs to fill the GPU
 // several times over, never more than there are chunks
 static int reduce_groups(const pkm_plan* pl, const ReduceGeom& g, long long nchunk) {
-  const long long n_outer = (long long)(g.kt ? g.nt : 1) * (g.kv ? g.nv : 1);
+  const long long n_outer = (long long)(g.kt ? g.nt : 1) * (g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
   long long G = ((long long)pl->num_sms * 32 + n_outer - 1) / n_outer;
   G = std::max<long long>(1, std::min<long long>(G, nchunk));
   return (int)G;
@@ -473,23 +574,23 @@ static int reduce_groups(const pkm_plan* pl, const ReduceGeom& g, long long nchu
 // one online pass + (x dropped) the fold of the chunk-group partials; leaves the pairs in (mx, sum)
 static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, const double* d_log_dv,
                          const double* d_log_lw, double* d_mx, double* d_sum, double* d_part,
-                         long long nout, double* d_gmax, cudaStream_t st) {
+                         long long nout, double* d_gmax, int uniform_dv, cudaStream_t st) {
   const int PB = 256 / g.nz;
   const long long nchunk = (g.npix + PB - 1) / PB;
   const size_t smem = sizeof(double) * ((size_t)g.nt + g.nv + (size_t)g.nt * g.nz);
   PKM_REQUIRE(smem <= 40 * 1024, "age/velocity/metallicity grid too large for the reduction kernel");
   if (g.kx) {
-    dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
+    dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
     k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
-                                            pl->d_exp_tab, d_mx, d_sum, d_gmax, PB, nchunk);
+                                            pl->d_exp_tab, d_mx, d_sum, d_gmax, PB, nchunk, uniform_dv);
     return 1;
   }
   const int G = reduce_groups(pl, g, nchunk);
   double* pm = d_part;
   double* ps = d_part + nout * G;
-  dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? g.nv : 1);
+  dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
   k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
-                                          pl->d_exp_tab, pm, ps, d_gmax, PB, nchunk);
+                                          pl->d_exp_tab, pm, ps, d_gmax, PB, nchunk, uniform_dv);
   k_reduce_combine<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(pm, ps, nout, G, d_mx, d_sum);
   return 2;
 }
@@ -541,7 +642,7 @@ void launch_reduce_logp(pkm_plan* pl, const double* logp, const ReduceSrc& src, 
     pl->launches += 1;
     if (lw) {
       // normalisation: scalar log-sum-exp of the weighted array (one more pass)
-      pl->launches += reduce_online(pl, logp, g0, d_log_dv, d_log_lw, d_mx0, d_sum0, d_part, 1, nullptr, st);
+      pl->launches += reduce_online(pl, logp, g0, d_log_dv, d_log_lw, d_mx0, d_sum0, d_part, 1, nullptr, src.uniform_dv, st);
       // d_sum0 <- mx0 + log(sum0) = log normalisation (finalize on the 1-element array)
       k_reduce_finalize<<<1, 32, 0, st>>>(d_sum0, d_mx0, 1, g0, pl->d_log_dt, d_log_dv, pl->d_log_dz, nullptr, nullptr, 0);
       k_sub_density<<<grid, 256, 0, st>>>(out, ntot, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_sum0, density);
@@ -554,7 +655,7 @@ void launch_reduce_logp(pkm_plan* pl, const double* logp, const ReduceSrc& src, 
     return;
   }
 
-  pl->launches += reduce_online(pl, logp, g, d_log_dv, d_log_lw, d_mx, out, d_part, nout, lw ? d_gmax : nullptr, st);
+  pl->launches += reduce_online(pl, logp, g, d_log_dv, d_log_lw, d_mx, out, d_part, nout, lw ? d_gmax : nullptr, src.uniform_dv, st);
   if (lw) k_reduce_total<<<fgrid, 256, 0, st>>>(d_mx, out, nout, d_gmax, d_total);
   k_reduce_finalize<<<fgrid, 256, 0, st>>>(out, d_mx, nout, g, pl->d_log_dt, d_log_dv, pl->d_log_dz,
                                            lw ? d_gmax : nullptr, lw ? d_total : nullptr, density);
