@@ -544,6 +544,7 @@ def run_b200(args):
         del logp
         torch.cuda.empty_cache()
         cube_e2e = cube if world == 1 else build_cube(args, nx1=rows, nx2=nxl)
+        cube_e2e.dx, cube_e2e.dy = cube.dx, cube.dy     # the shard's pixels ARE the global cube's pixels
         cmp = pkm.components.Component(cube=cube_e2e, log_p_tvxz=np_in)
 
         def step_e2e():
