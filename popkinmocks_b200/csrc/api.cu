@@ -123,7 +123,7 @@ static void plan_free(pkm_plan* pl) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_Sw); fr(pl->d_Sw32);
+  fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_CIt_oct); fr(pl->d_CR); fr(pl->d_CI); fr(pl->d_Sw); fr(pl->d_Sw32);
   fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_omega);
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz); fr(pl->d_exp_tab);
@@ -178,7 +178,7 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
     }
 
     // ---- density path tables
-    pl->density_ok = desc->v0_idx >= 0 && desc->v0_idx < desc->nv && pl->nfi >= 4 && pl->nfi <= 64;
+    pl->density_ok = desc->v0_idx >= 0 && desc->v0_idx < desc->nv && pl->nfi >= 4;
     if (pl->density_ok) {
       SplineTables sp;
       build_spline_tables(pl->nfi, nfo, sp);
@@ -388,7 +388,7 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
     PKM_REQUIRE(out_layout == PKM_LAYOUT_CUBE || out_layout == PKM_LAYOUT_PIXEL_MAJOR, "bad out_layout %d", out_layout);
     if (pl->d.v0_idx < 0)
       PKM_THROW(PKM_ERR_NO_ZERO_BIN, "no velocity bin centred on zero (nv=%d): the density path is undefined", pl->d.nv);
-    PKM_REQUIRE(pl->density_ok, "density path unavailable for nv=%d (needs 6 <= nv <= 127)", pl->d.nv);
+    PKM_REQUIRE(pl->density_ok, "density path unavailable for nv=%d (the cubic spline needs nv >= 6)", pl->d.nv);
     use_device(pl->d.device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool in_host = !pkm_is_device_pointer(dens);
@@ -398,7 +398,6 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
     const int64_t pix_begin = (int64_t)row_begin * nx2;
     const int64_t npix = (int64_t)(row_end - row_begin) * nx2;
     if (npix == 0) return;
-    const int pxb = coeff_choose_pxb(pl);
 
     // Host buffers are pipelined: H2D of tile i+1 (copy stream) and D2H of tile i-1 (output
     // stream) overlap the kernels of tile i (caller's stream); two staging slots each way.
@@ -412,7 +411,6 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
     const bool side_transpose = cube_npix > 0;
     if (side_transpose) tile = std::min<int64_t>(tile, ((npix + 3) / 4 + 31) & ~int64_t(31));
     tile = std::max((tile / 32) * 32, 32);  // the coefficient layout groups pixels by 32
-    (void)pxb;
 
     pl->coef.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
     pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);

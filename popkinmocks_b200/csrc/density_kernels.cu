@@ -336,7 +336,7 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
             const double* __restrict__ exp2_tab) {
   extern __shared__ __align__(128) double smem[];
   constexpr int MB = TM;
-  const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, pxb = g.pxb, v0 = g.v0;
+  const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, pxb = g.pxb, v0 = g.v0;
   const int nks = (ne + 3) >> 2;
   const int frag_elems = nks * MB * 32;
   const int NC = pxb * nz;                       // dense box pitch (a multiple of 16)
@@ -381,9 +381,6 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   const int nitem = nz * (pxb >> 3);
   const int iz = warp % nz, oct = warp / nz;
   const int fr = lane >> 2, fk = lane & 3;
-  const int half = NC >> 1;                      // double2 columns per velocity row
-  const int fu0 = tid / half, fc0 = tid - fu0 * half;
-  const int fdu = K1_THREADS / half, fdc = K1_THREADS - fdu * half;
 
   unsigned phases = 0u;
 #ifdef PKM_K1_PROF
@@ -398,46 +395,19 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
     const int t = (int)(tile / nxb);
     const int xb = (int)(tile - (long long)t * nxb);
     double* Bs = Bbuf + (size_t)b * buf_elems;
-    // fold v <-> -v in place (e = sum, o = difference of the rolled profile), exp fused; two
-    // row pairs per pass so that eight exps are in flight per thread
-    int u = fu0, c2 = fc0;
-    auto fold_pass = [&]() {
-      int u2 = u + fdu, c22 = c2 + fdc;
-      if (c22 >= half) { c22 -= half; ++u2; }
-      const bool two = u2 < ne;
-      double2* pa = reinterpret_cast<double2*>(Bs + (size_t)row_plus(u, v0, nv) * NC) + c2;
-      double2* pb = reinterpret_cast<double2*>(Bs + (size_t)row_minus(u, v0, nv) * NC) + c2;
-      double2* qa = reinterpret_cast<double2*>(Bs + (size_t)row_plus(two ? u2 : u, v0, nv) * NC) + (two ? c22 : c2);
-      double2* qb = reinterpret_cast<double2*>(Bs + (size_t)row_minus(two ? u2 : u, v0, nv) * NC) + (two ? c22 : c2);
-      double2 a = *pa, bb = *pb, c = *qa, d = *qb;
-      if (g.is_log) {
-        a.x = exp_tab(a.x, etab); a.y = exp_tab(a.y, etab);
-        bb.x = exp_tab(bb.x, etab); bb.y = exp_tab(bb.y, etab);
-        c.x = exp_tab(c.x, etab); c.y = exp_tab(c.y, etab);
-        d.x = exp_tab(d.x, etab); d.y = exp_tab(d.y, etab);
-      }
-      *pa = make_double2(a.x + bb.x, a.y + bb.y);
-      if (pa != pb) *pb = make_double2(a.x - bb.x, a.y - bb.y);
-      if (two) {
-        *qa = make_double2(c.x + d.x, c.y + d.y);
-        if (qa != qb) *qb = make_double2(c.x - d.x, c.y - d.y);
-      }
-      u = u2 + fdu;
-      c2 = c22 + fdc;
-      if (c2 >= half) { c2 -= half; ++u; }
-    };
-    while (u < ne) fold_pass();
-    K1_TICK(1);
-    __syncthreads();
-    K1_TICK(2);
     // the other buffer holds the previous tile's staged coefficients: once the store engine has
-    // read them (it had the whole fold to do so) the slab of the next tile streams in
+    // read them the slab of the next tile streams in behind this tile's GEMM
     if (tid == 0 && it > 0) {
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       if (tile + tstep < ntile) issue(tile + tstep, b ^ 1);
     }
     // GEMM on the FP64 tensor cores: C[m = mb*8 + fr][pixels 2 fk, 2 fk + 1] of this warp's 8 pixels
-    // at metallicity iz, real and imaginary part
+    // at metallicity iz, real and imaginary part.  The v <-> -v fold of the real DFT (e = sum,
+    // o = difference of the rolled profile; halves the GEMM) and exp(log p) happen HERE, while the
+    // B fragments are formed: every slab element belongs to exactly one (lane, k-step) of exactly
+    // one warp, so nothing is evaluated twice, the slab stays read-only and the separate fold pass
+    // (4.3k of 16.6k cycles per tile, one CTA barrier) is gone.  Even and odd part use the same
+    // rolled index u (the odd operand has a zero column for u = 0).
     double accr[MB][2], acci[MB][2];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) accr[mb][0] = accr[mb][1] = acci[mb][0] = acci[mb][1] = 0.0;
@@ -445,11 +415,21 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       const double* Bcol = Bs + (oct * 8 + fr) * nz + iz;
       const double* Ar = As_r + lane;
       const double* Ai = As_i + lane;
+      auto fetch = [&](int ks, double& pa, double& pb) {
+        const int u = min(ks * 4 + fk, ne - 1);               // u >= ne has zero A
+        pa = Bcol[(size_t)row_plus(u, v0, nv) * NC];
+        pb = Bcol[(size_t)row_minus(u, v0, nv) * NC];
+      };
+      double pa, pb;
+      fetch(0, pa, pb);
       for (int ks = 0; ks < nks; ++ks) {
-        // E[u] lives in row +u, O[u] (u >= 1) in row -u of the folded slab; u >= K has zero A
-        const int ue = min(ks * 4 + fk, ne - 1), uo = min(ks * 4 + fk, no - 1);
-        const double be = Bcol[(size_t)row_plus(ue, v0, nv) * NC];
-        const double bo = Bcol[(size_t)row_minus(uo + 1, v0, nv) * NC];
+        double qa = pa, qb = pb;
+        if (ks + 1 < nks) fetch(ks + 1, pa, pb);               // next step's raw values, ahead of the DMMAs
+        if (g.is_log) {
+          qa = exp_tab(qa, etab);
+          qb = exp_tab(qb, etab);
+        }
+        const double be = qa + qb, bo = qa - qb;
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
           dmma_m8n8k4(accr[mb][0], accr[mb][1], Ar[(ks * MB + mb) * 32], be);
@@ -496,13 +476,16 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
 
 // A operand in DMMA fragment order: element [ks][mb][lane] = C[m = mb*8 + lane/4][u = ks*4 + lane%4]
 // (zero outside the matrix), so a warp's fragment load is one contiguous 256-byte read.
-static void upload_fragments(const std::vector<double>& C, int nfi, int K, int MB, int nks, double** d_out) {
+// `shift` = 1 stores column u of the fragment table from matrix column u - 1 (zero for u = 0): the
+// octet kernel indexes the odd part O[u] with the same rolled position u as the even part.
+static void upload_fragments(const std::vector<double>& C, int nfi, int K, int MB, int nks, double** d_out,
+                             int shift = 0) {
   std::vector<double> h((size_t)nks * MB * 32, 0.0);
   for (int ks = 0; ks < nks; ++ks)
     for (int mb = 0; mb < MB; ++mb)
       for (int lane = 0; lane < 32; ++lane) {
-        const int m = mb * 8 + lane / 4, u = ks * 4 + lane % 4;
-        if (m < nfi && u < K) h[((size_t)ks * MB + mb) * 32 + lane] = C[(size_t)m * K + u];
+        const int m = mb * 8 + lane / 4, u = ks * 4 + lane % 4 - shift;
+        if (m < nfi && u >= 0 && u < K) h[((size_t)ks * MB + mb) * 32 + lane] = C[(size_t)m * K + u];
       }
   PKM_CUDA(cudaMalloc(d_out, h.size() * sizeof(double)));
   PKM_CUDA(cudaMemcpy(*d_out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -510,11 +493,17 @@ static void upload_fragments(const std::vector<double>& C, int nfi, int K, int M
 
 void density_tables_upload(pkm_plan* pl) {
   pl->TM = (pl->nfi + 7) / 8;   // number of 8-row blocks
-  PKM_REQUIRE(pl->TM <= 8, "nv=%d too large for the coefficient kernel (nfi=%d > 64)", pl->d.nv, pl->nfi);
+  // plain row-major copies for the generic kernel (nfi > 64, or PKM_COEFF_GENERIC=1 for testing)
+  PKM_CUDA(cudaMalloc(&pl->d_CR, std::max<size_t>(pl->fold.CR.size(), 1) * sizeof(double)));
+  PKM_CUDA(cudaMemcpy(pl->d_CR, pl->fold.CR.data(), pl->fold.CR.size() * sizeof(double), cudaMemcpyHostToDevice));
+  PKM_CUDA(cudaMalloc(&pl->d_CI, std::max<size_t>(pl->fold.CI.size(), 1) * sizeof(double)));
+  PKM_CUDA(cudaMemcpy(pl->d_CI, pl->fold.CI.data(), pl->fold.CI.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (pl->TM > 8) return;       // the tensor-core kernels keep the operands resident in shared memory: nfi <= 64
   const int nks = (pl->fold.ne + 3) / 4;
   pl->nfiP = nks * pl->TM * 32;  // doubles per A operand
   upload_fragments(pl->fold.CR, pl->nfi, pl->fold.ne, pl->TM, nks, &pl->d_CRt);
   upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt);
+  upload_fragments(pl->fold.CI, pl->nfi, pl->fold.no, pl->TM, nks, &pl->d_CIt_oct, 1);
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
@@ -688,7 +677,7 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   g.out_f32 = pl->d.precision == 1;
   g.use_tma = 2;
   KernelTimer tm(pl, PKM_K_COEFF, st);
-  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt, pl->d_exp_tab);
+  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab);
   PKM_CUDA(cudaGetLastError());
 #ifdef PKM_K1_PROF
   {
@@ -707,11 +696,98 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   return true;
 }
 
+// ----------------------------------------------------------------------------
+// Generic coefficient kernel for velocity grids whose folded matrices do not fit the resident-
+// operand tensor-core kernels above (nfi = nv/2 + 1 > 64, e.g. IFUCube's default nv = 200/201):
+// plain FP64 FMAs, the folded matrices read through L1 as warp-uniform loads.  Any shape, any
+// alignment; several times slower per column than the DMMA kernels - a correctness path.
+// CTA = (age t, 64 consecutive density columns); thread = (column, group of 4 output rows).
+// ----------------------------------------------------------------------------
+constexpr int KG_COLS = 64, KG_ROWS = 4;
+__global__ void __launch_bounds__(256)
+k_coeff_generic(const double* __restrict__ dens, K1Geom g, const double* __restrict__ CR,
+                const double* __restrict__ CI, double2* __restrict__ cT) {
+  extern __shared__ double kg_smem[];          // e [ne][64] | o [no][64]
+  const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, no = g.no, v0 = g.v0;
+  double* se = kg_smem;
+  double* so = kg_smem + (size_t)ne * KG_COLS;
+  const int t = blockIdx.y;
+  const long long col0 = (long long)blockIdx.x * KG_COLS;
+  const long long ncol = (long long)g.npix_tile * nz;
+  const size_t vstride = (size_t)g.npix_total * nz;
+  const double* src = dens + (size_t)t * nv * vstride + (size_t)g.pix0 * nz + col0;
+  for (int i = threadIdx.x; i < ne * KG_COLS; i += blockDim.x) {
+    const int u = i / KG_COLS, c = i - u * KG_COLS;
+    double a = 0.0, b = 0.0;
+    if (col0 + c < ncol) {
+      a = __ldg(src + (size_t)row_plus(u, v0, nv) * vstride + c);
+      b = __ldg(src + (size_t)row_minus(u, v0, nv) * vstride + c);
+      if (g.is_log) { a = exp(a); b = exp(b); }
+    }
+    se[i] = a + b;                              // self-paired rows carry weight 1/2 in CR
+    if (u >= 1 && u - 1 < no) so[(size_t)(u - 1) * KG_COLS + c] = a - b;
+  }
+  __syncthreads();
+  const int c = threadIdx.x % KG_COLS, rg = threadIdx.x / KG_COLS;
+  const long long col = col0 + c;
+  if (col >= ncol) return;
+  const int x = (int)(col / nz), z = (int)(col - (long long)x * nz);
+  const size_t obase = (((size_t)(x >> 5) * g.nt * nz + (size_t)t * nz + z) * nfi) * 32 + (x & 31);
+  for (int m0 = rg * KG_ROWS; m0 < nfi; m0 += KG_ROWS * (256 / KG_COLS)) {
+    double ar[KG_ROWS], ai[KG_ROWS];
+#pragma unroll
+    for (int r = 0; r < KG_ROWS; ++r) ar[r] = ai[r] = 0.0;
+    for (int u = 0; u < ne; ++u) {
+      const double e = se[(size_t)u * KG_COLS + c];
+#pragma unroll
+      for (int r = 0; r < KG_ROWS; ++r)
+        if (m0 + r < nfi) ar[r] = fma(__ldg(CR + (size_t)(m0 + r) * ne + u), e, ar[r]);
+    }
+    for (int u = 0; u < no; ++u) {
+      const double o = so[(size_t)u * KG_COLS + c];
+#pragma unroll
+      for (int r = 0; r < KG_ROWS; ++r)
+        if (m0 + r < nfi) ai[r] = fma(__ldg(CI + (size_t)(m0 + r) * no + u), o, ai[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < KG_ROWS; ++r) {
+      if (m0 + r >= nfi) continue;
+      const size_t ci = obase + (size_t)(m0 + r) * 32;
+      if (g.out_f32) reinterpret_cast<float2*>(cT)[ci] = make_float2((float)ar[r], (float)ai[r]);
+      else cT[ci] = make_double2(ar[r], ai[r]);
+    }
+  }
+}
+
+static void launch_coeff_generic(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
+                                 int64_t pix0, int npix_tile, int xpad, double2* cT, cudaStream_t st) {
+  K1Geom g;
+  g.ngroup = 1; g.use_tma = 0;
+  g.npix_total = npix_total; g.pix0 = pix0; g.npix_tile = npix_tile; g.xpad = xpad;
+  g.nv = pl->d.nv; g.nz = pl->d.nz; g.nfi = pl->nfi; g.ne = pl->fold.ne; g.no = pl->fold.no;
+  g.pxb = 0; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
+  g.out_f32 = pl->d.precision == 1;
+  const size_t smem = sizeof(double) * (size_t)(g.ne + g.no) * KG_COLS;
+  PKM_REQUIRE(smem <= 200 * 1024, "nv=%d too large for the coefficient kernels", pl->d.nv);
+  PKM_REQUIRE(pl->d.nt <= 65535, "nt=%d too large for the generic coefficient kernel", pl->d.nt);
+  PKM_CUDA(cudaFuncSetAttribute(k_coeff_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long ncol = (long long)npix_tile * g.nz;
+  dim3 grid((unsigned)((ncol + KG_COLS - 1) / KG_COLS), (unsigned)pl->d.nt);
+  KernelTimer tm(pl, PKM_K_COEFF, st);
+  k_coeff_generic<<<grid, 256, smem, st>>>(dens, g, pl->d_CR, pl->d_CI, cT);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches++;
+}
+
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total, int64_t pix0,
                   int npix_tile, int xpad, double2* cT, cudaStream_t st) {
+  PKM_REQUIRE(xpad % 32 == 0 && xpad >= npix_tile, "internal: xpad=%d not a multiple of 32", xpad);
+  if (pl->TM > 8 || getenv("PKM_COEFF_GENERIC")) {
+    launch_coeff_generic(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, cT, st);
+    return;
+  }
   int ngroup = 1;
   const int pxb = coeff_choose_pxb(pl, &ngroup);
-  PKM_REQUIRE(xpad % 32 == 0 && xpad >= npix_tile, "internal: xpad=%d not a multiple of 32", xpad);
   bool done = false;
   switch (pl->TM) {
 #define CASE(T) case T: done = launch_coeff_oct_t<T>(pl, dens, is_log, npix_total, pix0, npix_tile, xpad, cT, st); break;

@@ -122,6 +122,9 @@ struct pkm_plan {
   int TM = 0, nfiP = 0;         // kernel 1: TM = 8-row output blocks, nfiP = doubles per A operand
   double* d_CRt = nullptr;      // real-part operand (A^-1 x cosine fold) in DMMA fragment order [nks][TM][32]
   double* d_CIt = nullptr;      // imaginary-part operand, same layout
+  double* d_CR = nullptr;       // folded matrices, plain row major [nfi][ne] / [nfi][no] (generic kernel)
+  double* d_CI = nullptr;
+  double* d_CIt_oct = nullptr;  // the same with the rolled index shifted by one (octet kernel: O[u] at column u)
   double2* d_Sw = nullptr;      // [nwseg][nchunk*TZC][KT]  S-hat' = FXw*dz*dt, tz = t*nz+z, zero padded
   float2* d_Sw32 = nullptr;     // float32 copy of d_Sw (precision = 1 only)
   int32_t* d_wseg = nullptr;    // [nwseg][4]

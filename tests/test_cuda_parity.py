@@ -8,7 +8,7 @@ the golden files do not cover.  Tolerances: fp64 path <= 1e-10 max-norm relative
 import numpy as np
 import pytest
 
-from conftest import golden_cube, load_golden, rel_err
+from conftest import build_cube, golden_cube, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -236,7 +236,8 @@ def test_output_embedded_in_a_larger_cube(gpu_ok):
 @pytest.mark.parametrize("ssp_kw,nv,nx", [
     (dict(lmd_min=3540.5, lmd_max=7409.6), 101, (2, 3)),   # full-resolution MILES range: n_fft = 11179 = 7*1597, M = 32768 (global-scratch FFT)
     (dict(age_rebin=8, z_rebin=4), 7, (3, 3)),             # smallest velocity grid the cubic spline admits (nfi = 4)
-    (dict(age_rebin=8, z_rebin=12), 127, (1, 5)),          # largest supported nv (nfi = 64), a single metallicity bin
+    (dict(age_rebin=8, z_rebin=12), 127, (1, 5)),          # largest nv of the tensor-core coefficient kernels (nfi = 64), one metallicity bin
+    (dict(age_rebin=8, z_rebin=4), 201, (2, 3)),           # IFUCube's default-sized velocity grid (nfi = 101): generic coefficient kernel
     (dict(age_rebin=53, z_rebin=3), 33, (1, 1)),           # one age bin, one pixel
 ])
 def test_edge_configurations_against_oracle(gpu_ok, ssp_kw, nv, nx):
@@ -324,3 +325,19 @@ def test_synthetic_density_is_shard_independent(gpu_ok):
     assert np.max(np.abs(host - dev)) < 1e-14
     u = np.exp(dev) / kw["scale"]
     assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.05
+
+
+def test_generic_coefficient_kernel_matches_the_tensor_core_kernels(gpu_ok, monkeypatch):
+    """PKM_COEFF_GENERIC=1 forces the plain-FMA coefficient kernel (the path of nv > 127) on a
+    shape the DMMA kernels also handle: same cube to rounding, in float64 and float32 mode."""
+    from popkinmocks_b200 import engine
+    name = "g2_rebin_nv21_prime"
+    g = load_golden(name)
+    cube = build_cube(name)
+    for precision, tol in (("float64", 1e-13), ("float32", 1e-6)):
+        ref = engine.Plan(cube, precision=precision).ybar_density(g["wn_log_p_tvxz"], is_log=True)
+        monkeypatch.setenv("PKM_COEFF_GENERIC", "1")
+        got = engine.Plan(cube, precision=precision).ybar_density(g["wn_log_p_tvxz"], is_log=True)
+        monkeypatch.delenv("PKM_COEFF_GENERIC")
+        assert rel_err(got, ref) < tol, precision
+    assert rel_err(got, g["wn_ybar"]) < 1e-5
