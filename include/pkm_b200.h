@@ -264,6 +264,46 @@ PKM_API int32_t pkm_synth_log_density(double* out, int32_t nt, int32_t nv, int64
                                       int64_t npix, int32_t nz, uint64_t seed, double scale,
                                       int32_t device, void* stream);
 
+/* ---- parametric-model maps on the device -----------------------
+ * The O(pixels) inputs of the Gaussian-LOSVD path, generated in HBM from O(nt) parameter vectors.
+ * x1 [nx1], x2 [nx2]: pixel centres (host); (cx, cy), rotation: the component frame
+ * (popkinmocks/components/parametric.py:43-49).  All outputs are DEVICE buffers.
+ *
+ * pkm_disk_maps <- GrowingDisk.set_p_x_t / set_mu_v / set_sig_v / set_t_dep
+ *                  (popkinmocks/components/growing_disk.py:30-239)
+ *   age_pars host [10][nt]: rows q, rc, alpha of p(x|t); q, rc, K of mu_v; q, alpha, sig_in, sig_out of
+ *   sig_v (already interpolated in age on the host); scale = max |x'| over the cube.
+ *   log_p_x_t [nt][npix] receives the log DENSITY p(x|t) normalised per age (log_dxdy = log(dx dy)),
+ *   mu_v, sig_v [nt][npix].  If t_dep and row_idx are given: t_dep_pars host {q, alpha, t_dep_in,
+ *   t_dep_out}, t_dep_grid host [ngrid] ascending (the tabulated depletion times of
+ *   parametric.py:213-247); t_dep [npix] and the index of the nearest grid entry row_idx [npix]
+ *   (parametric.py:262, first minimum on ties). */
+PKM_API int32_t pkm_disk_maps(const double* x1, const double* x2, int32_t nx1, int32_t nx2, double cx, double cy,
+                              double rotation, const double* age_pars, int32_t nt, double scale,
+                              const double* t_dep_pars, const double* t_dep_grid, int32_t ngrid,
+                              double* log_p_x_t, double* mu_v, double* sig_v, double* t_dep, int32_t* row_idx,
+                              double log_dxdy, int32_t device, void* stream);
+/* pkm_stream_maps <- Stream.set_p_x_t / set_mu_v (popkinmocks/components/stream.py:28-127):
+ *   centres_x/y host [nsmp] = r(theta) cos/sin(theta) of the samples along the arc, sig their width,
+ *   half_dx/dy = half the pixel size.  log_p_x [npix] receives log P(pixel) normalised to one over the
+ *   cube (the caller subtracts log(dx dy) for the density); mu_v [npix] the piecewise-linear velocity. */
+PKM_API int32_t pkm_stream_maps(const double* x1, const double* x2, int32_t nx1, int32_t nx2, double cx, double cy,
+                                double rotation, const double* centres_x, const double* centres_y, int32_t nsmp,
+                                double sig, double half_dx, double half_dy, double theta_lo, double theta_hi,
+                                double v_lo, double v_hi, double* log_p_x, double* mu_v, double log_dxdy,
+                                int32_t device, void* stream);
+/* pkm_assemble_txz <- ParametricComponent.get_p("txz", density=False) and get_log_p("txz")
+ * (popkinmocks/components/parametric.py:541-566):
+ *   P[t][x][z] = exp(log_P_t[t] + log_p_x[t or 0][x] + log_dxdy + log_Pz_rows[row_idx[x]][t][z])
+ *   log_p[t][x][z] = the corresponding log density (log_dt, log_dz host = log bin widths).
+ * log_P_t host [nt] (volume weighted), log_p_x device [nt][npix] (px_per_age != 0) or [npix],
+ * log_Pz_rows host [nrow][nt][nz] = log P(z | t, depletion-time row) (volume weighted), row_idx device
+ * [npix] or NULL (nrow == 1).  P_txz / log_p_txz: device [nt][npix][nz], either may be NULL. */
+PKM_API int32_t pkm_assemble_txz(const double* log_P_t, const double* log_dt, const double* log_p_x,
+                                 int32_t px_per_age, double log_dxdy, const double* log_Pz_rows, int32_t nrow,
+                                 const double* log_dz, const int32_t* row_idx, int32_t nt, int64_t npix,
+                                 int32_t nz, double* P_txz, double* log_p_txz, int32_t device, void* stream);
+
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA; best of `repeats`
  * timed launches of a register-resident DFMA chain on every SM).  The roofline denominator of
  * the FP64-pipe-bound kernels; MEASURED_PEAKS.json carries no FP64 figure. */

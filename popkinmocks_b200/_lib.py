@@ -81,6 +81,11 @@ SIGNATURES = {
     "pkm_histogram5d": (_I32, [C.POINTER(_P), _P, _I64, C.POINTER(_P), C.POINTER(_I32), _P, _I32, _P]),
     "pkm_pixelate_gaussian": (_I32, [_P, _P, _P, _P, _I32, _I32, _I64, _I32, _I32, _P, _I32, _P]),
     "pkm_synth_log_density": (_I32, [_P, _I32, _I32, _I64, _I64, _I64, _I32, _U64, _F64, _I32, _P]),
+    "pkm_disk_maps": (_I32, [_P, _P, _I32, _I32, _F64, _F64, _F64, _P, _I32, _F64, _P, _P, _I32, _P, _P, _P, _P, _P,
+                             _F64, _I32, _P]),
+    "pkm_stream_maps": (_I32, [_P, _P, _I32, _I32, _F64, _F64, _F64, _P, _P, _I32, _F64, _F64, _F64, _F64, _F64,
+                               _F64, _F64, _P, _P, _F64, _I32, _P]),
+    "pkm_assemble_txz": (_I32, [_P, _P, _P, _I32, _F64, _P, _I32, _P, _P, _I32, _I64, _I32, _P, _P, _I32, _P]),
     "pkm_fp64_fma_peak": (_I32, [_I32, _I32, C.POINTER(_F64)]),
 }
 

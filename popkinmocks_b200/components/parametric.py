@@ -19,7 +19,7 @@ import numpy as np
 from scipy import special, stats
 
 from . import base
-from .. import engine
+from .. import _lib, engine
 
 
 def _log_diff_exp(log_hi, log_lo):
@@ -57,6 +57,70 @@ class ParametricComponent(base.Component):
         self.xxp = c * dx1 - s * dx2
         self.yyp = s * dx1 + c * dx2
         self.get_z_interpolation_grid()
+
+    # ------------------------------------------------------------------ lazy host arrays / device maps
+    # The O(pixels) arrays the reference builds in `set_*` (log_p_x_t, p_x_t, t_dep, log_p_z_tx, p_z_tx,
+    # mu_v, sig_v) stay available as attributes but are computed on first ACCESS: `set_*` only records
+    # the parameters.  `evaluate_ybar` and `pixelate` never touch them - they build the same maps in
+    # HBM from the parameters (`_build_device_maps`, pkm_disk_maps / pkm_stream_maps /
+    # pkm_assemble_txz), so nothing of size nx1*nx2 is computed on the host or crosses PCIe.
+    def _set_lazy(self, names, method):
+        lazy = self.__dict__.setdefault("_lazy", {})
+        for name in names:
+            self.__dict__.pop(name, None)
+            lazy[name] = method
+        self.__dict__.pop("_pkm_maps", None)          # parameters changed: device maps are stale
+
+    def __getattr__(self, name):
+        lazy = self.__dict__.get("_lazy")
+        if lazy is not None and name in lazy:
+            getattr(self, lazy[name])()                # fills self.__dict__[name] (and its siblings)
+            return self.__dict__[name]
+        raise AttributeError(f"{type(self).__name__!s} object has no attribute {name!r}")
+
+    def __getstate__(self):
+        state = super().__getstate__()
+        state.pop("_pkm_maps", None)                   # device tensors are not pickled
+        return state
+
+    def _build_device_maps(self, device):
+        """Subclasses with device kernels return dict(log_p_x, px_per_age, mu_v, sig_v, rows,
+        row_idx) of CUDA tensors; None means 'use the host arrays'."""
+        return None
+
+    def _device_maps(self, device=0):
+        """P(t,x,z) [nt,nx1,nx2,nz], the log density log p(t,x,z), mu_v, sig_v on `device`, built
+        there from the model parameters; None if this class has no device generator."""
+        _lib.require_gpu()
+        cache = self.__dict__.setdefault("_pkm_maps", {})
+        if device in cache:
+            return cache[device]
+        import torch
+        built = self._build_device_maps(device)
+        if built is None:
+            return None
+        cube = self.cube
+        nz, nt = cube.ssps.par_dims
+        npix = cube.nx * cube.ny
+        dev = f"cuda:{device}"
+        rows = np.asarray(built["rows"])
+        # log P(z | t, depletion-time row), volume weighted, [row][t][z]
+        log_p_z_t_row = self._enrichment_table(rows)                         # [z, t, row] log density
+        log_dz = np.log(cube.construct_volume_element("z"))
+        log_Pz = np.ascontiguousarray(np.moveaxis(log_p_z_t_row, (0, 1, 2), (2, 1, 0)) + log_dz)
+        log_dt = np.log(cube.construct_volume_element("t"))
+        log_P_t = _lib.as_f64(self.log_p_t + log_dt)
+        P = torch.empty((nt, cube.nx, cube.ny, nz), dtype=torch.float64, device=dev)
+        logp = torch.empty_like(P)
+        row_idx = built.get("row_idx")
+        _lib.check(_lib.load().pkm_assemble_txz(
+            _lib.ptr(log_P_t), _lib.ptr(_lib.as_f64(log_dt)), _lib.ptr(built["log_p_x"]), int(built["px_per_age"]),
+            float(np.log(cube.dx) + np.log(cube.dy)), _lib.ptr(log_Pz), int(rows.size), _lib.ptr(_lib.as_f64(log_dz)),
+            _lib.ptr(row_idx), int(nt), int(npix), int(nz), _lib.ptr(P), _lib.ptr(logp), int(device), None))
+        out = dict(P_txz=P, log_p_txz=logp, mu_v=built["mu_v"], sig_v=built["sig_v"],
+                   log_p_x=built["log_p_x"], t_dep=built.get("t_dep"), row_idx=row_idx, rows=rows)
+        cache[device] = out
+        return out
 
     # ------------------------------------------------------------------ star formation history
     def get_beta_a_b_from_lmd_phi(self, lmd, phi):
@@ -117,6 +181,11 @@ class ParametricComponent(base.Component):
         inverted by interpolation onto the SSP ages (parametric.py:213-247)."""
         self.ahat = 10.0 ** (-0.689)
         self.bhat = 1.899 - 1.0
+        key = ("_pkm_z_grid", tuple(t_dep_lim), n_t_dep, n_z)
+        cached = self.cube.__dict__.get(key)
+        if cached is not None:                         # same cube, same table: components share it
+            self.t, self.z_t_interp_grid = cached
+            return
         z_max = 0.9999 * self.ahat ** (-1.0 / self.bhat)
         t_hubble = self.cube.ssps.par_edges[1][-1]
         t_dep = np.logspace(np.log10(t_dep_lim[0]), np.log10(t_dep_lim[1]), n_t_dep)
@@ -128,20 +197,13 @@ class ParametricComponent(base.Component):
         for i in range(n_t_dep):
             z_of_t[i] = np.interp(t_ssps, t_of_z[i], z)
         self.z_t_interp_grid = dict(t=t_ssps, z=z_of_t, t_dep=t_dep)
+        self.cube.__dict__[key] = (self.t, self.z_t_interp_grid)
 
-    def evaluate_chemical_enrichment_model_base(self, t_dep):
-        """log p(z|t,x) for a map of depletion times t_dep[x1,x2] (parametric.py:253-289).
-
-        Linear metallicity is Gaussian about the tabulated mean with variance a z^b, binned
-        onto the SSP metallicity edges and normalised over the grid."""
+    def _enrichment_table(self, rows):
+        """log p(z | t, row) [z, t, len(rows)] for rows of the tabulated depletion-time grid
+        (parametric.py:253-289): linear metallicity is Gaussian about the tabulated mean with
+        variance a z^b, binned onto the SSP metallicity edges and normalised over the grid."""
         grid = self.z_t_interp_grid
-        nearest = np.argmin(np.abs(t_dep[:, :, None] - grid["t_dep"]), axis=-1)
-        # p(z|t,x) depends on x only through the tabulated depletion time nearest to t_dep[x]:
-        # evaluate the model once per distinct table row and gather (same arithmetic per element
-        # as the reference, which works on the full [z+1, t, x1, x2] arrays - bit-identical, and
-        # 10-100x less work for maps with few distinct depletion times)
-        rows, inverse = np.unique(nearest.ravel(), return_inverse=True)
-        inverse = inverse.reshape(nearest.shape)
         z_mu = grid["z"][rows].T                                          # [t, row]
         z_sd = (self.ahat * z_mu ** self.bhat) ** 0.5
         lin_z_edges = 10.0 ** self.cube.ssps.par_edges[0]
@@ -152,11 +214,24 @@ class ParametricComponent(base.Component):
         log_P = _log_diff_exp(log_cdf[1:], log_cdf[:-1])                  # [z, t, row]
         log_dz = np.log(self.cube.construct_volume_element("z"))
         log_norm = special.logsumexp(log_P.T + log_dz, -1).T
-        log_p_z_t_row = log_P - log_norm
+        return log_P - log_norm
+
+    def evaluate_chemical_enrichment_model_base(self, t_dep):
+        """log p(z|t,x) for a map of depletion times t_dep[x1,x2] (parametric.py:253-289)."""
+        grid = self.z_t_interp_grid
+        nearest = np.argmin(np.abs(t_dep[:, :, None] - grid["t_dep"]), axis=-1)
+        # p(z|t,x) depends on x only through the tabulated depletion time nearest to t_dep[x]:
+        # evaluate the model once per distinct table row and gather (same arithmetic per element
+        # as the reference, which works on the full [z+1, t, x1, x2] arrays - bit-identical, and
+        # 10-100x less work for maps with few distinct depletion times)
+        rows, inverse = np.unique(nearest.ravel(), return_inverse=True)
+        inverse = inverse.reshape(nearest.shape)
+        log_p_z_t_row = self._enrichment_table(rows)
         return log_p_z_t_row[:, :, inverse], np.exp(log_p_z_t_row)[:, :, inverse]   # [z, t, x1, x2]
 
     def set_p_z_tx(self):
-        self.log_p_z_tx, self.p_z_tx = self.evaluate_chemical_enrichment_model_base(self.t_dep)
+        self.__dict__["log_p_z_tx"], self.__dict__["p_z_tx"] = \
+            self.evaluate_chemical_enrichment_model_base(self.t_dep)
 
     def evaluate_chemical_enrichment_model(self, t_dep):
         """p(z|t) for one spatially constant depletion time."""
@@ -247,6 +322,10 @@ class ParametricComponent(base.Component):
         if batch not in ("none", "column", "spaxel"):
             raise ValueError("Unknown option for batch")
         plan = engine.get_plan(self.cube, device=device)
+        maps = self._device_maps(device)
+        if maps is not None:                           # P(t,x,z), mu_v, sig_v generated in HBM
+            self.ybar = plan.ybar_gaussian(maps["P_txz"], maps["mu_v"], maps["sig_v"]).cpu().numpy()
+            return
         P_txz = self.get_p("txz", density=False)
         self.ybar = plan.ybar_gaussian(P_txz, self.mu_v, self.sig_v)
 
@@ -256,11 +335,17 @@ class ParametricComponent(base.Component):
 
         The reference builds log p(t,v,x,z) on the host (parametric.py:567-596: normal-cdf
         differences over the velocity bins, parametric.py:180-211) - 20.8 GB at 201x201 pixels.
-        Here only log p(t,x,z), mu_v and sig_v cross PCIe; pkm_pixelate_gaussian writes the 5-D
+        Here log p(t,x,z), mu_v and sig_v are generated in HBM from the model parameters (or, for
+        classes without a device generator, cross PCIe); pkm_pixelate_gaussian writes the 5-D
         array into HBM, where `evaluate_ybar`, `get_p` and the moments of the returned
         `Component` read it without a host round trip."""
-        log_p_txz = self._log_marginal("txz", density=True, light_weighted=False)
-        log_p = engine.pixelate_gaussian(log_p_txz, self.mu_v, self.sig_v, self.cube.v_edg,
+        maps = self._device_maps(device)
+        if maps is not None:
+            log_p_txz, mu_v, sig_v = maps["log_p_txz"], maps["mu_v"], maps["sig_v"]
+        else:
+            log_p_txz = self._log_marginal("txz", density=True, light_weighted=False)
+            mu_v, sig_v = self.mu_v, self.sig_v
+        log_p = engine.pixelate_gaussian(log_p_txz, mu_v, sig_v, self.cube.v_edg,
                                          density=True, device=device, on_device=True)
         return base.Component(cube=self.cube, log_p_tvxz=log_p)
 

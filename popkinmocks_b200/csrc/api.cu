@@ -378,10 +378,32 @@ static void pipe_init(pkm_plan* pl) {
 // ----------------------------------------------------------------------------
 // cube_npix > 0: cube layout written into a larger cube [n_fft][cube_npix] at pixel offset
 // cube_pix0 (local or peer device memory); otherwise the output covers exactly the rows asked for.
+static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
+                            int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
+                            int32_t out_layout, int64_t cube_npix, int64_t cube_pix0, void* stream);
+
 static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
                             int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
                             int32_t out_layout, int64_t cube_npix, int64_t cube_pix0, void* stream) {
+  const int32_t rc = density_body(pl, dens, is_log, nx1, nx2, row_begin, row_end, ybar_out, out_layout, cube_npix,
+                                  cube_pix0, stream);
+  if (rc != PKM_OK && pl) {
+    // a failure in the middle of the tile loop may leave asynchronous copies on the caller's host
+    // buffers in flight: drain the plan's streams before handing the buffers back
+    if (pl->s_copy) cudaStreamSynchronize(pl->s_copy);
+    if (pl->s_comp) cudaStreamSynchronize(pl->s_comp);
+    if (pl->s_k2) cudaStreamSynchronize(pl->s_k2);
+    cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, int32_t nx1,
+                            int32_t nx2, int32_t row_begin, int32_t row_end, double* ybar_out,
+                            int32_t out_layout, int64_t cube_npix, int64_t cube_pix0, void* stream) {
   return guarded([&] {
+    PkmRange range_call("pkm_ybar_density");
     PKM_REQUIRE(pl && dens && ybar_out, "null argument");
     PKM_REQUIRE(nx1 >= 1 && nx2 >= 1 && row_begin >= 0 && row_end <= nx1 && row_begin <= row_end,
                 "bad pixel range rows [%d,%d) of %d x %d", row_begin, row_end, nx1, nx2);
@@ -430,6 +452,7 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
     for (int64_t p0 = 0; p0 < npix; p0 += tile, ++it) {
       const int np = (int)std::min<int64_t>(tile, npix - p0);
       const int slot = (int)(it & 1);
+      PkmRange range_tile("pkm density tile: coeff + contract + irfft");
       const double* src = dens;
       int64_t src_npix = npix_total, src_pix0 = pix_begin + p0;
       if (in_host) {
@@ -595,6 +618,7 @@ extern "C" int32_t pkm_ybar_gaussian(pkm_plan* pl, const double* P_txz, const do
                                      int32_t nx1, int32_t nx2, int32_t row_begin, int32_t row_end,
                                      double* ybar_out, int32_t out_layout, void* stream) {
   return guarded([&] {
+    PkmRange range_call("pkm_ybar_gaussian");
     PKM_REQUIRE(pl && P_txz && mu_v && sig_v && omega && ybar_out && mu_strides && sig_strides, "null argument");
     PKM_REQUIRE(nx1 >= 1 && nx2 >= 1 && row_begin >= 0 && row_end <= nx1 && row_begin <= row_end,
                 "bad pixel range rows [%d,%d) of %d x %d", row_begin, row_end, nx1, nx2);
@@ -839,6 +863,7 @@ extern "C" int32_t pkm_reduce_logp_multi(pkm_plan* pl, const double* log_p_tvxz,
                                          const uint32_t* keep_masks, const int32_t* density,
                                          double* const* outs, void* stream) {
   return guarded([&] {
+    PkmRange range_call("pkm_reduce_logp");
     PKM_REQUIRE(pl && log_p_tvxz && log_dv && keep_masks && density && outs && npix >= 1 && n_out >= 1 && n_out <= 16,
                 "bad argument");
     use_device(pl->d.device);
@@ -988,6 +1013,7 @@ extern "C" int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t 
                              uint64_t offset, double ybar_max, double* yobs, double* sigma_out,
                              int32_t device, void* stream) {
   return guarded([&] {
+    PkmRange range_call("pkm_noise");
     PKM_REQUIRE(ybar && n >= 1 && (yobs || sigma_out), "bad argument");
     PKM_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (ShotNoise) or 1 (ConstantSNR)");
     if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
@@ -1025,6 +1051,112 @@ extern "C" int32_t pkm_noise(const double* ybar, int64_t n, double snr, int32_t 
     }
     PKM_CUDA(cudaStreamSynchronize(st));
     buf.release();
+  });
+}
+
+// ----------------------------------------------------------------------------
+// parametric-model maps on the device
+// ----------------------------------------------------------------------------
+namespace {
+// small host arrays -> one device scratch buffer; returns device pointers in order
+struct Staged {
+  DevBuf buf;
+  std::vector<const double*> ptr;
+};
+void stage_small(Staged& s, std::initializer_list<std::pair<const double*, size_t>> arrays, cudaStream_t st) {
+  size_t total = 0;
+  for (auto& a : arrays) total += a.second;
+  std::vector<double> h;
+  h.reserve(total);
+  for (auto& a : arrays) h.insert(h.end(), a.first, a.first + a.second);
+  s.buf.reserve(sizeof(double) * std::max<size_t>(total, 1));
+  PKM_CUDA(cudaMemcpyAsync(s.buf.p, h.data(), sizeof(double) * total, cudaMemcpyHostToDevice, st));
+  PKM_CUDA(cudaStreamSynchronize(st));   // h is a local
+  size_t off = 0;
+  for (auto& a : arrays) {
+    s.ptr.push_back(s.buf.as<double>() + off);
+    off += a.second;
+  }
+}
+int sm_count(int device) {
+  cudaDeviceProp prop;
+  PKM_CUDA(cudaGetDeviceProperties(&prop, device));
+  return prop.multiProcessorCount;
+}
+}  // namespace
+
+extern "C" int32_t pkm_disk_maps(const double* x1, const double* x2, int32_t nx1, int32_t nx2, double cx, double cy,
+                                 double rotation, const double* age_pars, int32_t nt, double scale,
+                                 const double* t_dep_pars, const double* t_dep_grid, int32_t ngrid,
+                                 double* log_p_x_t, double* mu_v, double* sig_v, double* t_dep, int32_t* row_idx,
+                                 double log_dxdy, int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(x1 && x2 && age_pars && log_p_x_t && mu_v && sig_v && nx1 >= 1 && nx2 >= 1 && nt >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    PKM_REQUIRE(pkm_is_device_pointer(log_p_x_t) && pkm_is_device_pointer(mu_v) && pkm_is_device_pointer(sig_v),
+                "outputs must be device buffers");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nsm = sm_count(device);
+    Staged sm;
+    stage_small(sm, {{x1, (size_t)nx1}, {x2, (size_t)nx2}, {age_pars, (size_t)10 * nt},
+                     {t_dep_grid ? t_dep_grid : x1, (size_t)(t_dep_grid ? ngrid : 0)}}, st);
+    ModelFrame mf{cx, cy, std::cos(rotation), std::sin(rotation), nx1, nx2};
+    const int64_t npix = (int64_t)nx1 * nx2;
+    launch_disk_maps(mf, sm.ptr[0], sm.ptr[1], sm.ptr[2], nt, scale, log_p_x_t, mu_v, sig_v, nsm, st);
+    launch_normalise_rows(log_p_x_t, nt, npix, log_dxdy, st);
+    if (t_dep && row_idx) {
+      PKM_REQUIRE(t_dep_pars && t_dep_grid && ngrid >= 1, "t_dep needs its parameters and the tabulated grid");
+      PKM_REQUIRE(pkm_is_device_pointer(t_dep) && pkm_is_device_pointer(row_idx), "outputs must be device buffers");
+      launch_disk_t_dep(mf, sm.ptr[0], sm.ptr[1], t_dep_pars[0], t_dep_pars[1], t_dep_pars[2], t_dep_pars[3], scale,
+                        sm.ptr[3], ngrid, t_dep, row_idx, nsm, st);
+    }
+    PKM_CUDA(cudaStreamSynchronize(st));   // the staging buffer dies with this frame
+  });
+}
+
+extern "C" int32_t pkm_stream_maps(const double* x1, const double* x2, int32_t nx1, int32_t nx2, double cx, double cy,
+                                   double rotation, const double* centres_x, const double* centres_y, int32_t nsmp,
+                                   double sig, double half_dx, double half_dy, double theta_lo, double theta_hi,
+                                   double v_lo, double v_hi, double* log_p_x, double* mu_v, double log_dxdy,
+                                   int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(x1 && x2 && centres_x && centres_y && log_p_x && mu_v && nx1 >= 1 && nx2 >= 1 && nsmp >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    PKM_REQUIRE(pkm_is_device_pointer(log_p_x) && pkm_is_device_pointer(mu_v), "outputs must be device buffers");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Staged sm;
+    stage_small(sm, {{x1, (size_t)nx1}, {x2, (size_t)nx2}, {centres_x, (size_t)nsmp}, {centres_y, (size_t)nsmp}}, st);
+    ModelFrame mf{cx, cy, std::cos(rotation), std::sin(rotation), nx1, nx2};
+    launch_stream_maps(mf, sm.ptr[0], sm.ptr[1], sm.ptr[2], sm.ptr[3], nsmp, sig, half_dx, half_dy, theta_lo, theta_hi,
+                       v_lo, v_hi, log_p_x, mu_v, sm_count(device), st);
+    launch_normalise_rows(log_p_x, 1, (int64_t)nx1 * nx2, 0.0, st);   // mass normalised to one over the cube ...
+    PKM_CUDA(cudaStreamSynchronize(st));
+    (void)log_dxdy;
+  });
+}
+
+extern "C" int32_t pkm_assemble_txz(const double* log_P_t, const double* log_dt, const double* log_p_x,
+                                    int32_t px_per_age, double log_dxdy, const double* log_Pz_rows, int32_t nrow,
+                                    const double* log_dz, const int32_t* row_idx, int32_t nt, int64_t npix,
+                                    int32_t nz, double* P_txz, double* log_p_txz, int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(log_P_t && log_dt && log_p_x && log_Pz_rows && log_dz && (P_txz || log_p_txz) && nt >= 1 && npix >= 1 &&
+                nz >= 1 && nrow >= 1, "bad argument");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    PKM_REQUIRE(pkm_is_device_pointer(log_p_x) && (!row_idx || pkm_is_device_pointer(row_idx)) &&
+                (!P_txz || pkm_is_device_pointer(P_txz)) && (!log_p_txz || pkm_is_device_pointer(log_p_txz)),
+                "maps and outputs must be device buffers");
+    PKM_REQUIRE(row_idx || nrow == 1, "several enrichment rows need a row index map");
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Staged sm;
+    stage_small(sm, {{log_P_t, (size_t)nt}, {log_dt, (size_t)nt}, {log_Pz_rows, (size_t)nrow * nt * nz},
+                     {log_dz, (size_t)nz}}, st);
+    launch_assemble_txz(sm.ptr[0], sm.ptr[1], log_p_x, px_per_age ? npix : 0, log_dxdy, sm.ptr[2], sm.ptr[3],
+                        reinterpret_cast<const int*>(row_idx), nt, npix, nz, P_txz, log_p_txz, sm_count(device), st);
+    PKM_CUDA(cudaStreamSynchronize(st));
   });
 }
 
@@ -1117,6 +1249,7 @@ extern "C" int32_t pkm_pixelate_gaussian(const double* log_w_txz, const double* 
                                          int32_t nz, int32_t density, double* out, int32_t device,
                                          void* stream) {
   return guarded([&] {
+    PkmRange range_call("pkm_pixelate_gaussian");
     PKM_REQUIRE(log_w_txz && mu_v && sig_v && v_edg && out, "bad argument");
     PKM_REQUIRE(nt >= 1 && nv >= 1 && npix >= 1 && nz >= 1, "bad shape");
     if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");

@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libpkm_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -44,6 +45,10 @@ void pkm_set_error(const std::string& msg);
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }        // a throw between reserve() and the explicit release() must not leak
   void reserve(size_t bytes);
   void release();
   template <class T>
@@ -224,6 +229,26 @@ void launch_pixelate(const double* log_w, const double* mu, const double* sig, c
                      cudaStream_t st);
 void launch_synth_logp(double* out, int nt, int nv, int64_t total_pix, int64_t pix0, int64_t npix, int nz,
                        uint64_t seed, double scale, int num_sms, cudaStream_t st);
+// parametric-model maps (model_kernels.cu)
+struct ModelFrame {
+  double cx, cy, c, s;   // centre, cos / sin of the rotation
+  int nx1, nx2;
+};
+void launch_disk_maps(const ModelFrame& mf, const double* d_x1, const double* d_x2, const double* d_age_pars,
+                      int nt, double scale, double* log_rho, double* mu_v, double* sig_v, int num_sms,
+                      cudaStream_t st);
+void launch_disk_t_dep(const ModelFrame& mf, const double* d_x1, const double* d_x2, double q, double alpha,
+                       double t_in, double t_out, double scale, const double* d_grid, int ngrid, double* t_dep,
+                       int* row, int num_sms, cudaStream_t st);
+void launch_stream_maps(const ModelFrame& mf, const double* d_x1, const double* d_x2, const double* d_cx,
+                        const double* d_cy, int nsmp, double sig, double hwx, double hwy, double th_lo,
+                        double th_hi, double v_lo, double v_hi, double* log_p, double* mu_v, int num_sms,
+                        cudaStream_t st);
+void launch_normalise_rows(double* a, int nrow, int64_t ncol, double log_cell, cudaStream_t st);
+void launch_assemble_txz(const double* d_log_P_t, const double* d_log_dt, const double* log_px,
+                         int64_t px_age_stride, double log_dxdy, const double* d_log_Pz, const double* d_log_dz,
+                         const int* row, int nt, int64_t npix, int nz, double* P_txz, double* log_p_txz,
+                         int num_sms, cudaStream_t st);
 bool pkm_is_device_pointer(const void* p);
 
 // RAII CUDA-event bracket of one launch on its own stream (no-op unless plan->profiling)
@@ -244,5 +269,13 @@ struct KernelTimer {
     cudaEventRecord(t.e1, st);
     pl->timed.push_back(t);
   }
+};
+// NVTX range (header-only NVTX 3: a no-op unless a profiler is attached) around the hot-path calls,
+// so nsys / ncu timelines show the entry points and their per-tile kernel groups by name
+struct PkmRange {
+  explicit PkmRange(const char* name) { nvtxRangePushA(name); }
+  ~PkmRange() { nvtxRangePop(); }
+  PkmRange(const PkmRange&) = delete;
+  PkmRange& operator=(const PkmRange&) = delete;
 };
 double run_fma_probe(int num_sms, int repeats);  // TFLOP/s

@@ -768,7 +768,8 @@ k_hist5d(const double* __restrict__ s0, const double* __restrict__ s1, const dou
   }
 }
 
-__global__ void k_u64_to_f64(const unsigned long long* __restrict__ in, double* __restrict__ out, long long n) {
+// converts in place (in == out): no __restrict__
+__global__ void k_u64_to_f64(const unsigned long long* in, double* out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) out[i] = (double)in[i];
 }

@@ -470,3 +470,56 @@ def test_nan_and_empty_densities_through_both_coefficient_kernels(gpu_ok, monkey
         ref = R.ybar_density_literal(np.exp(logp[:, :, :, 16:19]), cube.v_edg, s.FXw, s.par_dims, s.n_fft, s.dv,
                                      s.delta_t, s.delta_z, cube.dx, cube.dy)
     assert rel_err(res["1"][:, :, 16:19], ref) < TOL
+
+
+@pytest.mark.parametrize("tag", ["d1_", "d2_", "s1_"])
+def test_device_model_maps_match_the_host_maps(gpu_ok, tag):
+    """pkm_disk_maps / pkm_stream_maps / pkm_assemble_txz: the O(pixels) inputs of the Gaussian
+    path generated in HBM from the model parameters agree with the host (reference-formula) arrays
+    to <= 1e-12, and with the reference's own arrays in the golden file."""
+    cube = pkm.ifu_cube.IFUCube(ssps=golden_cube(G1).ssps, nx1=13, nx2=9, nv=41, vrng=(-1000.0, 1000.0))
+    comp = BUILDERS[tag](cube)
+    maps = comp._device_maps(0)
+    assert maps is not None
+    for lazy in ("mu_v", "sig_v", "log_p_x_t", "log_p_z_tx", "t_dep"):
+        assert lazy not in comp.__dict__, lazy             # nothing of size nx1*nx2 was built on the host
+    mu = np.broadcast_to(maps["mu_v"].cpu().numpy(), comp.mu_v.shape)
+    sg = np.broadcast_to(maps["sig_v"].cpu().numpy(), comp.sig_v.shape)
+    assert np.max(np.abs(mu - comp.mu_v)) < 1e-12 * max(1.0, np.max(np.abs(comp.mu_v)))
+    assert np.max(np.abs(sg - comp.sig_v)) < 1e-12 * np.max(np.abs(comp.sig_v))
+    P_host = comp.get_p("txz", density=False)
+    assert rel_err(maps["P_txz"].cpu().numpy(), P_host) < 1e-12
+    logp_host = comp.get_log_p("txz", density=True)
+    # log domain on the bulk; far from a stream the pixel masses are differences of nearly equal
+    # cdfs, where one ulp of log_ndtr is a 1e-8 relative change of a 1e-30 probability
+    ok = np.isfinite(logp_host) & (logp_host > np.max(logp_host) - 25.0)
+    # (pixels on the far side of every stream sample integrate the UPPER tail of the normal cdf,
+    # where the reference's own log-cdf difference carries ~1e-7 relative noise: looser there)
+    assert np.allclose(maps["log_p_txz"].cpu().numpy()[ok], logp_host[ok], rtol=0,
+                       atol=1e-10 if tag != "s1_" else 1e-6)
+    assert rel_err(np.exp(maps["log_p_txz"].cpu().numpy()), np.exp(logp_host)) < 1e-12
+    if maps["t_dep"] is not None:
+        assert np.max(np.abs(maps["t_dep"].cpu().numpy() - comp.t_dep)) < 1e-13
+        grid = comp.z_t_interp_grid["t_dep"]
+        nearest = np.argmin(np.abs(comp.t_dep[:, :, None] - grid), axis=-1)
+        got = maps["row_idx"].cpu().numpy() + int(maps["rows"][0])
+        # a pixel exactly half way between two table rows may round either way after one ulp in t_dep
+        differ = got != nearest
+        assert differ.mean() < 0.02
+        assert np.all(np.abs(np.abs(comp.t_dep[differ] - grid[got[differ]])
+                             - np.abs(comp.t_dep[differ] - grid[nearest[differ]])) < 1e-12)
+    # and the hot path fed by them reproduces the reference cube
+    g = load_golden(G1)
+    small = BUILDERS[tag](golden_cube(G1))
+    small.evaluate_ybar()
+    assert "mu_v" not in small.__dict__
+    assert rel_err(small.ybar, g[tag + "ybar"]) < TOL
+    tw = small.pixelate()
+    ref = small.get_log_p("tvxz", density=True)
+    got = tw.log_p_tvxz.cpu().numpy()
+    # bins within 1e-4 of the cell's peak bin in the log domain, everything in the p domain (the far
+    # upper tail of the reference's signed logsumexp is quantised, see the pixelation test above)
+    with np.errstate(invalid="ignore"):
+        bulk = ref > ref.max(axis=1, keepdims=True) + np.log(1e-4)
+    assert np.max(np.abs(got[bulk] - ref[bulk])) < 1e-10
+    assert rel_err(np.exp(got), np.exp(ref)) < 1e-13
