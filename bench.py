@@ -477,14 +477,52 @@ def run_b200(args):
         P /= P.sum()
         mu_v = 400.0 * (torch.rand((nt, rows, nxl), dtype=torch.float64, device=dev, generator=gen) - 0.5)
         sig_v = 20.0 + 200.0 * torch.rand((nt, rows, nxl), dtype=torch.float64, device=dev, generator=gen)
+        hbm_peak_o = 6650.0
+        try:
+            hbm_peak_o = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:  # noqa: BLE001
+            pass
+
+        def hbm_roof(nbytes, ms):
+            return {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak_o, "unit": "GB/s",
+                    "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak_o}
+
         ms = timed(lambda: plan.ybar_gaussian(P, mu_v, sig_v, out=out))
+        # executed FP64 work of path A per (k, t, x): 2*nz FMAs of the metallicity contraction (complex x
+        # real), a 6-operation recurrence for exp(-i mu w - sig^2 w^2 / 2) and a complex multiply-add
+        flops_a = (n_fft // 2 + 1) * nt * (4.0 * nz + 14.0) * npix
         other["gaussian_path_A"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
-                                    "ref": "ParametricComponent.evaluate_ybar parametric.py:335-407"}
+                                    "ref": "ParametricComponent.evaluate_ybar parametric.py:335-407",
+                                    "roofline": {"bound": "fp64", "achieved": flops_a / (ms * 1e-3) / 1e12,
+                                                 "peak": fp64_peak, "unit": "TFLOP/s",
+                                                 "frac": flops_a / (ms * 1e-3) / 1e12 / fp64_peak,
+                                                 "note": "executed flops (the kernel replaces SURVEY 8d's 68 nt "
+                                                         "transcendental flops per frequency by a recurrence); "
+                                                         "includes the inverse FFT and the transpose"}}
+        # the same path from the model PARAMETERS: construction + device maps + evaluate_ybar, wall clock
+        import popkinmocks_b200 as pkm_
+        import bench_workloads as W_
+
+        def model_wall(make):
+            make(cube).evaluate_ybar(device=local)            # warm (tables cached on the cube)
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            c_ = make(cube)
+            c_.evaluate_ybar(device=local)
+            return 1e3 * (time.perf_counter() - t0_)
+        other["growing_disk_setup_plus_evaluate_ybar"] = {
+            "ms": model_wall(W_.make_disk), "note": "GrowingDisk(cube) + set_p_t/set_p_x_t/set_t_dep/set_mu_v/"
+            "set_sig_v + evaluate_ybar() wall clock: the O(pixels) maps are generated in HBM (pkm_disk_maps, "
+            "pkm_assemble_txz); includes the D2H of the 1.6 GB cube into a pageable NumPy array",
+            "ref": "growing_disk.py:30-239, parametric.py:335-407"}
+        other["stream_setup_plus_evaluate_ybar"] = {
+            "ms": model_wall(W_.make_stream), "ref": "stream.py:28-138, parametric.py:335-407"}
         # analytic pixelation of the same Gaussian component into a second 5-D device array
         log_w = torch.log(P)
         pix = torch.empty_like(logp)
         ms = timed(lambda: engine.pixelate_gaussian(log_w, mu_v, sig_v, cube.v_edg, device=local, out=pix))
         other["pixelate_gaussian"] = {"ms": ms, "GB_per_s": pix.numel() * 8 / (ms * 1e-3) / 1e9,
+                                      "roofline": hbm_roof(pix.numel() * 8, ms),
                                       "note": "pkm_pixelate_gaussian: writes log p(t,v,x,z) once (HBM-write bound)",
                                       "ref": "ParametricComponent._get_log_p_tvxz parametric.py:567-596"}
         del P, mu_v, sig_v, log_w, pix
@@ -500,11 +538,13 @@ def run_b200(args):
             ms = timed(lambda: plan.reduce_logp(logp, log_dv, keep, False))
             other["log_marginal_" + keep] = {
                 "ms": ms, "GB_per_s": logp.numel() * 8 / (ms * 1e-3) / 1e9,
+                "roofline": hbm_roof(logp.numel() * 8, ms),
                 "note": "pkm_reduce_logp: one streaming pass (online log-sum-exp) over the 5-D array; "
-                        "one exp per element makes it FP64-pipe bound, not HBM bound",
+                        "one table exponential per element: issue/FP64 bound at about half the HBM rate",
                 "ref": ref}
         ms = timed(lambda: engine.noise(out, 100.0, 0, seed=1, want_sigma=False))
         other["shot_noise"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
+                               "roofline": hbm_roof(3 * out.numel() * 8, ms),   # max pass + read + write
                                "ref": "ShotNoise.get_noisy_data noise.py:16-71"}
         # the same cube over the full MILES wavelength range (3540-7410 A): n_fft = 11179 = 7*1597,
         # 2.3x more voxels per pixel; the inverse FFT no longer fits shared memory (M = 32768)

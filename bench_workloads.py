@@ -155,9 +155,21 @@ def run_c2(nx=51, nv=101, steps=10, warmup=3, device=0, e2e_steps=3):
     med_ab = float(np.median(np.abs(y_a / y_b - 1.0)))                            # tests/test_all.py:103-115
 
     # ---- the class API with host arrays
-    e2e_ms = _wall(lambda: disk.evaluate_ybar(device=device), e2e_steps)
-    err_api = _rel(disk.ybar, y_a)
-    flops_vox = plan.nfo * (4.0 * nt * nz + 68.0 * nt) / plan.n_fft               # SURVEY.md 8d, path A
+    # model parameters -> host cube: construction, device maps, kernels, D2H (nothing is cached
+    # between steps: every step builds a fresh GrowingDisk)
+    holder = {}
+
+    def api_step():
+        holder["disk"] = make_disk(cube)
+        holder["disk"].evaluate_ybar(device=device)
+    e2e_ms = _wall(api_step, e2e_steps)
+    err_api = _rel(holder["disk"].ybar, y_a)
+    n_rows = int(holder["disk"]._device_maps(device)["rows"].size)
+    h2d_bytes = 8 * (10 * nt + cube.nx + cube.ny + 1000 + 2 * nt + n_rows * nt * nz + nz)
+    # executed FP64 work per voxel: per (k, t, x) 2*nz FMAs of the metallicity contraction, a 6-operation
+    # recurrence for exp(-i mu w - sig^2 w^2/2) and a complex multiply-add (SURVEY.md 8d counts 68 nt
+    # flops per frequency for evaluating the exponential directly: 3.1 kFLOP/voxel algorithmic)
+    flops_vox = plan.nfo * nt * (4.0 * nz + 14.0) / plan.n_fft
     fp64_peak = engine.fp64_fma_peak(device)
     k_ms = kt["gaussian"][0] / max(kt["gaussian"][1], 1)
     return {
@@ -168,15 +180,17 @@ def run_c2(nx=51, nv=101, steps=10, warmup=3, device=0, e2e_steps=3):
                          "partly stay in L2 between steps, as they would for a user looping over models"},
         "voxels": voxels, "ms_per_step": ms, "value": voxels / (ms * 1e-3), "launches": int(launches),
         "e2e": {"value": voxels / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(P_txz.nbytes + 2 * disk.mu_v.nbytes),
-                "d2h_bytes_per_step": int(disk.ybar.nbytes), "steps": e2e_steps,
-                "api": "GrowingDisk.evaluate_ybar() (host maps -> host cube; includes get_p('txz') on the host)"},
+                "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(holder["disk"].ybar.nbytes), "steps": e2e_steps,
+                "api": "GrowingDisk(cube); set_p_t/set_p_x_t/set_t_dep/set_mu_v/set_sig_v; evaluate_ybar() - "
+                       "model parameters in, host cube out; the O(pixels) maps are generated in HBM, so the "
+                       "H2D traffic is the O(nt) parameter vectors and the enrichment table rows"},
         "roofline": {"bound": "fp64", "kernel": "k_gaussian", "achieved": flops_vox * voxels / (k_ms * 1e-3) / 1e12,
                      "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": flops_vox * voxels / (k_ms * 1e-3) / 1e12 / fp64_peak, "traffic": None,
                      "flops_per_voxel": flops_vox, "peak_source": "pkm_fp64_fma_peak measured in this run",
-                     "note": "SURVEY.md 8d algorithmic FP64 work of path A (3.1 kFLOP/voxel); the kernel "
-                             "spends part of it on the FP64 tensor cores (DMMA)"},
+                     "note": "executed FP64 work (1.6 kFLOP/voxel; SURVEY.md 8d's algorithmic figure is 3.1); "
+                             "the metallicity contraction runs on the FP64 tensor cores (DMMA)"},
         "kernels": {k: {"ms_per_step": m / steps, "launches_per_step": c / steps} for k, (m, c) in kt.items() if c},
         "other_paths": {"density_path_B_on_pixelated_twin": {"ms": ms_b, "voxel_per_s": voxels / (ms_b * 1e-3)},
                         "host_model_setup_s": setup_s},

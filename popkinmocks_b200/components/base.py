@@ -362,23 +362,29 @@ class Component(object):
         plan = engine.get_plan(self.cube, device=device, precision=dtype)
         src = self.log_p_tvxz
         cached = self.__dict__.get("_pkm_dev")
-        if engine._is_cuda_tensor(src):
-            self.ybar = plan.ybar_density(src, is_log=True).cpu().numpy()
-            return
-        if cached is not None and cached[0] is src and cached[1] == device:
-            self.ybar = plan.ybar_density(cached[2], is_log=True).cpu().numpy()
+        if engine._is_cuda_tensor(src) or (cached is not None and cached[0] is src and cached[1] == device):
+            dev_src = src if engine._is_cuda_tensor(src) else cached[2]
+            out = self._new_host_cube(plan.n_fft)
+            plan.ybar_density(dev_src, is_log=True, out=out)
+            self.ybar = out
             return
         # the reference evaluates get_p('tvxz') = exp(log p + log dV - log dV); exp is fused
         host = np.ascontiguousarray(src, dtype=np.float64)
         engine.pin_host_array(host)
-        # drop the previous result first so that its page-locked block can be reused (it is not,
-        # and stays valid, if the caller still holds the old array)
+        out = self._new_host_cube(plan.n_fft)
+        plan.ybar_density(host, is_log=True, out=out)
+        self.ybar = out
+
+    def _new_host_cube(self, n_fft):
+        """A page-locked [n_fft, nx1, nx2] result buffer (torch's caching host allocator), viewed as
+        a NumPy array: device-to-host copies into it run at PCIe rate.  The previous result is
+        dropped first so that its block can be reused (it is not, and stays valid, if the caller
+        still holds the old array)."""
         self.__dict__.pop("ybar", None)
         self.__dict__.pop("_pkm_ybar_pin", None)
-        keep, out = engine.pinned_empty((plan.n_fft, self.cube.nx, self.cube.ny))
-        plan.ybar_density(host, is_log=True, out=out)
+        keep, out = engine.pinned_empty((n_fft, self.cube.nx, self.cube.ny))
         self.__dict__["_pkm_ybar_pin"] = keep
-        self.ybar = out
+        return out
 
     # ------------------------------------------------------------------ persistence
     def dill_dump(self, fname, direc=None):

@@ -323,11 +323,12 @@ class ParametricComponent(base.Component):
             raise ValueError("Unknown option for batch")
         plan = engine.get_plan(self.cube, device=device)
         maps = self._device_maps(device)
+        out = self._new_host_cube(plan.n_fft)
         if maps is not None:                           # P(t,x,z), mu_v, sig_v generated in HBM
-            self.ybar = plan.ybar_gaussian(maps["P_txz"], maps["mu_v"], maps["sig_v"]).cpu().numpy()
-            return
-        P_txz = self.get_p("txz", density=False)
-        self.ybar = plan.ybar_gaussian(P_txz, self.mu_v, self.sig_v)
+            plan.ybar_gaussian(maps["P_txz"], maps["mu_v"], maps["sig_v"], out=out)
+        else:
+            plan.ybar_gaussian(self.get_p("txz", density=False), self.mu_v, self.sig_v, out=out)
+        self.ybar = out
 
     def pixelate(self, device=0):
         """The pixelated twin of this component, `Component(cube, self.get_log_p("tvxz"))`, with

@@ -339,7 +339,7 @@ def axpy_cubes(ybars, weights, device=0):
         out = torch.empty_like(ybars[0])
     else:
         ybars = [_lib.as_f64(y) for y in ybars]
-        out = np.empty_like(ybars[0])
+        out = pinned_empty(ybars[0].shape)[1]          # page-locked: the D2H of the sum runs at PCIe rate
     n = int(np.prod(ybars[0].shape))
     ptrs = (C.c_void_p * len(ybars))(*[_lib.ptr(y) for y in ybars])
     w = _lib.as_f64(weights)
