@@ -426,13 +426,50 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
     size_t per_px = sizeof(double2) * (size_t)pl->ntz * pl->nfi + sizeof(double2) * pl->nfo + sizeof(double) * n;
     if (in_host) per_px += 2 * sizeof(double) * (size_t)nt * nv * nz;
     if (out_host) per_px += 2 * sizeof(double) * n;
-    int tile = pixel_tile(pl, npix, per_px);
-    if (in_host || out_host) tile = std::min<int64_t>(tile, ((npix + 7) / 8 + 31) & ~int64_t(31));
-    // embedded (possibly peer-memory) cube: the transposes run on a side stream and overlap the
-    // next tile's kernels, so the NVLink stores of all ranks do not pile up at the end
+    // Pixel tiles.  Upper bound: the workspace; host buffers: at least 8 tiles so that copies and
+    // kernels overlap.  Every tile is sized to a WHOLE number of waves of the contraction kernel
+    // (its CTAs are long: a last, nearly empty wave costs as much as a full one).  Embedded
+    // (possibly peer-memory) cube: the transposes and the NVLink copies run on a side stream behind
+    // the next tile's kernels, so the range is cut into four tiles.
     const bool side_transpose = cube_npix > 0;
-    if (side_transpose) tile = std::min<int64_t>(tile, ((npix + 3) / 4 + 31) & ~int64_t(31));
-    tile = std::max((tile / 32) * 32, 32);  // the coefficient layout groups pixels by 32
+    const int max_pg = std::max(1, pixel_tile(pl, npix, per_px) / 32);
+    const int64_t total_pg = (npix + 31) / 32;
+    const double wave = contract_wave_pixel_groups(pl);
+    // largest whole number of waves within pg pixel groups (a contraction CTA covers 4 groups, so
+    // tiles are whole CTA rows), at least one group
+    auto whole_waves = [&](double pg) -> int {
+      const double m = std::floor(pg / wave);
+      int r = m >= 1.0 ? ((int)std::floor(m * wave) / 4) * 4 : (int)pg;
+      if (r < 1) r = (int)pg;
+      return std::max(1, std::min(r, max_pg));
+    };
+    std::vector<int> sched;                           // pixels per tile
+    {
+      int64_t rem = total_pg;
+      if (side_transpose) {
+        // four near-equal tiles (whole CTA rows): measured best on 8 GPUs - a geometric schedule with
+        // a small last tile (less exposed copy) lost more to half-empty contraction launches
+        const int t = (int)std::min<int64_t>(max_pg, (((total_pg + 3) / 4 + 3) / 4) * 4);
+        while (rem > 0) {
+          sched.push_back((int)std::min<int64_t>(rem, t));
+          rem -= sched.back();
+        }
+      } else {
+        const double want = (in_host || out_host) ? std::min<double>(max_pg, std::ceil(total_pg / 8.0)) : max_pg;
+        const int t = whole_waves(want);
+        while (rem > 0) {
+          sched.push_back((int)std::min<int64_t>(rem, t));
+          rem -= sched.back();
+        }
+      }
+      int64_t left = npix;
+      for (int& t : sched) {                          // pixel groups -> pixels (the last tile may be ragged)
+        t = (int)std::min<int64_t>((int64_t)t * 32, left);
+        left -= t;
+      }
+    }
+    int tile = 32;                                    // the largest tile, padded to whole groups of 32
+    for (int t : sched) tile = std::max(tile, (t + 31) & ~31);
 
     pl->coef.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
     pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
@@ -449,8 +486,8 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
     }
 
     int64_t it = 0;
-    for (int64_t p0 = 0; p0 < npix; p0 += tile, ++it) {
-      const int np = (int)std::min<int64_t>(tile, npix - p0);
+    for (int64_t p0 = 0; p0 < npix; p0 += sched[it], ++it) {
+      const int np = sched[it];
       const int slot = (int)(it & 1);
       PkmRange range_tile("pkm density tile: coeff + contract + irfft");
       const double* src = dens;

@@ -1083,6 +1083,12 @@ k_contract_f32(const float2* __restrict__ Sw, const double* __restrict__ Ww,
   }
 }
 
+double contract_wave_pixel_groups(const pkm_plan* pl) {
+  // resident warps per GPU / warps per pixel group (one warp = one warp segment x 32 pixels)
+  const double warps = (double)pl->num_sms * K2_WARPS * (pl->d.precision == 1 ? 3 : K2_CTAS_PER_SM);
+  return std::max(1e-3, warps / std::max(1, pl->wsegs.nwseg));
+}
+
 // side stream (+ fork / join events) for the alternate launches of one tile, created on first use
 static bool contract_side_stream(pkm_plan* pl) {
   if (pl->s_k2) return true;

@@ -174,6 +174,8 @@ struct pkm_plan {
 void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_total,
                   int64_t pix0, int npix_tile, int xpad, double2* cT, cudaStream_t st);
 // kernel 2: coefficients -> Yhat[x][nfo]
+// pixel groups (of 32) that fill the GPU once with contraction CTAs (real valued)
+double contract_wave_pixel_groups(const pkm_plan* pl);
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
                      cudaStream_t st);
 // gaussian path -> Yhat[x][nfo]
