@@ -311,6 +311,11 @@ def run_b200(args):
     import torch.distributed as dist
     from popkinmocks_b200 import _lib, engine
 
+    # NUMA-local cores for this rank: the page-locked e2e buffers are then allocated next to the GPU
+    numa_cpus = None
+    if world > 1 and not os.environ.get("PKM_BENCH_NO_AFFINITY"):
+        from popkinmocks_b200 import sharding as _sh
+        numa_cpus = _sh.bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -578,12 +583,40 @@ def run_b200(args):
         # the call a user of the reference makes: Component(cube, log_p_tvxz).evaluate_ybar() on a
         # HOST array (page-locked in place by the class on first use), result = a host NumPy cube
         import popkinmocks_b200 as pkm
-        h_in = torch.empty(logp.shape, dtype=torch.float64, pin_memory=True)
-        h_in.copy_(logp)
-        np_in = h_in.numpy()
+        # Multi-GPU: this leg is bound by host-to-device copies, and the GPUs of one box do not all
+        # see the same host bandwidth (tools/h2d_probe.py: PCIe switches shared by 4 GPUs).  The
+        # pixel ranges of the e2e leg are therefore sized in proportion to each rank's MEASURED
+        # concurrent H2D rate (256 MB probe), so that all ranks finish their copies together.
+        e0_, e1_ = r0, r1
+        h2d_rates = None
+        if world > 1 and args.scaling == "strong" and not os.environ.get("PKM_BENCH_EQUAL_E2E"):
+            pb = torch.empty(1 << 25, dtype=torch.float64, pin_memory=True)
+            db = torch.empty(1 << 25, dtype=torch.float64, device=dev)
+            db.copy_(pb, non_blocking=True)
+            barrier()
+            tp0 = time.perf_counter()
+            for _ in range(4):
+                db.copy_(pb, non_blocking=True)
+            torch.cuda.synchronize()
+            rate = torch.tensor([4 * pb.numel() * 8 / (time.perf_counter() - tp0) / 1e9], dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(rate) for _ in range(world)]
+            dist.all_gather(allr, rate)
+            h2d_rates = [float(a) for a in allr]
+            cum = np.concatenate([[0.0], np.cumsum(h2d_rates)]) / sum(h2d_rates)
+            bounds = [int(round(total_pix * c)) for c in cum]
+            e0_, e1_ = bounds[rank], bounds[rank + 1]
+            del pb, db
         del logp
         torch.cuda.empty_cache()
-        cube_e2e = cube if world == 1 else build_cube(args, nx1=rows, nx2=nxl)
+        rows_e = e1_ - e0_ if world > 1 else rows
+        shard = engine.synth_log_density(pix0=e0_, npix=(e1_ - e0_) if world > 1 else npix, device=local, **synth)
+        shard = shard.view(nt, nv, rows_e, nxl, nz)
+        h_in = torch.empty(shard.shape, dtype=torch.float64, pin_memory=True)
+        h_in.copy_(shard)
+        np_in = h_in.numpy()
+        del shard
+        torch.cuda.empty_cache()
+        cube_e2e = cube if world == 1 else build_cube(args, nx1=rows_e, nx2=nxl)
         cube_e2e.dx, cube_e2e.dy = cube.dx, cube.dy     # the shard's pixels ARE the global cube's pixels
         cmp = pkm.components.Component(cube=cube_e2e, log_p_tvxz=np_in)
 
@@ -595,8 +628,11 @@ def run_b200(args):
         e2e_err = None
         if spot_ref is not None and spot_px:
             # the class-API cube must be the cube verified above (rank 0's pixel range of it)
-            got = cmp.ybar.reshape(n_fft, -1)[:, [p - r0 for p in spot_px]]
-            e2e_err = float(np.max(np.abs(got - spot_ref)) / np.max(np.abs(spot_ref)))
+            keep = [i for i, p in enumerate(spot_px) if e0_ <= p < e1_] if world > 1 else list(range(len(spot_px)))
+            if keep:
+                got = cmp.ybar.reshape(n_fft, -1)[:, [spot_px[i] - (e0_ if world > 1 else r0) for i in keep]]
+                ref_ = spot_ref[:, keep]
+                e2e_err = float(np.max(np.abs(got - ref_)) / np.max(np.abs(ref_)))
         w2 = sampler.mark() if sampler else 0
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -610,13 +646,17 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": voxels_per_step * args.e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int(cmp.ybar.size * 8),
+               "h2d_bytes_per_step": int(voxels_per_step // n_fft * nt * nv * nz * 8) if world > 1 else int(h_in.numel() * 8),
+               "d2h_bytes_per_step": int(voxels_per_step * 8) if world > 1 else int(cmp.ybar.size * 8),
+               "h2d_GBps_per_rank_probe": h2d_rates,
+               "pixels_per_rank": ("proportional to the probed H2D rates" if h2d_rates else "equal"),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "api": "popkinmocks_b200.components.Component(cube, log_p_tvxz).evaluate_ybar()",
                "max_rel_diff_vs_device_cube": e2e_err,
                "note": "per rank: host log_p_tvxz (page-locked in place) -> Component.evaluate_ybar -> host "
                        "NumPy cube; H2D of tile i+1, kernels of tile i and D2H of tile i-1 overlap inside "
-                       "pkm_ybar_density; multi-GPU ranks leave their pixel ranges on their own host buffers"}
+                       "pkm_ybar_density; multi-GPU ranks leave their pixel ranges on their own host buffers; "
+                       "byte counts are whole-job totals"}
 
     clocks = sampler.stop(windows) if sampler else None
 
@@ -665,6 +705,7 @@ def run_b200(args):
                                             "frac": b_min * per_gpu / 1e9 / hbm_peak},
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
             "gather": (args.gather if world > 1 else None), "gather_note": gather_note,
+            "numa_affinity": (f"{len(numa_cpus)} local cores" if numa_cpus else None),
             "verify": verify,
             "kernels": kern, "per_rank": per_rank, "other_paths": other, "cpu_baseline": cpu, "clocks": clocks,
         }

@@ -22,6 +22,30 @@ def my_rows(nx1, world_size, rank):
     return b[rank], b[rank + 1]
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPU cores local to GPU `device_index` (NVML's ideal CPU
+    affinity), so that page-locked host buffers allocated afterwards are first-touched on the
+    GPU's own NUMA node and host<->device copies do not cross the socket interconnect.
+    Returns the list of CPUs, or None if NVML / the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device_index]) if visible and visible.replace(",", "").isdigit() else device_index
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 - NVML missing, containers without the syscall, ...
+        return None
+
+
 def gather_pixel_major(tile, nx1, nx2, dist=None, dst=0):
     """Gather per-rank spaxel-major tiles [rows_r*nx2, n] on `dst`.
 
