@@ -532,6 +532,18 @@ def run_b200(args):
                                       "ref": "ParametricComponent._get_log_p_tvxz parametric.py:567-596"}
         del P, mu_v, sig_v, log_w, pix
         plan32 = engine.Plan(cube, device=local, precision="float32")
+        P32 = torch.rand((nt, rows, nxl, nz), dtype=torch.float64, device=dev, generator=gen)
+        P32 /= P32.sum()
+        mu32 = 400.0 * (torch.rand((nt, rows, nxl), dtype=torch.float64, device=dev, generator=gen) - 0.5)
+        sg32 = 20.0 + 200.0 * torch.rand((nt, rows, nxl), dtype=torch.float64, device=dev, generator=gen)
+        ms = timed(lambda: plan32.ybar_gaussian(P32, mu32, sg32, out=out))
+        y32 = out.clone()
+        plan.ybar_gaussian(P32, mu32, sg32, out=out)
+        other["gaussian_path_A_float32"] = {
+            "voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
+            "max_rel_diff_vs_float64": float((y32 - out).abs().max() / out.abs().max()),
+            "note": "optional float32 arithmetic of the Gaussian path (k_gaussian_f32), tolerance 1e-5; the inverse FFT stays float64"}
+        del P32, mu32, sg32, y32
         ms = timed(lambda: plan32.ybar_density(logp, is_log=True, out=out))
         other["density_path_B_float32"] = {"voxel_per_s": voxels_per_step / (ms * 1e-3), "ms": ms,
                                            "note": "optional float32 contraction, tolerance 1e-5"}

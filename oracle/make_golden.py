@@ -130,9 +130,26 @@ def save(name, rec):
     print(f"{name}: {os.path.getsize(path)/1e6:.2f} MB, {len(rec)} arrays")
 
 
+def golden_ppxf(pkm):
+    """g5: the reference's pad="ppxf" option (model_grids.py:263-281): n_fft = next power of two
+    above the 1021 log-lambda pixels = 1024, so the cube has 3 more samples than the spectra and
+    the convolution wraps into the padding.  Paths A and B of the unmodified reference."""
+    cube = make_cube(pkm, 2, 3, 21, age_rebin=6, z_rebin=2)
+    cube.ssps._calculate_fourier_transform(pad="ppxf")
+    rec = cube_record(cube)
+    rec["n_pix"] = np.array(cube.ssps.n_pix)
+    rec.update(parametric_record("d1_", disk_one(pkm, cube)))
+    wrec, _ = base_records(pkm, cube, white_noise_log_p(cube, 5), with_dists=False)
+    rec.update({"wn_" + k[2:]: v for k, v in wrec.items()})
+    save("g5_ppxf_pad_nv21", rec)
+
+
 def main():
     pkm = ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "g5":      # added in round 2: leaves g1-g4 untouched
+        golden_ppxf(pkm)
+        return
 
     # ---- g1: conftest galaxy (full 53x12 grid, nv=41 -> n_fft=1992 even), 3x2 pixels
     cube = make_cube(pkm, 3, 2, 41)
@@ -186,6 +203,7 @@ def main():
     except Exception as exc:  # noqa: BLE001
         rec["b_error"] = np.array(type(exc).__name__)
     save("g4_even_nv40", rec)
+    golden_ppxf(pkm)
 
 
 if __name__ == "__main__":

@@ -124,7 +124,7 @@ static void plan_free(pkm_plan* pl) {
     p = nullptr;
   };
   fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_CIt_oct); fr(pl->d_CR); fr(pl->d_CI); fr(pl->d_Sw); fr(pl->d_Sw32);
-  fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_omega);
+  fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_SA32); fr(pl->d_omega);
   fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz); fr(pl->d_exp_tab);
   collect_timers(pl);

@@ -138,6 +138,7 @@ struct pkm_plan {
   // gaussian path
   int ga_nks = 0, ga_nkt = 0;   // k-steps of 4 metallicities, frequency tiles of 64
   double* d_SA = nullptr;       // FXw (unscaled) in DMMA fragment order [nkt][nt][16][nks][32]
+  float2* d_SA32 = nullptr;     // FXw as float2 [nkt][nt][64][nz] (precision = 1 only)
   double* d_omega = nullptr;    // [nfo] the reference's omega array
   std::vector<double> h_omega;  // host copy of what d_omega holds (re-uploaded only when it changes)
 

@@ -21,6 +21,8 @@ GOLDEN_CUBES = {
     "g2_rebin_nv21_prime": dict(nx1=4, nx2=5, nv=21, ssp=dict(age_rebin=6, z_rebin=2)),
     "g3_full_nv101_odd": dict(nx1=1, nx2=2, nv=101, ssp={}),
     "g4_even_nv40": dict(nx1=2, nx2=2, nv=40, ssp=dict(age_rebin=4, z_rebin=3)),
+    # the reference's pad="ppxf" option: n_fft = 1024 > n_pix = 1021 (model_grids.py:263-281)
+    "g5_ppxf_pad_nv21": dict(nx1=2, nx2=3, nv=21, ssp=dict(age_rebin=6, z_rebin=2), pad="ppxf"),
 }
 
 _cache = {}
@@ -37,8 +39,11 @@ def build_cube(name):
     import popkinmocks_b200 as pkm
     cfg = GOLDEN_CUBES[name]
     ssps = pkm.milesSSPs(**cfg["ssp"])
-    return pkm.ifu_cube.IFUCube(ssps=ssps, nx1=cfg["nx1"], nx2=cfg["nx2"], nv=cfg["nv"],
+    cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=cfg["nx1"], nx2=cfg["nx2"], nv=cfg["nv"],
                                 vrng=(-1000.0, 1000.0))
+    if cfg.get("pad"):
+        cube.ssps._calculate_fourier_transform(pad=cfg["pad"])
+    return cube
 
 
 def golden_cube(name):

@@ -24,6 +24,7 @@ def _plan(name):
     ("g2_rebin_nv21_prime", ["d1_", "s1_"]),
     ("g3_full_nv101_odd", ["d1_"]),
     ("g4_even_nv40", ["d2_"]),
+    ("g5_ppxf_pad_nv21", ["d1_"]),          # pad="ppxf": n_fft = 1024 > n_pix = 1021
 ])
 def test_gaussian_path_matches_reference(gpu_ok, name, tags):
     g = load_golden(name)
@@ -39,6 +40,7 @@ def test_gaussian_path_matches_reference(gpu_ok, name, tags):
     ("g1_conftest_full_nv41", ["b_"]),
     ("g2_rebin_nv21_prime", ["b_", "wn_"]),
     ("g3_full_nv101_odd", ["wn_"]),
+    ("g5_ppxf_pad_nv21", ["wn_"]),          # pad="ppxf" (model_grids.py:263-281)
 ])
 def test_density_path_matches_reference(gpu_ok, name, tags):
     g = load_golden(name)
@@ -341,3 +343,19 @@ def test_generic_coefficient_kernel_matches_the_tensor_core_kernels(gpu_ok, monk
         monkeypatch.delenv("PKM_COEFF_GENERIC")
         assert rel_err(got, ref) < tol, precision
     assert rel_err(got, g["wn_ybar"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,tags", [("g1_conftest_full_nv41", ["d1_", "d2_", "s1_"]), ("g2_rebin_nv21_prime", ["d1_", "s1_"]),
+                                       ("g3_full_nv101_odd", ["d1_"]), ("g4_even_nv40", ["d2_"]),
+                                       ("g5_ppxf_pad_nv21", ["d1_"])])
+def test_float32_gaussian_path_within_1e5(gpu_ok, name, tags):
+    """Optional float32 arithmetic of the Gaussian-LOSVD path (k_gaussian_f32): BASELINE.json
+    tolerance 1e-5 max-norm against the reference's float64 cube."""
+    from popkinmocks_b200 import engine
+    g = load_golden(name)
+    plan32 = engine.get_plan(golden_cube(name), precision="float32")
+    for tag in tags:
+        y32 = plan32.ybar_gaussian(g[tag + "P_txz"], g[tag + "mu_v"], g[tag + "sig_v"])
+        err = rel_err(y32, g[tag + "ybar"])
+        assert err < 1e-5, (name, tag, err)
+        assert err > 1e-12      # it really is the float32 path

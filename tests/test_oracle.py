@@ -27,7 +27,8 @@ def _grid(g):
 
 @pytest.mark.parametrize("name,tags", [("g1_conftest_full_nv41", ["d1_", "d2_", "s1_"]),
                                        ("g2_rebin_nv21_prime", ["d1_", "s1_"]),
-                                       ("g3_full_nv101_odd", ["d1_"]), ("g4_even_nv40", ["d2_"])])
+                                       ("g3_full_nv101_odd", ["d1_"]), ("g4_even_nv40", ["d2_"]),
+                                       ("g5_ppxf_pad_nv21", ["d1_"])])
 def test_gaussian_path(name, tags):
     g = load_golden(name)
     for tag in tags:
@@ -37,7 +38,8 @@ def test_gaussian_path(name, tags):
 
 
 @pytest.mark.parametrize("name,tag", [("g1_conftest_full_nv41", "b_"), ("g2_rebin_nv21_prime", "b_"),
-                                      ("g2_rebin_nv21_prime", "wn_"), ("g3_full_nv101_odd", "wn_")])
+                                      ("g2_rebin_nv21_prime", "wn_"), ("g3_full_nv101_odd", "wn_"),
+                                      ("g5_ppxf_pad_nv21", "wn_")])
 def test_density_path_literal_and_fused(name, tag):
     g = load_golden(name)
     with np.errstate(over="ignore"):
