@@ -204,6 +204,17 @@ PKM_API int32_t pkm_reduce_logp_from(pkm_plan* plan, const double* log_P_src, ui
                                      const double* log_dv, const double* light_weights, uint32_t keep_mask,
                                      int32_t density, double* out, void* stream);
 
+/* A marginal or conditional distribution assembled on the device from log-probability marginals
+ * (base.py:130-177): out[dependent axes..., conditioning axes...] = log P(joint) - log P(given)
+ * - (density ? log dV(dependent axes) : 0), exponentiated if `exponentiate` (get_p instead of
+ * get_log_p).  log_P_joint holds the axes of joint_mask, log_P_given (or NULL for a plain marginal)
+ * those of given_mask (a subset), both as produced by pkm_reduce_logp* with density = 0; axes inside
+ * each group are in t, v, x, z order, which is the reference's array layout.  Device buffers only. */
+PKM_API int32_t pkm_conditional(pkm_plan* plan, const double* log_P_joint, uint32_t joint_mask,
+                                const double* log_P_given, uint32_t given_mask, int64_t npix,
+                                const double* log_dv, int32_t density, int32_t exponentiate, double* out,
+                                void* stream);
+
 /* Moments of a conditional 1-D distribution straight from device-resident log marginals
  * (base.py:130-177 + 208-260 in one kernel): P_i = exp(log_joint[a][i][b] - log_given[a][b]) with the
  * variable on the middle axis (nouter x nvar x ninner, C order; log_given [nouter][ninner] or NULL),

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pkm_reduce_logp": (_I32, [_P, _P, _I64, _P, _P, _U32, _I32, _P, _P]),
     "pkm_reduce_logp_multi": (_I32, [_P, _P, _I64, _P, _P, _I32, _P, _P, C.POINTER(_P), _P]),
     "pkm_reduce_logp_from": (_I32, [_P, _P, _U32, _I64, _P, _P, _U32, _I32, _P, _P]),
+    "pkm_conditional": (_I32, [_P, _P, _U32, _P, _U32, _I64, _P, _I32, _I32, _P, _P]),
     "pkm_moments_logp": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P, _I32, _P]),
     "pkm_moments": (_I32, [_P, _P, _I64, _I64, _P, _I32, _P]),
     "pkm_noise": (_I32, [_P, _I64, _F64, _I32, _U64, _U64, _F64, _P, _P, _I32, _P]),

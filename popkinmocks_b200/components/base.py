@@ -76,14 +76,43 @@ class Component(object):
         Variables are listed alphabetically on each side of the underscore; `density=False`
         returns volume-element weighted probabilities; `light_weighted` switches from mass
         to light weighting.  Array axes follow the order of the string ('x' is two axes)."""
+        out = self._device_distribution(which_dist, density, light_weighted, exponentiate=True)
+        if out is not None:
+            return out
         return np.exp(self.get_log_p(which_dist, density=density, light_weighted=light_weighted))
 
     def get_log_p(self, which_dist, density=True, light_weighted=False):
+        out = self._device_distribution(which_dist, density, light_weighted, exponentiate=False)
+        if out is not None:
+            return out
         if "_" in which_dist:
             return self._get_log_conditional_distribution(which_dist, density=density,
                                                           light_weighted=light_weighted)
         return self._get_log_marginal_distribution(which_dist, density=density,
                                                    light_weighted=light_weighted)
+
+    def _device_distribution(self, which_dist, density, light_weighted, exponentiate):
+        """get_p / get_log_p of the pixelated density assembled on the device (pkm_conditional):
+        log P(joint) - log P(given) - log dV and the exponential are one kernel on the cached log
+        marginals, and only the result crosses PCIe.  None = not applicable (subclasses with
+        their own `_log_marginal`, hard-coded conditionals, arrays streamed from the host)."""
+        if type(self)._log_marginal is not Component._log_marginal:
+            return None
+        dependent, _, given = which_dist.partition("_")
+        if given and getattr(self, "_get_log_p_" + which_dist, None) is not None:
+            return None
+        joint = "".join(sorted(dependent + given))
+        if "".join(sorted(dependent)) != dependent or "".join(sorted(given)) != given or joint == "tvxz":
+            return None                                  # the 5-D array itself goes through pkm_reduce_logp
+        log_joint = self._log_marginal_dev(joint, light_weighted)
+        if not engine._is_torch(log_joint):
+            return None
+        log_given = self._log_marginal_dev(given, light_weighted) if given else None
+        cube = self.cube
+        plan = engine.get_plan(cube, device=int(log_joint.device.index or 0))
+        log_dv = np.log(cube.v_edg[1:] - cube.v_edg[:-1])
+        return plan.conditional(log_joint, joint, log_given, given, cube.nx * cube.ny, log_dv, density,
+                                exponentiate, (cube.nx, cube.ny))
 
     def _get_log_marginal_distribution(self, which_dist, density=True, light_weighted=False):
         fn = getattr(self, "_get_log_p_" + which_dist)

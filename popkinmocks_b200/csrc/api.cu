@@ -982,6 +982,24 @@ extern "C" int32_t pkm_reduce_logp_from(pkm_plan* pl, const double* log_P_src, u
   });
 }
 
+extern "C" int32_t pkm_conditional(pkm_plan* pl, const double* log_P_joint, uint32_t joint_mask,
+                                   const double* log_P_given, uint32_t given_mask, int64_t npix,
+                                   const double* log_dv, int32_t density, int32_t exponentiate, double* out,
+                                   void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(pl && log_P_joint && log_dv && out && npix >= 1, "bad argument");
+    PKM_REQUIRE(joint_mask <= 0xF && (given_mask & ~joint_mask) == 0, "the conditioners must be axes of the joint");
+    PKM_REQUIRE(pkm_is_device_pointer(log_P_joint) && pkm_is_device_pointer(out) &&
+                (!log_P_given || pkm_is_device_pointer(log_P_given)), "device buffers required");
+    PKM_REQUIRE((given_mask == 0) == (log_P_given == nullptr) || given_mask == 0, "given_mask without log_P_given");
+    use_device(pl->d.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const ReduceConsts c = upload_reduce_consts(pl, log_dv, nullptr, st);
+    launch_conditional(pl, log_P_joint, joint_mask, log_P_given, log_P_given ? given_mask : 0, npix, c.log_dv,
+                       density, exponentiate, out, st);
+  });
+}
+
 extern "C" int32_t pkm_moments_logp(const double* log_joint, const double* log_given, const double* values,
                                     int64_t nouter, int64_t nvar, int64_t ninner, double* out, int32_t device,
                                     void* stream) {

@@ -214,6 +214,9 @@ void launch_reduce_logp(pkm_plan* pl, const double* logp, const ReduceSrc& src, 
                         cudaStream_t st);
 void launch_apply_log_dv(pkm_plan* pl, double* out, const ReduceSrc& src, const double* d_log_dv,
                          uint32_t keep_mask, double sign, cudaStream_t st);
+void launch_conditional(pkm_plan* pl, const double* log_joint, uint32_t joint_mask, const double* log_given,
+                        uint32_t given_mask, int64_t npix, const double* d_log_dv, int density, int do_exp,
+                        double* out, cudaStream_t st);
 void launch_moments_logp(const double* log_joint, const double* log_given, const double* values,
                          int64_t nouter, int64_t nvar, int64_t ninner, double* out, cudaStream_t st);
 void density_tables_upload(pkm_plan* pl);

@@ -502,6 +502,56 @@ __global__ void k_apply_log_dv(double* __restrict__ out, long long nout, ReduceG
   }
 }
 
+// Conditional / plain distribution from device-resident log-probability marginals (base.py:130-177):
+//   out[dep axes..., given axes...] = log P(joint) - log P(given) - (density ? log dV(dep) : 0), optionally
+//   exponentiated.  Axes inside each group are in (t, v, x, z) order; `e*` are the extents of the
+//   joint (1 for an absent axis), `g*` flags mark the conditioning axes.  log_given may be NULL.
+struct CondGeom {
+  int et, ev, ez;
+  long long ex;
+  int gt, gv, gx, gz;      // 1 = axis belongs to the conditioners
+  int density, do_exp;
+  double log_dxdy;
+};
+__global__ void k_conditional(const double* __restrict__ lj, const double* __restrict__ lg, CondGeom c,
+                              const double* __restrict__ log_dt, const double* __restrict__ log_dv,
+                              const double* __restrict__ log_dz, long long n, double* __restrict__ out) {
+  // output dimension list: dependents first, then conditioners, each in t, v, x, z order
+  long long ext[8];
+  int axis[8], nd = 0;
+  const long long e4[4] = {c.et, c.ev, c.ex, c.ez};
+  const int g4[4] = {c.gt, c.gv, c.gx, c.gz};
+  for (int pass = 0; pass < 2; ++pass)
+    for (int a = 0; a < 4; ++a)
+      if (g4[a] == pass && e4[a] > 1) { ext[nd] = e4[a]; axis[nd] = a; ++nd; }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long idx[4] = {0, 0, 0, 0};
+    long long r = i;
+    for (int d = nd - 1; d >= 0; --d) {
+      idx[axis[d]] = r % ext[d];
+      r /= ext[d];
+    }
+    const long long ij = ((idx[0] * c.ev + idx[1]) * c.ex + idx[2]) * c.ez + idx[3];
+    double val = lj[ij];
+    if (lg) {
+      long long ig = 0;
+      for (int a = 0; a < 4; ++a)
+        if (g4[a]) ig = ig * e4[a] + idx[a];
+      val -= lg[ig];                               // (-inf) - (-inf) = NaN where P(given) = 0, as in the reference
+    }
+    if (c.density) {
+      double ldv = 0.0;
+      if (!c.gt && c.et > 1) ldv += log_dt[idx[0]];
+      if (!c.gv && c.ev > 1) ldv += log_dv[idx[1]];
+      if (!c.gx && c.ex > 1) ldv += c.log_dxdy;
+      if (!c.gz && c.ez > 1) ldv += log_dz[idx[3]];
+      val -= ldv;
+    }
+    out[i] = c.do_exp ? exp(val) : val;
+  }
+}
+
 // numpy.max semantics: NaN if any element is NaN
 __global__ void k_max(const double* __restrict__ x, long long n, double* result, int* nan_flag) {
   double m = -INFINITY;
@@ -694,6 +744,24 @@ void launch_apply_log_dv(pkm_plan* pl, double* out, const ReduceSrc& src, const 
   if (g.kz) nout *= g.nz;
   const int grid = (int)std::min<long long>((nout + 255) / 256, (long long)pl->num_sms * 16);
   k_apply_log_dv<<<grid, 256, 0, st>>>(out, nout, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, sign);
+  PKM_CUDA(cudaGetLastError());
+  pl->launches += 1;
+}
+
+void launch_conditional(pkm_plan* pl, const double* log_joint, uint32_t joint_mask, const double* log_given,
+                        uint32_t given_mask, int64_t npix, const double* d_log_dv, int density, int do_exp,
+                        double* out, cudaStream_t st) {
+  CondGeom c;
+  c.et = (joint_mask & 1) ? pl->d.nt : 1;
+  c.ev = (joint_mask & 2) ? pl->d.nv : 1;
+  c.ex = (joint_mask & 4) ? npix : 1;
+  c.ez = (joint_mask & 8) ? pl->d.nz : 1;
+  c.gt = given_mask & 1; c.gv = (given_mask >> 1) & 1; c.gx = (given_mask >> 2) & 1; c.gz = (given_mask >> 3) & 1;
+  c.density = density; c.do_exp = do_exp;
+  c.log_dxdy = std::log(pl->d.dx) + std::log(pl->d.dy);
+  const long long n = (long long)c.et * c.ev * c.ex * c.ez;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)pl->num_sms * 16));
+  k_conditional<<<grid, 256, 0, st>>>(log_joint, log_given, c, pl->d_log_dt, d_log_dv, pl->d_log_dz, n, out);
   PKM_CUDA(cudaGetLastError());
   pl->launches += 1;
 }

@@ -237,6 +237,23 @@ class Plan:
                                                      _lib.ptr(lw), n, masks, dens, ptrs, None))
         return outs
 
+    def conditional(self, log_joint, joint, log_given, given, npix, log_dv, density, exponentiate, xshape):
+        """A (conditional) distribution from device-resident log-probability marginals
+        (pkm_conditional): axes = dependents (joint minus given) then conditioners, each group in
+        t, v, x, z order.  Returns a NumPy array (the result of get_p / get_log_p)."""
+        import torch
+        dims = {"t": [self.nt], "v": [self.nv], "x": list(xshape), "z": [self.nz]}
+        dep = [a for a in "tvxz" if a in joint and a not in given]
+        shape = sum((dims[a] for a in dep), []) + sum((dims[a] for a in "tvxz" if a in given), [])
+        out = torch.empty(tuple(shape), dtype=torch.float64, device=log_joint.device)
+        ldv = _lib.as_f64(log_dv)
+        lg = None if log_given is None else log_given.contiguous()
+        _lib.check(_lib.load().pkm_conditional(self._h, _lib.ptr(log_joint.contiguous()), self._mask(joint),
+                                               _lib.ptr(lg), self._mask(given) if lg is not None else 0, int(npix),
+                                               _lib.ptr(ldv), int(bool(density)), int(bool(exponentiate)),
+                                               _lib.ptr(out), None))
+        return out.cpu().numpy()
+
     def reduce_logp_from(self, src, src_keep, npix, log_dv, keep, density, light_weights=None):
         """A log-marginal reduced from the device-resident log-PROBABILITY marginal `src` over the
         axes `src_keep` (pkm_reduce_logp_from); `light_weights` re-weights a mass-weighted source
