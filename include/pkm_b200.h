@@ -315,6 +315,20 @@ PKM_API int32_t pkm_assemble_txz(const double* log_P_t, const double* log_dt, co
                                  const double* log_dz, const int32_t* row_idx, int32_t nt, int64_t npix,
                                  int32_t nz, double* P_txz, double* log_p_txz, int32_t device, void* stream);
 
+/* SSP operand pipeline on the device <- milesSSPs.logarithmically_resample
+ * + calculate_fourier_transform (popkinmocks/model_grids.py:240-281):
+ *   Xw[j][s]  = sum_{q<4} tap_w[j][q] * coef[tap_idx[j]+q][s]      (cubic B-spline evaluated at the uniform
+ *               log-wavelength grid; coef [ncoef][nssp] = not-a-knot B-spline coefficients of the SSP
+ *               spectra over log(lambda), tap_idx/tap_w [n_pix]([4]) = first coefficient and the four
+ *               basis values of every output pixel - the O(n_lambda) tables come from the host)
+ *   FXw[k][s] = sum_j Xw[j][s] exp(-2 pi i j k / n_fft), k <= n_fft/2   (= numpy.fft.rfft(Xw.T, n_fft).T; any
+ *               n_fft >= n_pix, so pad=False and pad="ppxf" are the same call)
+ * coef, tap_idx, tap_w: host.  Xw_out [n_pix][nssp] float64, FXw_out [n_fft/2+1][nssp] complex128: host or
+ * device. */
+PKM_API int32_t pkm_ssp_operand(const double* coef, int32_t ncoef, const int32_t* tap_idx, const double* tap_w,
+                                int32_t n_pix, int32_t nssp, int32_t n_fft, double* Xw_out, double* FXw_out,
+                                int32_t device, void* stream);
+
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (2 flops per FMA; best of `repeats`
  * timed launches of a register-resident DFMA chain on every SM).  The roofline denominator of
  * the FP64-pipe-bound kernels; MEASURED_PEAKS.json carries no FP64 figure. */

@@ -87,6 +87,7 @@ SIGNATURES = {
     "pkm_stream_maps": (_I32, [_P, _P, _I32, _I32, _F64, _F64, _F64, _P, _P, _I32, _F64, _F64, _F64, _F64, _F64,
                                _F64, _F64, _P, _P, _F64, _I32, _P]),
     "pkm_assemble_txz": (_I32, [_P, _P, _P, _I32, _F64, _P, _I32, _P, _P, _I32, _I64, _I32, _P, _P, _I32, _P]),
+    "pkm_ssp_operand": (_I32, [_P, _I32, _P, _P, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "pkm_fp64_fma_peak": (_I32, [_I32, _I32, C.POINTER(_F64)]),
 }
 

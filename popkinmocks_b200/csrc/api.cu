@@ -1215,6 +1215,47 @@ extern "C" int32_t pkm_assemble_txz(const double* log_P_t, const double* log_dt,
   });
 }
 
+extern "C" int32_t pkm_ssp_operand(const double* coef, int32_t ncoef, const int32_t* tap_idx, const double* tap_w,
+                                   int32_t n_pix, int32_t nssp, int32_t n_fft, double* Xw_out, double* FXw_out,
+                                   int32_t device, void* stream) {
+  return guarded([&] {
+    PKM_REQUIRE(coef && tap_idx && tap_w && Xw_out && FXw_out, "null argument");
+    PKM_REQUIRE(ncoef >= 4 && n_pix >= 1 && nssp >= 1 && n_fft >= n_pix, "bad shape (n_fft must be >= n_pix)");
+    if (pkm_device_count() <= 0) PKM_THROW(PKM_ERR_CUDA, "no CUDA device visible (there is no CPU fallback)");
+    for (int j = 0; j < n_pix; ++j)
+      PKM_REQUIRE(tap_idx[j] >= 0 && tap_idx[j] + 4 <= ncoef, "tap_idx[%d] out of range", j);
+    use_device(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nfo = n_fft / 2 + 1;
+    // exp(-2 pi i r / n) in long double, rounded once
+    const long double PI_L = 3.14159265358979323846264338327950288419716939937510L;
+    std::vector<double> wn((size_t)2 * n_fft);
+    for (int r = 0; r < n_fft; ++r) {
+      const long double ang = -2.0L * PI_L * (long double)r / (long double)n_fft;
+      wn[2 * r] = (double)cosl(ang);
+      wn[2 * r + 1] = (double)sinl(ang);
+    }
+    const size_t n_c = (size_t)ncoef * nssp, n_x = (size_t)n_pix * nssp, n_f = (size_t)2 * nfo * nssp;
+    DevBuf buf;
+    buf.reserve(sizeof(double) * (n_c + 4 * (size_t)n_pix + wn.size() + n_x + n_f) + sizeof(int) * ((size_t)n_pix + 2));
+    double* d_coef = buf.as<double>();
+    double* d_w = d_coef + n_c;
+    double* d_wn = d_w + 4 * (size_t)n_pix;
+    double* d_X = d_wn + wn.size();
+    double* d_F = d_X + n_x;
+    int* d_idx = reinterpret_cast<int*>(d_F + n_f);
+    PKM_CUDA(cudaMemcpyAsync(d_coef, coef, sizeof(double) * n_c, cudaMemcpyHostToDevice, st));
+    PKM_CUDA(cudaMemcpyAsync(d_w, tap_w, sizeof(double) * 4 * n_pix, cudaMemcpyHostToDevice, st));
+    PKM_CUDA(cudaMemcpyAsync(d_wn, wn.data(), sizeof(double) * wn.size(), cudaMemcpyHostToDevice, st));
+    PKM_CUDA(cudaMemcpyAsync(d_idx, tap_idx, sizeof(int) * n_pix, cudaMemcpyHostToDevice, st));
+    launch_ssp_operand(d_coef, d_idx, d_w, reinterpret_cast<const double2*>(d_wn), n_pix, nssp, n_fft, d_X,
+                       reinterpret_cast<double2*>(d_F), sm_count(device), st);
+    PKM_CUDA(cudaMemcpyAsync(Xw_out, d_X, sizeof(double) * n_x, cudaMemcpyDefault, st));
+    PKM_CUDA(cudaMemcpyAsync(FXw_out, d_F, sizeof(double) * n_f, cudaMemcpyDefault, st));
+    PKM_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
 extern "C" int32_t pkm_fp64_fma_peak(int32_t device, int32_t repeats, double* tflops_out) {
   return guarded([&] {
     PKM_REQUIRE(tflops_out && repeats >= 1, "bad argument");

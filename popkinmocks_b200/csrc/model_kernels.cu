@@ -247,3 +247,70 @@ void launch_assemble_txz(const double* d_log_P_t, const double* d_log_dt, const 
                                                        d_log_Pz, d_log_dz, row, nt, npix, nz, P_txz, log_p_txz);
   PKM_CUDA(cudaGetLastError());
 }
+
+// ----------------------------------------------------------------------------
+// SSP operand pipeline: the constant operand S-hat of the hot path,
+// milesSSPs.logarithmically_resample + calculate_fourier_transform
+// (/root/reference/popkinmocks/model_grids.py:240-281), for all SSPs at once:
+//   Xw[j][s]  = sum_{q<4} tap_w[j][q] * coef[tap_idx[j] + q][s]          cubic B-spline evaluation
+//   FXw[k][s] = sum_{j<n_pix} Xw[j][s] * exp(-2 pi i (j k mod n_fft) / n_fft)      real DFT, zero padded
+// The host keeps the O(n_lambda) parts (the banded not-a-knot solve for the B-spline coefficients and
+// the 4 basis values per output pixel, both from SciPy); the O(n_lambda x n_ssp) evaluation and the
+// O(n^2 x n_ssp) transform run here.  Any n_fft (the DFT is direct, with exact integer phase
+// reduction against a long-double table), so pad="ppxf" and pad=False take the same path.
+// ----------------------------------------------------------------------------
+namespace {
+__global__ void k_ssp_resample(const double* __restrict__ coef, const int* __restrict__ tap_idx,
+                               const double* __restrict__ tap_w, int n_pix, int nssp, double* __restrict__ Xw) {
+  const long long n = (long long)n_pix * nssp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i / nssp), s = (int)(i - (long long)j * nssp);
+    const int i0 = tap_idx[j];
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc = fma(tap_w[4 * j + q], coef[(size_t)(i0 + q) * nssp + s], acc);
+    Xw[i] = acc;
+  }
+}
+
+// thread = (4 consecutive frequencies, one SSP); the phase index advances by k modulo n (no products)
+constexpr int DFT_KB = 4;
+__global__ void __launch_bounds__(128)
+k_ssp_rdft(const double* __restrict__ Xw, const double2* __restrict__ wn, int n_pix, int nssp, int n_fft, int nfo,
+           double2* __restrict__ FXw) {
+  const int s = blockIdx.y * blockDim.x + threadIdx.x;
+  const int k0 = blockIdx.x * DFT_KB;
+  if (s >= nssp) return;
+  int r[DFT_KB];
+  double2 acc[DFT_KB];
+#pragma unroll
+  for (int b = 0; b < DFT_KB; ++b) {
+    r[b] = 0;
+    acc[b] = make_double2(0.0, 0.0);
+  }
+  for (int j = 0; j < n_pix; ++j) {
+    const double x = __ldg(Xw + (size_t)j * nssp + s);
+#pragma unroll
+    for (int b = 0; b < DFT_KB; ++b) {
+      const double2 w = __ldg(wn + r[b]);          // exp(-2 pi i r / n): the same address for the whole warp
+      acc[b].x = fma(x, w.x, acc[b].x);
+      acc[b].y = fma(x, w.y, acc[b].y);
+      r[b] += k0 + b;
+      if (r[b] >= n_fft) r[b] -= n_fft;
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < DFT_KB; ++b)
+    if (k0 + b < nfo) FXw[(size_t)(k0 + b) * nssp + s] = acc[b];
+}
+}  // namespace
+
+void launch_ssp_operand(const double* d_coef, const int* d_tap_idx, const double* d_tap_w, const double2* d_wn,
+                        int n_pix, int nssp, int n_fft, double* d_Xw, double2* d_FXw, int num_sms, cudaStream_t st) {
+  const int nfo = n_fft / 2 + 1;
+  k_ssp_resample<<<grid_for((long long)n_pix * nssp, num_sms), 256, 0, st>>>(d_coef, d_tap_idx, d_tap_w, n_pix, nssp, d_Xw);
+  PKM_CUDA(cudaGetLastError());
+  dim3 grid((unsigned)((nfo + DFT_KB - 1) / DFT_KB), (unsigned)((nssp + 127) / 128));
+  k_ssp_rdft<<<grid, 128, 0, st>>>(d_Xw, d_wn, n_pix, nssp, n_fft, nfo, d_FXw);
+  PKM_CUDA(cudaGetLastError());
+}

@@ -255,6 +255,8 @@ void launch_assemble_txz(const double* d_log_P_t, const double* d_log_dt, const 
                          int64_t px_age_stride, double log_dxdy, const double* d_log_Pz, const double* d_log_dz,
                          const int* row, int nt, int64_t npix, int nz, double* P_txz, double* log_p_txz,
                          int num_sms, cudaStream_t st);
+void launch_ssp_operand(const double* d_coef, const int* d_tap_idx, const double* d_tap_w, const double2* d_wn,
+                        int n_pix, int nssp, int n_fft, double* d_Xw, double2* d_FXw, int num_sms, cudaStream_t st);
 bool pkm_is_device_pointer(const void* p);
 
 // RAII CUDA-event bracket of one launch on its own stream (no-op unless plan->profiling)

@@ -30,10 +30,12 @@ class IFUCube(object):
         x1rng, x2rng (tuple): spatial extents (arbitrary units)
         vrng (tuple): velocity extent, km/s
         interp_kind (string): interpolation used to log-resample the SSPs
+        operand_device (int, optional, extension): build the SSP operand (log-resampling + Fourier
+            transform of all SSPs) on this GPU instead of with SciPy/NumPy on the host
     """
 
     def __init__(self, ssps=None, nx1=300, nx2=299, nv=200, x1rng=(-1, 1),
-                 x2rng=(-1, 1), vrng=(-1000, 1000), interp_kind="cubic"):
+                 x2rng=(-1, 1), vrng=(-1000, 1000), interp_kind="cubic", operand_device=None):
         self.ssps = ssps
         self.nx, self.ny, self.nv = nx1, nx2, nv
         self.x1rng, self.x2rng = x1rng, x2rng
@@ -46,8 +48,14 @@ class IFUCube(object):
         self.xx, self.yy = np.meshgrid(self.x, self.y, indexing="ij")
         self.v_edg = np.linspace(*vrng, nv + 1)
         dv = self.v_edg[1] - self.v_edg[0]
-        self.ssps._logarithmically_resample(dv=dv, interp_kind=interp_kind)
-        self.ssps._calculate_fourier_transform()
+        if operand_device is None:
+            self.ssps._logarithmically_resample(dv=dv, interp_kind=interp_kind)
+            self.ssps._calculate_fourier_transform()
+        else:
+            # extension: log-resampling and Fourier transform of the SSPs on the GPU (cubic only)
+            if interp_kind != "cubic":
+                raise ValueError("operand_device supports interp_kind='cubic' only")
+            self.ssps.prepare_operand_on_device(dv=dv, device=int(operand_device))
         self.ssps.get_light_weights()
         self._pkm_plans = {}
 

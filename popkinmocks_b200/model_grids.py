@@ -176,6 +176,50 @@ class milesSSPs(modelGrid):
         self.n_fft = n_fft
         self.FXw = np.fft.rfft(self.Xw.T, n_fft).T
 
+    def prepare_operand_on_device(self, dv=5.0, pad=False, device=0):
+        """`_logarithmically_resample(dv)` + `_calculate_fourier_transform(pad)` with the
+        O(n_lambda x n_ssp) spline evaluation and the O(n^2 x n_ssp) real DFT on the GPU
+        (pkm_ssp_operand; SURVEY.md section 8f rank 4, model_grids.py:240-281).
+
+        The host keeps what is O(n_lambda): the banded not-a-knot solve for the B-spline
+        coefficients and the four basis values of every output pixel (SciPy - the same
+        `make_interp_spline` that `interp1d(kind="cubic")` uses).  `Xw` / `FXw` agree with the host
+        path to ~1e-14 (direct DFT instead of pocketfft), not bit for bit - the default host path
+        keeps the operand identical to the reference's."""
+        from . import _lib
+        self.speed_of_light = SPEED_OF_LIGHT
+        self.dv = dv
+        self.dw = dv / SPEED_OF_LIGHT
+        log_lmd = np.log(self.lmd)
+        self.w = np.arange(np.min(log_lmd), np.max(log_lmd), self.dw)
+        spl = interpolate.make_interp_spline(log_lmd, self.X, k=3, check_finite=False)       # [n_lmd, n_ssp]
+        design = interpolate.BSpline.design_matrix(self.w, spl.t, 3).tocsr()                 # 4 values per row
+        n_pix = self.w.size
+        counts = np.diff(design.indptr)
+        if not np.all(counts == 4):
+            raise ValueError("unexpected B-spline design matrix structure")
+        tap_idx = np.ascontiguousarray(design.indices.reshape(n_pix, 4)[:, 0], dtype=np.int32)
+        if not np.all(np.diff(design.indices.reshape(n_pix, 4), axis=1) == 1):
+            raise ValueError("unexpected B-spline design matrix structure")
+        tap_w = _lib.as_f64(design.data.reshape(n_pix, 4))
+        self.n_pix = n_pix
+        if pad is False or pad == False:  # noqa: E712
+            n_fft = n_pix
+        elif pad == "ppxf":
+            n_fft = 2 ** int(np.ceil(np.log2(n_pix)))
+        else:
+            raise ValueError("Unknown choice for pad")
+        self.pad, self.n_fft = pad, n_fft
+        coef = _lib.as_f64(spl.c)
+        nssp = coef.shape[1]
+        Xw = np.empty((n_pix, nssp))
+        FXw = np.empty((n_fft // 2 + 1, nssp), dtype=np.complex128)
+        _lib.require_gpu()
+        _lib.check(_lib.load().pkm_ssp_operand(_lib.ptr(coef), int(coef.shape[0]), _lib.ptr(tap_idx), _lib.ptr(tap_w),
+                                               int(n_pix), int(nssp), int(n_fft), _lib.ptr(Xw), _lib.ptr(FXw),
+                                               int(device), None))
+        self.Xw, self.FXw = Xw, FXw
+
     def get_light_weights(self):
         """light_weights[t, z] = sum over wavelength of the (linear-lambda) SSP flux."""
         self.light_weights = np.sum(self.X, 0).reshape(self.par_dims).T
