@@ -23,6 +23,10 @@
 #include "exp_tab.cuh"
 #include "pkm_internal.h"
 
+#ifndef PKM_K1_APREFETCH
+#define PKM_K1_APREFETCH 0
+#endif
+
 // ============================================================================
 // async-copy helpers (1-D TMA bulk copies completing on an mbarrier)
 // ============================================================================
@@ -84,6 +88,7 @@ struct K1Geom {
   int use_tma;  // 0 = plain loads, 1 = one 1-D bulk copy per velocity row, 2 = one 2-D tensor copy per tile
   int ngroup;   // independent warp groups per CTA (1 or 2), each running its own tile pipeline
   int out_f32;  // store the coefficients as float2 (float32 arithmetic mode of the contraction)
+  int ncp;      // octet kernel: slab pitch in doubles (box width of the tensor copy)
 };
 
 // velocity row holding rolled position +u / -u  (np.roll(p, nv - v0), base.py:843)
@@ -339,9 +344,13 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, pxb = g.pxb, v0 = g.v0;
   const int nks = (ne + 3) >> 2;
   const int frag_elems = nks * MB * 32;
-  const int NC = pxb * nz;                       // dense box pitch (a multiple of 16)
-  const int slab_elems = nv * NC;
-  const int buf_elems = (max(nv, 2 * nfi) * NC + 15) & ~15;   // slab, later the [nz][nfi][2 pxb] staging box
+  const int NC = pxb * nz;                       // density columns of a tile (a multiple of 16)
+  // slab pitch: the tensor copy fetches a box two columns wider than the tile (the extra columns
+  // belong to the next pixel or are zero filled), because a 96-double pitch puts the four rolled
+  // velocities of a B fragment on the same shared-memory banks (8-way conflicts; 4-way with 98)
+  const int NCP = g.ncp;
+  const int slab_elems = nv * NCP;
+  const int buf_elems = (max(nv * NCP, 2 * nfi * NC) + 15) & ~15;   // slab, later the [nz][nfi][2 pxb] staging box
   double* As_r = smem;
   double* As_i = As_r + frag_elems;
   double* Bbuf = As_i + frag_elems;
@@ -417,11 +426,20 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
       const double* Ai = As_i + lane;
       auto fetch = [&](int ks, double& pa, double& pb) {
         const int u = min(ks * 4 + fk, ne - 1);               // u >= ne has zero A
-        pa = Bcol[(size_t)row_plus(u, v0, nv) * NC];
-        pb = Bcol[(size_t)row_minus(u, v0, nv) * NC];
+        pa = Bcol[(size_t)row_plus(u, v0, nv) * NCP];
+        pb = Bcol[(size_t)row_minus(u, v0, nv) * NCP];
       };
       double pa, pb;
       fetch(0, pa, pb);
+#if PKM_K1_APREFETCH
+      // the A fragments of the next k-step are loaded while this step's DMMAs issue
+      double ar[MB], ai[MB];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        ar[mb] = Ar[mb * 32];
+        ai[mb] = Ai[mb * 32];
+      }
+#endif
       for (int ks = 0; ks < nks; ++ks) {
         double qa = pa, qb = pb;
         if (ks + 1 < nks) fetch(ks + 1, pa, pb);               // next step's raw values, ahead of the DMMAs
@@ -430,11 +448,31 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
           qb = exp_tab(qb, etab);
         }
         const double be = qa + qb, bo = qa - qb;
+#if PKM_K1_APREFETCH
+        double nr[MB], ni[MB];
+        const int kn = min(ks + 1, nks - 1);
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          nr[mb] = Ar[(kn * MB + mb) * 32];
+          ni[mb] = Ai[(kn * MB + mb) * 32];
+        }
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          dmma_m8n8k4(accr[mb][0], accr[mb][1], ar[mb], be);
+          dmma_m8n8k4(acci[mb][0], acci[mb][1], ai[mb], bo);
+        }
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          ar[mb] = nr[mb];
+          ai[mb] = ni[mb];
+        }
+#else
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
           dmma_m8n8k4(accr[mb][0], accr[mb][1], Ar[(ks * MB + mb) * 32], be);
           dmma_m8n8k4(acci[mb][0], acci[mb][1], Ai[(ks * MB + mb) * 32], bo);
         }
+#endif
       }
     }
     K1_TICK(3);
@@ -610,8 +648,14 @@ static void launch_coeff_t(pkm_plan* pl, const double* dens, int is_log, int64_t
   pl->launches++;
 }
 
+#ifndef PKM_K1_APREFETCH
+#define PKM_K1_APREFETCH 0
+#endif
+#ifndef PKM_K1_PITCH_PAD
+#define PKM_K1_PITCH_PAD 2
+#endif
 static size_t coeff_oct_smem(const pkm_plan* pl, int NC) {
-  const size_t buf_elems = ((size_t)std::max(pl->d.nv, 2 * pl->nfi) * NC + 15) & ~size_t(15);
+  const size_t buf_elems = (std::max<size_t>((size_t)pl->d.nv * (NC + PKM_K1_PITCH_PAD), (size_t)2 * pl->nfi * NC) + 15) & ~size_t(15);
   return ((size_t)2 * pl->nfiP + 2 * buf_elems + PKM_EXP_TAB) * sizeof(double) + 16;
 }
 
@@ -659,7 +703,8 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
                        npix_total * nz < (1LL << 31);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  if (!base_ok || !encode_density_map(&tmap, dens, npix_total * nz, (int64_t)pl->d.nt * nv, NC, nv)) return false;
+  if (!base_ok || !encode_density_map(&tmap, dens, npix_total * nz, (int64_t)pl->d.nt * nv, NC + PKM_K1_PITCH_PAD, nv))
+    return false;
   CUtensorMap omap;
   memset(&omap, 0, sizeof(omap));
   if (nz > 256 || pl->nfi > 256 ||
@@ -676,6 +721,7 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   g.pxb = pxb; g.nt = pl->d.nt; g.is_log = is_log; g.v0 = pl->d.v0_idx;
   g.out_f32 = pl->d.precision == 1;
   g.use_tma = 2;
+  g.ncp = NC + PKM_K1_PITCH_PAD;
   KernelTimer tm(pl, PKM_K_COEFF, st);
   k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab);
   PKM_CUDA(cudaGetLastError());
