@@ -511,10 +511,14 @@ def run_b200(args):
         def model_wall(make):
             make(cube).evaluate_ybar(device=local)            # warm (tables cached on the cube)
             torch.cuda.synchronize()
-            t0_ = time.perf_counter()
-            c_ = make(cube)
-            c_.evaluate_ybar(device=local)
-            return 1e3 * (time.perf_counter() - t0_)
+            walls = []
+            for _ in range(3):                                # median of three (page-locked result buffers recycle)
+                t0_ = time.perf_counter()
+                c_ = make(cube)
+                c_.evaluate_ybar(device=local)
+                walls.append(1e3 * (time.perf_counter() - t0_))
+                del c_
+            return statistics.median(walls)
         other["growing_disk_setup_plus_evaluate_ybar"] = {
             "ms": model_wall(W_.make_disk), "note": "GrowingDisk(cube) + set_p_t/set_p_x_t/set_t_dep/set_mu_v/"
             "set_sig_v + evaluate_ybar() wall clock: the O(pixels) maps are generated in HBM (pkm_disk_maps, "
