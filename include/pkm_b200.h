@@ -90,7 +90,7 @@ PKM_API int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw, co
                         const double* delta_z, pkm_plan** plan_out);
 PKM_API int32_t pkm_plan_destroy(pkm_plan* plan);
 /* Cap the device workspace (bytes) used for intermediate spline coefficients; the
- * pixel batch is tiled to fit.  0 restores the default (4 GiB). */
+ * pixel batch is tiled to fit.  0 restores the default (8 GiB). */
 PKM_API int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes);
 /* Number of kernels launched by this plan since creation (for bench accounting). */
 PKM_API int64_t pkm_plan_launch_count(const pkm_plan* plan);

@@ -131,12 +131,18 @@ static void plan_free(pkm_plan* pl) {
   for (int i = 0; i < 2; ++i)
     for (cudaEvent_t e : {pl->ev_in[i], pl->ev_done[i], pl->ev_out[i], pl->ev_ready[i]})
       if (e) cudaEventDestroy(e);
-  if (pl->s_k2) cudaStreamDestroy(pl->s_k2);
-  if (pl->ev_k2_fork) cudaEventDestroy(pl->ev_k2_fork);
-  if (pl->ev_k2_join) cudaEventDestroy(pl->ev_k2_join);
+  for (int i = 0; i < 2; ++i) {
+    if (pl->s_k2[i]) cudaStreamDestroy(pl->s_k2[i]);
+    if (pl->ev_k2_fork[i]) cudaEventDestroy(pl->ev_k2_fork[i]);
+    if (pl->ev_k2_join[i]) cudaEventDestroy(pl->ev_k2_join[i]);
+  }
+  if (pl->s_lane) cudaStreamDestroy(pl->s_lane);
+  if (pl->ev_lane_fork) cudaEventDestroy(pl->ev_lane_fork);
+  if (pl->ev_lane_join) cudaEventDestroy(pl->ev_lane_join);
   if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
   if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
   pl->coef.release(); pl->yhat.release(); pl->ypx.release(); pl->misc.release(); pl->small.release();
+  pl->coef1.release(); pl->yhat1.release(); pl->ypx1.release();
   for (int i = 0; i < 2; ++i) {
     pl->stage_in[i].release();
     pl->stage_out[i].release();
@@ -264,7 +270,7 @@ extern "C" int32_t pkm_plan_set_workspace_limit(pkm_plan* plan, int64_t bytes) {
   return guarded([&] {
     PKM_REQUIRE(plan, "null plan");
     PKM_REQUIRE(bytes >= 0, "negative workspace limit");
-    plan->ws_limit = bytes == 0 ? (size_t(4) << 30) : size_t(bytes);
+    plan->ws_limit = bytes == 0 ? (size_t(8) << 30) : size_t(bytes);
   });
 }
 
@@ -360,6 +366,19 @@ void emit_tile(pkm_plan* pl, const OutSpec& o, const double* ypx, int64_t pix_of
 
 }  // namespace
 
+// tile lanes of the device-resident density path: PKM_TILE_LANES=1 serialises the tiles, 2 forces
+// two lanes, unset (-1) = two lanes when the tiles are small
+static int tile_lanes() {
+  const char* e = getenv("PKM_TILE_LANES");
+  return e ? atoi(e) : -1;
+}
+
+// pixel tiles of a range evaluated into an embedded (peer-memory) cube
+static int peer_tiles() {
+  const char* e = getenv("PKM_PEER_TILES");
+  return e ? std::max(1, atoi(e)) : 8;
+}
+
 // streams / events of the host-buffer pipeline (created on first use)
 static void pipe_init(pkm_plan* pl) {
   if (pl->s_copy) return;
@@ -392,7 +411,9 @@ static int32_t density_impl(pkm_plan* pl, const double* dens, int32_t is_log, in
     // buffers in flight: drain the plan's streams before handing the buffers back
     if (pl->s_copy) cudaStreamSynchronize(pl->s_copy);
     if (pl->s_comp) cudaStreamSynchronize(pl->s_comp);
-    if (pl->s_k2) cudaStreamSynchronize(pl->s_k2);
+    for (int i = 0; i < 2; ++i)
+      if (pl->s_k2[i]) cudaStreamSynchronize(pl->s_k2[i]);
+    if (pl->s_lane) cudaStreamSynchronize(pl->s_lane);
     cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
     cudaGetLastError();
   }
@@ -447,9 +468,11 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
     {
       int64_t rem = total_pg;
       if (side_transpose) {
-        // four near-equal tiles (whole CTA rows): measured best on 8 GPUs - a geometric schedule with
-        // a small last tile (less exposed copy) lost more to half-empty contraction launches
-        const int t = (int)std::min<int64_t>(max_pg, (((total_pg + 3) / 4 + 3) / 4) * 4);
+        // eight near-equal tiles (whole CTA rows) alternating between the two lanes: measured best on
+        // 8 GPUs (4 tiles 9.78, 6 tiles 9.57, 8 tiles 9.55 ms per cube); a geometric schedule with a
+        // small last tile (less exposed copy) lost more to half-empty contraction launches
+        const int nt_peer = peer_tiles();
+        const int t = (int)std::min<int64_t>(max_pg, (((total_pg + nt_peer - 1) / nt_peer + 3) / 4) * 4);
         while (rem > 0) {
           sched.push_back((int)std::min<int64_t>(rem, t));
           rem -= sched.back();
@@ -475,6 +498,27 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
     pl->yhat.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
     pl->ypx.reserve(sizeof(double) * (size_t)n * tile);
     if (in_host || out_host || side_transpose) pipe_init(pl);
+    // Device-resident input and output: the tiles alternate between two lanes (own streams and
+    // workspaces), so that the kernels of one tile fill the wave tails - and the latency-bound
+    // inverse FFT - of the other.
+    // Worth it when the tiles are small (a few waves per kernel: 8 GPUs sharing one cube, small
+    // workspaces); large tiles run in order, which also keeps per-kernel event times meaningful.
+    const int lanes_env = tile_lanes();
+    const bool lanes_auto = side_transpose || tile <= 4096;
+    const int nlanes = (!in_host && !out_host && sched.size() > 1 && (lanes_env == 2 || (lanes_env < 0 && lanes_auto))) ? 2 : 1;
+    if (nlanes == 2) {
+      pl->coef1.reserve(sizeof(double2) * (size_t)pl->ntz * pl->nfi * tile);
+      pl->yhat1.reserve(sizeof(double2) * (size_t)pl->nfo * tile);
+      if (!side_transpose) pl->ypx1.reserve(sizeof(double) * (size_t)n * tile);
+      if (!pl->s_lane) {
+        PKM_CUDA(cudaStreamCreateWithFlags(&pl->s_lane, cudaStreamNonBlocking));
+        PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_lane_fork, cudaEventDisableTiming));
+        PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_lane_join, cudaEventDisableTiming));
+      }
+      PKM_CUDA(cudaEventRecord(pl->ev_lane_fork, reinterpret_cast<cudaStream_t>(stream)));
+      PKM_CUDA(cudaStreamWaitEvent(pl->s_lane, pl->ev_lane_fork, 0));
+    }
+    cudaStream_t const st0 = reinterpret_cast<cudaStream_t>(stream);
     cudaStream_t s_in = pl->s_copy, s_out = pl->s_comp;
     const bool pm = out_layout == PKM_LAYOUT_PIXEL_MAJOR;
     OutSpec o{ybar_out, out_host, out_layout, npix, n};
@@ -489,6 +533,11 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
     for (int64_t p0 = 0; p0 < npix; p0 += sched[it], ++it) {
       const int np = sched[it];
       const int slot = (int)(it & 1);
+      const int lane = nlanes == 2 ? slot : 0;
+      cudaStream_t st = lane ? pl->s_lane : st0;
+      DevBuf& coef = lane ? pl->coef1 : pl->coef;
+      DevBuf& yhat = lane ? pl->yhat1 : pl->yhat;
+      DevBuf& ypxb = lane ? pl->ypx1 : pl->ypx;
       PkmRange range_tile("pkm density tile: coeff + contract + irfft");
       const double* src = dens;
       int64_t src_npix = npix_total, src_pix0 = pix_begin + p0;
@@ -506,15 +555,15 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
         src_npix = np;
         src_pix0 = 0;
       }
-      launch_coeff(pl, src, is_log, src_npix, src_pix0, np, tile, pl->coef.as<double2>(), st);
+      launch_coeff(pl, src, is_log, src_npix, src_pix0, np, tile, coef.as<double2>(), st);
       if (in_host) PKM_CUDA(cudaEventRecord(pl->ev_done[slot], st));
-      launch_contract(pl, pl->coef.as<double2>(), np, tile, pl->yhat.as<double2>(), st);
+      launch_contract(pl, coef.as<double2>(), np, tile, yhat.as<double2>(), st, lane);
       if (side_transpose) {
         // two pixel-major buffers (stage_out doubles as the second one)
         pl->stage_out[slot].reserve(sizeof(double) * (size_t)n * tile);
         double* ypx = pl->stage_out[slot].as<double>();
         PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_out[slot], 0));      // transpose of tile it-2 has drained it
-        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, ypx, st);
+        launch_irfft_czt(pl, yhat.as<double2>(), np, pl->d.dx * pl->d.dy, ypx, st);
         PKM_CUDA(cudaEventRecord(pl->ev_ready[slot], st));
         PKM_CUDA(cudaStreamWaitEvent(s_out, pl->ev_ready[slot], 0));
         // transpose locally, then let a copy engine move the [n][np] block into the (possibly
@@ -533,8 +582,8 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
         continue;
       }
       if (!out_host) {
-        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
-        emit_tile(pl, o, pl->ypx.as<double>(), p0, np, 0, st);
+        launch_irfft_czt(pl, yhat.as<double2>(), np, pl->d.dx * pl->d.dy, ypxb.as<double>(), st);
+        emit_tile(pl, o, ypxb.as<double>(), p0, np, 0, st);
         continue;
       }
       // host output: the staging slot must have been drained by the D2H of tile it-2
@@ -542,11 +591,11 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
       double* stage = pl->stage_out[slot].as<double>();
       PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_out[slot], 0));
       if (pm) {
-        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, stage, st);
+        launch_irfft_czt(pl, yhat.as<double2>(), np, pl->d.dx * pl->d.dy, stage, st);
       } else {
-        launch_irfft_czt(pl, pl->yhat.as<double2>(), np, pl->d.dx * pl->d.dy, pl->ypx.as<double>(), st);
+        launch_irfft_czt(pl, yhat.as<double2>(), np, pl->d.dx * pl->d.dy, ypxb.as<double>(), st);
         KernelTimer tm(pl, PKM_K_TRANSPOSE, st);
-        launch_transpose(pl->ypx.as<double>(), np, n, stage, np, 0, st);
+        launch_transpose(ypxb.as<double>(), np, n, stage, np, 0, st);
         pl->launches++;
       }
       PKM_CUDA(cudaEventRecord(pl->ev_ready[slot], st));
@@ -558,6 +607,10 @@ static int32_t density_body(pkm_plan* pl, const double* dens, int32_t is_log, in
         PKM_CUDA(cudaMemcpy2DAsync(ybar_out + p0, sizeof(double) * npix, stage, sizeof(double) * np,
                                    sizeof(double) * np, n, cudaMemcpyDeviceToHost, s_out));
       PKM_CUDA(cudaEventRecord(pl->ev_out[slot], s_out));
+    }
+    if (nlanes == 2) {
+      PKM_CUDA(cudaEventRecord(pl->ev_lane_join, pl->s_lane));
+      PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_lane_join, 0));
     }
     if (side_transpose) {
       // stream semantics for the caller: everything is complete once `st` reaches this point

@@ -1136,17 +1136,17 @@ double contract_wave_pixel_groups(const pkm_plan* pl) {
 }
 
 // side stream (+ fork / join events) for the alternate launches of one tile, created on first use
-static bool contract_side_stream(pkm_plan* pl) {
-  if (pl->s_k2) return true;
+static bool contract_side_stream(pkm_plan* pl, int lane) {
+  if (pl->s_k2[lane]) return true;
   if (getenv("PKM_CONTRACT_NO_FORK")) return false;
-  PKM_CUDA(cudaStreamCreateWithFlags(&pl->s_k2, cudaStreamNonBlocking));
-  PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_k2_fork, cudaEventDisableTiming));
-  PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_k2_join, cudaEventDisableTiming));
+  PKM_CUDA(cudaStreamCreateWithFlags(&pl->s_k2[lane], cudaStreamNonBlocking));
+  PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_k2_fork[lane], cudaEventDisableTiming));
+  PKM_CUDA(cudaEventCreateWithFlags(&pl->ev_k2_join[lane], cudaEventDisableTiming));
   return true;
 }
 
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
-                     cudaStream_t st) {
+                     cudaStream_t st, int lane) {
   if (pl->d.precision == 1) {
     const long long npg = (npix_tile + 31) / 32;
     const long long nitems = npg * pl->wsegs.nwseg;
@@ -1169,10 +1169,10 @@ void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, d
   // The launches of one tile are independent: every other one goes to a side stream so that the
   // CTAs of the next launch fill the SMs while the last wave of the previous one drains.
   const int nlaunch = (pl->wsegs.nwseg + K2_WP_SEGS - 1) / K2_WP_SEGS;
-  const bool fork = nlaunch > 1 && contract_side_stream(pl);
+  const bool fork = nlaunch > 1 && contract_side_stream(pl, lane);
   if (fork) {
-    PKM_CUDA(cudaEventRecord(pl->ev_k2_fork, st));
-    PKM_CUDA(cudaStreamWaitEvent(pl->s_k2, pl->ev_k2_fork, 0));
+    PKM_CUDA(cudaEventRecord(pl->ev_k2_fork[lane], st));
+    PKM_CUDA(cudaStreamWaitEvent(pl->s_k2[lane], pl->ev_k2_fork[lane], 0));
   }
   K2Weights wp;
   int li = 0;
@@ -1182,14 +1182,14 @@ void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, d
       for (int r = 0; r < PKM_KT; ++r)
         for (int q = 0; q < 3; ++q) wp.w[i][r][q] = pl->wsegs.w[((size_t)(ws0 + i) * PKM_KT + r) * 4 + q];
     const unsigned grid = (unsigned)(((npg + K2_WARPS - 1) / K2_WARPS) * nws);
-    cudaStream_t ls = (fork && (li & 1)) ? pl->s_k2 : st;
+    cudaStream_t ls = (fork && (li & 1)) ? pl->s_k2[lane] : st;
     k_contract<<<grid, K2_WARPS * 32, smem, ls>>>(wp, ws0, nws, pl->d_Sw, reinterpret_cast<const int4*>(pl->d_wseg), cT,
                                               yhat, pl->ntz, pl->nchunk, pl->nfi, npix_tile, pl->nfo, npg);
     PKM_CUDA(cudaGetLastError());
     pl->launches++;
   }
   if (fork) {
-    PKM_CUDA(cudaEventRecord(pl->ev_k2_join, pl->s_k2));
-    PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_k2_join, 0));
+    PKM_CUDA(cudaEventRecord(pl->ev_k2_join[lane], pl->s_k2[lane]));
+    PKM_CUDA(cudaStreamWaitEvent(st, pl->ev_k2_join[lane], 0));
   }
 }

@@ -118,7 +118,7 @@ struct pkm_plan {
   double k_ms[PKM_K_NCLASS] = {0, 0, 0, 0, 0};
   int64_t k_count[PKM_K_NCLASS] = {0, 0, 0, 0, 0};
   int num_sms = 148;
-  size_t ws_limit = size_t(4) << 30;
+  size_t ws_limit = size_t(8) << 30;
 
   // density path
   FoldTables fold;
@@ -162,8 +162,13 @@ struct pkm_plan {
   // host-buffer pipeline: s_copy = H2D stream, s_comp = D2H stream; per staging slot:
   // ev_in (H2D landed), ev_done (kernel 1 consumed it), ev_ready (output staged), ev_out (D2H done)
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
-  cudaStream_t s_k2 = nullptr;           // side stream of the contraction's alternate launches
-  cudaEvent_t ev_k2_fork = nullptr, ev_k2_join = nullptr;
+  // per tile lane (tiles alternate between two lanes whose kernels fill each other's wave tails):
+  // side stream of the contraction's alternate launches + its fork / join events
+  cudaStream_t s_k2[2] = {nullptr, nullptr};
+  cudaEvent_t ev_k2_fork[2] = {nullptr, nullptr}, ev_k2_join[2] = {nullptr, nullptr};
+  cudaStream_t s_lane = nullptr;         // main stream of lane 1 (lane 0 runs on the caller's stream)
+  cudaEvent_t ev_lane_fork = nullptr, ev_lane_join = nullptr;
+  DevBuf coef1, yhat1, ypx1;             // lane 1's workspace (lane 0: coef, yhat, ypx)
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
               ev_out[2] = {nullptr, nullptr}, ev_ready[2] = {nullptr, nullptr};
 };
@@ -178,7 +183,7 @@ void launch_coeff(pkm_plan* pl, const double* dens, int is_log, int64_t npix_tot
 // pixel groups (of 32) that fill the GPU once with contraction CTAs (real valued)
 double contract_wave_pixel_groups(const pkm_plan* pl);
 void launch_contract(pkm_plan* pl, const double2* cT, int npix_tile, int xpad, double2* yhat,
-                     cudaStream_t st);
+                     cudaStream_t st, int lane = 0);
 // gaussian path -> Yhat[x][nfo]
 void launch_gaussian(pkm_plan* pl, const double* P_txz, const double* mu, const int64_t* mu_st,
                      const double* sig, const int64_t* sig_st, int64_t nx2, int64_t npix_total,
