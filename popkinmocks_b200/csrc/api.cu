@@ -125,7 +125,7 @@ static void plan_free(pkm_plan* pl) {
   };
   fr(pl->d_CRt); fr(pl->d_CIt); fr(pl->d_CIt_oct); fr(pl->d_CR); fr(pl->d_CI); fr(pl->d_Sw); fr(pl->d_Sw32);
   fr(pl->d_wseg); fr(pl->d_wseg_w); fr(pl->d_SA); fr(pl->d_SA32); fr(pl->d_omega);
-  fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_wn);
+  fr(pl->d_chi); fr(pl->d_alpha); fr(pl->d_twiddle); fr(pl->d_Bhat); fr(pl->d_Bhat_h); fr(pl->d_pre); fr(pl->d_post); fr(pl->d_htw); fr(pl->d_wn);
   fr(pl->d_log_dt); fr(pl->d_log_dz); fr(pl->d_exp_tab);
   collect_timers(pl);
   for (int i = 0; i < 2; ++i)
@@ -232,6 +232,12 @@ extern "C" int32_t pkm_plan_create(const pkm_cube_desc* desc, const double* FXw,
     pl->d_alpha = upload(pl->czt.alpha);
     pl->d_twiddle = reinterpret_cast<double2*>(upload(pl->czt.twiddle));
     PKM_CUDA(cudaMalloc(&pl->d_Bhat, sizeof(double2) * pl->czt.M));
+    if (!pl->czt.pre.empty()) {
+      pl->d_pre = reinterpret_cast<double2*>(upload(pl->czt.pre));
+      pl->d_post = reinterpret_cast<double2*>(upload(pl->czt.post));
+      pl->d_htw = reinterpret_cast<double2*>(upload(pl->czt.htw));
+      PKM_CUDA(cudaMalloc(&pl->d_Bhat_h, sizeof(double2) * pl->czt.M));
+    }
     czt_prepare_filter(pl);
     {
       const long double PI_L = 3.14159265358979323846264338327950288419716939937510L;

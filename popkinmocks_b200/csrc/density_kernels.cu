@@ -512,6 +512,231 @@ k_coeff_oct(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CU
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ----------------------------------------------------------------------------
+// Barrier-free form of the octet kernel (the default).  Same tiles, same warp items, same fused
+// fold / exp, but no CTA-wide barrier inside the tile loop:
+//   * a PRODUCER warp issues the 2-D tensor copies: slab buffer b is refilled as soon as every
+//     consumer warp has arrived on empty[b] (mbarrier, one arrival per warp item) - the consumer
+//     side is the usual full[b] complete_tx wait;
+//   * a consumer warp releases the slab right after its last B fragment and then writes its
+//     accumulators straight to cT[x/32][t*nz + z][m][x%32] with 256-bit stores (a lane holds the
+//     complex coefficients of two adjacent pixels = one 32-byte sector; a warp store covers eight
+//     full 128-byte lines) - no staging box, so the slab is read-only for its whole life.
+// The warps of a CTA drift apart by up to one tile: one warp's stores, slab wait and exp chains run
+// under the other warps' DMMAs instead of every warp idling at two barriers per tile.
+// ----------------------------------------------------------------------------
+// Two table exponentials (exp_tab.cuh: same constants, same operation order, same results) cut
+// into stages so that the caller can interleave them with independent work.  The range / NaN
+// handling is one integer test on the high word (|x| >= 708 or NaN takes the rare slow path)
+// instead of three FP64 compares per value.
+// (The FP64 operations are volatile asm statements: that pins their order relative to the DMMAs,
+// which the compiler otherwise clusters.)
+__device__ __forceinline__ double vfma(double a, double b, double c) {
+  double d;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+  return d;
+}
+__device__ __forceinline__ double vmul(double a, double b) {
+  double d;
+  asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b));
+  return d;
+}
+__device__ __forceinline__ double vadd(double a, double b) {
+  double d;
+  asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b));
+  return d;
+}
+struct ExpPair {
+  double xa, xb, ya, yb;
+  double ta, tb, fa, fb, ra, rb, qa, qb, sa, sb, Ta, Tb;
+  __device__ __forceinline__ void stage(int st, const double* __restrict__ tab) {
+    switch (st) {
+      case 0:
+        ta = vfma(xa, 369.32993046757463228, 6755399441055744.0);
+        tb = vfma(xb, 369.32993046757463228, 6755399441055744.0);
+        fa = vadd(ta, -6755399441055744.0);
+        fb = vadd(tb, -6755399441055744.0);
+        break;
+      case 1:
+        ra = vfma(fa, -2.70760617331688990816e-03, xa);
+        rb = vfma(fb, -2.70760617331688990816e-03, xb);
+        Ta = tab[__double2loint(ta) & (PKM_EXP_TAB - 1)];
+        Tb = tab[__double2loint(tb) & (PKM_EXP_TAB - 1)];
+        break;
+      case 2:
+        ra = vfma(fa, -7.45396456746323320321e-13, ra);
+        rb = vfma(fb, -7.45396456746323320321e-13, rb);
+        break;
+      case 3:
+        qa = vfma(ra, 1.0 / 24.0, 1.0 / 6.0);
+        qb = vfma(rb, 1.0 / 24.0, 1.0 / 6.0);
+        sa = vmul(ra, ra);
+        sb = vmul(rb, rb);
+        break;
+      case 4:
+        qa = vfma(qa, ra, 0.5);
+        qb = vfma(qb, rb, 0.5);
+        break;
+      case 5:
+        qa = vfma(sa, qa, ra);                   // e^r - 1
+        qb = vfma(sb, qb, rb);
+        break;
+      default: {
+        qa = vfma(Ta, qa, Ta);                   // in [1, 2.01)
+        qb = vfma(Tb, qb, Tb);
+        const int ka = __double2loint(ta), kb = __double2loint(tb);
+        ya = __hiloint2double(__double2hiint(qa) + ((ka >> 8) << 20), __double2loint(qa));
+        yb = __hiloint2double(__double2hiint(qb) + ((kb >> 8) << 20), __double2loint(qb));
+        // |x| >= 708, inf or NaN: rare, and a warp-uniform branch keeps the FP64 compares out of
+        // the common path
+        const bool rare = max(__double2hiint(xa) & 0x7fffffff, __double2hiint(xb) & 0x7fffffff) >= 0x40862000;
+        if (__any_sync(0xffffffffu, rare)) {
+          ya = xa < -708.0 ? 0.0 : (xa > 709.0 ? INFINITY : (xa != xa ? xa : ya));
+          yb = xb < -708.0 ? 0.0 : (xb > 709.0 ? INFINITY : (xb != xb ? xb : yb));
+        }
+        break;
+      }
+    }
+  }
+};
+
+constexpr int K1F_THREADS = K1_THREADS + 32;   // 12 consumer warps + the producer warp
+template <int TM, bool IS_LOG>
+__global__ void __launch_bounds__(K1F_THREADS, 1)
+k_coeff_flow(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __restrict__ CRt,
+             const double* __restrict__ CIt, const double* __restrict__ exp2_tab,
+             double2* __restrict__ cT) {
+  extern __shared__ __align__(128) double smem[];
+  constexpr int MB = TM;
+  const int nv = g.nv, nz = g.nz, nfi = g.nfi, ne = g.ne, pxb = g.pxb, v0 = g.v0;
+  const int nks = (ne + 3) >> 2;
+  const int frag_elems = nks * MB * 32;
+  const int NCP = g.ncp;                         // slab pitch (see k_coeff_oct)
+  const int slab_elems = nv * NCP;
+  const int buf_elems = (slab_elems + 15) & ~15;
+  double* As_r = smem;
+  double* As_i = As_r + frag_elems;
+  double* Bbuf = As_i + frag_elems;
+  double* etab = Bbuf + 2 * (size_t)buf_elems;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(etab + PKM_EXP_TAB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nitem = nz * (pxb >> 3);
+  for (int i = tid; i < frag_elems; i += K1F_THREADS) {
+    As_r[i] = CRt[i];
+    As_i[i] = CIt[i];
+  }
+  for (int i = tid; i < PKM_EXP_TAB; i += K1F_THREADS) etab[i] = exp2_tab[i];
+  const unsigned full0 = smem_u32(bars), empty0 = full0 + 16u;
+  if (tid == 0) {
+    mbar_init(full0, 1);
+    mbar_init(full0 + 8, 1);
+    mbar_init(empty0, (unsigned)nitem);
+    mbar_init(empty0 + 8, (unsigned)nitem);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nxb = (g.npix_tile + pxb - 1) / pxb;
+  const long long ntile = (long long)nxb * g.nt;
+  const long long tstep = gridDim.x;
+
+  if (warp == K1_WARPS) {                        // ---- producer ----
+    if (lane == 0) {
+      long long tile = blockIdx.x;
+      for (int it = 0; tile < ntile; tile += tstep, ++it) {
+        const int b = it & 1;
+        if (it >= 2) mbar_wait(empty0 + 8u * b, (unsigned)((it >> 1) - 1) & 1u);
+        const int t = (int)(tile / nxb);
+        const int xb = (int)(tile - (long long)t * nxb);
+        mbar_expect_tx(full0 + 8u * b, (unsigned)slab_elems * 8u);
+        tensor2d_g2s(smem_u32(Bbuf + (size_t)b * buf_elems), &tmap,
+                     (int)((g.pix0 + (long long)xb * pxb) * nz), t * nv, full0 + 8u * b);
+      }
+    }
+    return;
+  }
+  if (warp >= nitem) return;                     // fewer items than consumer warps
+
+  // ---- consumers: warp = (metallicity iz, pixel octet oct) ----
+  const int iz = warp % nz, oct = warp / nz;
+  const int fr = lane >> 2, fk = lane & 3;
+  const double* Ar = As_r + lane;
+  const double* Ai = As_i + lane;
+  const size_t ntz = (size_t)g.nt * nz;
+  long long tile = blockIdx.x;
+  for (int it = 0; tile < ntile; tile += tstep, ++it) {
+    const int b = it & 1;
+    mbar_wait(full0 + 8u * b, (unsigned)(it >> 1) & 1u);
+    const int t = (int)(tile / nxb);
+    const int xb = (int)(tile - (long long)t * nxb);
+    const double* Bcol = Bbuf + (size_t)b * buf_elems + (oct * 8 + fr) * nz + iz;
+    double accr[MB][2], acci[MB][2];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) accr[mb][0] = accr[mb][1] = acci[mb][0] = acci[mb][1] = 0.0;
+    auto fetch = [&](int ks, double& pa, double& pb) {
+      const int u = min(ks * 4 + fk, ne - 1);               // u >= ne has zero A
+      pa = Bcol[(size_t)row_plus(u, v0, nv) * NCP];
+      pb = Bcol[(size_t)row_minus(u, v0, nv) * NCP];
+    };
+    // Software pipeline: raw values two k-steps ahead; the exp / fold of k-step ks+1 is cut into
+    // seven stages that are issued BETWEEN the DMMA pairs of k-step ks (DMMA and DFMA share the
+    // FP64 pipe: left to the compiler the two dependent exp chains - ~10 FP64 latencies - sit
+    // after the 14 DMMAs, where nothing of this warp covers them).
+    double pa, pb, be, bo;
+    fetch(0, pa, pb);
+    if (IS_LOG) {
+      pa = exp_tab(pa, etab);
+      pb = exp_tab(pb, etab);
+    }
+    be = pa + pb;
+    bo = pa - pb;
+    fetch(nks > 1 ? 1 : 0, pa, pb);
+    constexpr bool is_log = IS_LOG;
+    for (int ks = 0; ks < nks; ++ks) {
+      ExpPair ep;
+      ep.xa = pa;
+      ep.xb = pb;
+      double nbe = 0.0, nbo = 0.0;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        dmma_m8n8k4(accr[mb][0], accr[mb][1], Ar[(ks * MB + mb) * 32], be);
+        dmma_m8n8k4(acci[mb][0], acci[mb][1], Ai[(ks * MB + mb) * 32], bo);
+        // stages [mb * 7 / MB, (mb + 1) * 7 / MB) of the next step's B fragment
+#pragma unroll
+        for (int st = (mb * 7) / MB; st < ((mb + 1) * 7) / MB; ++st) {
+          if (st == 0 && ks + 2 < nks) fetch(ks + 2, pa, pb);
+          if (is_log) ep.stage(st, etab);
+          if (st == 6) {
+            const double ya = is_log ? ep.ya : ep.xa, yb = is_log ? ep.yb : ep.xb;
+            nbe = vadd(ya, yb);
+            nbo = vadd(ya, -yb);
+          }
+        }
+      }
+      be = nbe;
+      bo = nbo;
+    }
+    // the slab is consumed: one arrival per warp lets the producer refill it
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");
+    const int xg0 = xb * pxb + oct * 8;
+    const size_t base = (((size_t)(xg0 >> 5) * ntz + (size_t)t * nz + iz) * nfi) * 32 + (xg0 & 31) + 2 * fk;
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+      const int m = mb * 8 + fr;
+      if (m < nfi) {
+        const size_t ci = base + (size_t)m * 32;
+        if (g.out_f32)
+          *reinterpret_cast<float4*>(reinterpret_cast<float2*>(cT) + ci) =
+              make_float4((float)accr[mb][0], (float)acci[mb][0], (float)accr[mb][1], (float)acci[mb][1]);
+        else
+          asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(cT + ci), "d"(accr[mb][0]),
+                       "d"(acci[mb][0]), "d"(accr[mb][1]), "d"(acci[mb][1]) : "memory");
+      }
+    }
+  }
+}
+
 // A operand in DMMA fragment order: element [ks][mb][lane] = C[m = mb*8 + lane/4][u = ks*4 + lane%4]
 // (zero outside the matrix), so a warp's fragment load is one contiguous 256-byte read.
 // `shift` = 1 stores column u of the fragment table from matrix column u - 1 (zero for u = 0): the
@@ -659,6 +884,11 @@ static size_t coeff_oct_smem(const pkm_plan* pl, int NC) {
   return ((size_t)2 * pl->nfiP + 2 * buf_elems + PKM_EXP_TAB) * sizeof(double) + 16;
 }
 
+static size_t coeff_flow_smem(const pkm_plan* pl, int NC) {
+  const size_t buf_elems = ((size_t)pl->d.nv * (NC + PKM_K1_PITCH_PAD) + 15) & ~size_t(15);
+  return ((size_t)2 * pl->nfiP + 2 * buf_elems + PKM_EXP_TAB) * sizeof(double) + 32;
+}
+
 // 4-D view of the coefficient array cT[x/32][t*nz+z][m][x%32] (complex) in scalar elements:
 // dims {64 = 32 pixels x re/im, nfi, nt*nz, xpad/32}; box = {2 pxb, nfi, nz, 1} = one tile
 static bool encode_coeff_map(CUtensorMap* map, void* cT, bool f32, int nfi, int ntz, int ngroup32,
@@ -723,7 +953,15 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   g.use_tma = 2;
   g.ncp = NC + PKM_K1_PITCH_PAD;
   KernelTimer tm(pl, PKM_K_COEFF, st);
-  k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab);
+  const char* flow = getenv("PKM_COEFF_FLOW");          // "0" = the staged-store (TMA tensor store) form
+  if (!flow || atoi(flow) != 0) {
+    const size_t fsmem = coeff_flow_smem(pl, NC);
+    auto kern = is_log ? k_coeff_flow<TM, true> : k_coeff_flow<TM, false>;
+    PKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    kern<<<grid, K1F_THREADS, fsmem, st>>>(tmap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab, cT);
+  } else {
+    k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab);
+  }
   PKM_CUDA(cudaGetLastError());
 #ifdef PKM_K1_PROF
   {

@@ -14,6 +14,9 @@
 // inverse = its exact stage-by-stage inverse, so no bit-reversal pass is needed: the filter
 // spectrum is prepared once with the same forward routine (same permuted order).
 // Chirp phases are reduced exactly (j^2 mod 2n in integers) on the host.
+#include <algorithm>
+#include <cstdlib>
+
 #include "pkm_internal.h"
 
 constexpr int CZT_THREADS = 512;   // M/16 radix-16 work items for M = 8192; 128 registers per thread
@@ -321,6 +324,269 @@ k_irfft_czt(const double2* __restrict__ yhat, long long npix, int n, int nfo, in
 }
 
 // ----------------------------------------------------------------------------
+// "Halves" variant for M = 2 * 16^p (M = 8192 at the headline n_fft = 4907; also 512 and 32).
+// The chirp-z input occupies k < nfo <= M/2, so the first radix-2 DIF stage is free:
+//   half 0 = a[k],  half 1 = a[k] W_M^k   (folded into the input tables pre[0], pre[1]),
+// and the two H = M/2 point transforms are pure radix-16: p passes each way.  The LAST forward
+// pass and the FIRST inverse pass work on the same 16 contiguous elements, so they are fused in
+// registers around the filter multiply, and the radix-2 stage that rejoins the halves is fused
+// into the output pass (tables post[0], post[1] carry the chirp, the sign and conj W_M^m).
+// Per pixel: 2p passes + the output sweep instead of 2p + 2 + ..., 10 instead of 14 array sweeps
+// through shared memory at M = 8192, 6 CTA barriers instead of 8, and the per-pass twiddles
+// (273 values) live in shared memory instead of behind an L2 round trip at the head of every pass.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double2 w16_mul(double2 x, int k) {   // x * exp(-2 pi i k / 16)
+  const double C1 = 0.92387953251128674, S1 = 0.38268343236508977, C2 = 0.70710678118654752;
+  switch (k) {
+    case 0: return x;
+    case 1: return cmul(x, make_double2(C1, -S1));
+    case 2: return make_double2(C2 * (x.x + x.y), C2 * (x.y - x.x));
+    case 3: return cmul(x, make_double2(S1, -C1));
+    case 4: return make_double2(x.y, -x.x);
+    case 6: return make_double2(C2 * (x.y - x.x), -C2 * (x.x + x.y));
+    default: return cmul(x, make_double2(-C1, S1));   // k = 9
+  }
+}
+__device__ __forceinline__ double2 w16_mulc(double2 x, int k) {  // x * exp(+2 pi i k / 16)
+  const double C1 = 0.92387953251128674, S1 = 0.38268343236508977, C2 = 0.70710678118654752;
+  switch (k) {
+    case 0: return x;
+    case 1: return cmulc(x, make_double2(C1, -S1));
+    case 2: return make_double2(C2 * (x.x - x.y), C2 * (x.x + x.y));
+    case 3: return cmulc(x, make_double2(S1, -C1));
+    case 4: return make_double2(-x.y, x.x);
+    case 6: return make_double2(-C2 * (x.x + x.y), C2 * (x.x - x.y));
+    default: return cmulc(x, make_double2(-C1, S1));
+  }
+}
+
+// one forward radix-16 item with block twiddle u (level 1: u^m W16^(m b), level 2: (u^4)^n)
+__device__ __forceinline__ void r16_fwd(double2 (&x)[4][4], double2 u) {
+  Tw16 tw;
+  tw.init(u);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    bfly4_fwd(x[0][b], x[1][b], x[2][b], x[3][b]);
+    x[1][b] = cmul(x[1][b], tw.level1(1, b));
+    x[2][b] = cmul(x[2][b], tw.level1(2, b));
+    x[3][b] = cmul(x[3][b], tw.level1(3, b));
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    bfly4_fwd(x[a][0], x[a][1], x[a][2], x[a][3]);
+    x[a][1] = cmul(x[a][1], tw.v[0]);
+    x[a][2] = cmul(x[a][2], tw.v[1]);
+    x[a][3] = cmul(x[a][3], tw.v[2]);
+  }
+}
+__device__ __forceinline__ void r16_inv(double2 (&x)[4][4], double2 u) {
+  Tw16 tw;
+  tw.init(u);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    x[a][1] = cmulc(x[a][1], tw.v[0]);
+    x[a][2] = cmulc(x[a][2], tw.v[1]);
+    x[a][3] = cmulc(x[a][3], tw.v[2]);
+    bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    x[1][b] = cmulc(x[1][b], tw.level1(1, b));
+    x[2][b] = cmulc(x[2][b], tw.level1(2, b));
+    x[3][b] = cmulc(x[3][b], tw.level1(3, b));
+    bfly4_inv(x[0][b], x[1][b], x[2][b], x[3][b]);
+  }
+}
+// the same with u = 1 (blocks of 16 contiguous elements): only the W16 constants remain
+__device__ __forceinline__ void r16_fwd_unit(double2 (&x)[4][4]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    bfly4_fwd(x[0][b], x[1][b], x[2][b], x[3][b]);
+#pragma unroll
+    for (int m = 1; m < 4; ++m) x[m][b] = w16_mul(x[m][b], m * b);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) bfly4_fwd(x[a][0], x[a][1], x[a][2], x[a][3]);
+}
+__device__ __forceinline__ void r16_inv_unit(double2 (&x)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+#pragma unroll
+    for (int m = 1; m < 4; ++m) x[m][b] = w16_mulc(x[m][b], m * b);
+    bfly4_inv(x[0][b], x[1][b], x[2][b], x[3][b]);
+  }
+}
+
+// shared-memory twiddles of the halves transforms: htw = for Nb = H, H/16, ..., 256 the Nb/16 values
+// exp(-2 pi i j / Nb) (the u of a radix-16 pass with block Nb), concatenated (CztTables::htw)
+__device__ __forceinline__ void halves_stage_twiddles(double2* stw, const double2* __restrict__ htw, int M) {
+  int off = 0;
+  for (int Nb = M >> 1; Nb > 16; Nb >>= 4) off += Nb >> 4;
+  for (int j = threadIdx.x; j < off; j += blockDim.x) stw[j] = htw[j];
+}
+__host__ __device__ constexpr size_t halves_twiddle_elems(size_t M) { return M / 30 + 16; }   // >= sum of Nb/16
+
+// forward passes Nb = H ... 256 of both halves (in place in s, first pass fed by `in(h, k)`);
+// returns the twiddle offset after the last pass.  The Nb = 16 pass is left to the caller.
+template <class In>
+__device__ __forceinline__ int halves_forward(double2* s, const double2* stw, int M, int logH, In in,
+                                              bool& first) {
+  const int H = M >> 1;
+  int toff = 0;
+  for (int Nb = H; Nb > 16; Nb >>= 4) {
+    const int q = Nb >> 2, qq = Nb >> 4;
+    for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
+      const int h = i >> (logH - 4), li = i & ((H >> 4) - 1);
+      const int j = li & (qq - 1);
+      const int lbase = (li - j) * 16 + j;
+      double2 x[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int k = lbase + a * q + b * qq;
+          x[a][b] = first ? in(h, k) : s[sp(h * H + k)];
+        }
+      r16_fwd(x, stw[toff + j]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s[sp(h * H + lbase + a * q + b * qq)] = x[a][b];
+    }
+    __syncthreads();
+    toff += qq;
+    first = false;
+  }
+  return toff;
+}
+
+struct FilterHalvesInput {     // genuine radix-2 DIF stage of a full-length input
+  const double2* b;
+  const double2* twM;          // W_M^k
+  int H;
+  __device__ __forceinline__ double2 operator()(int h, int k) const {
+    const double2 lo = b[k], hi = b[k + H];
+    return h == 0 ? cadd(lo, hi) : cmul(csub(lo, hi), __ldg(twM + k));
+  }
+};
+struct CztHalvesInput {        // pre[h][k] = alpha_k chi_k (W_M^k)^h; DC / Nyquist use the real part only
+  const double2* yin;
+  const double2* pre;
+  int nfo, nyq;
+  __device__ __forceinline__ double2 operator()(int h, int k) const {
+    if (k >= nfo) return make_double2(0.0, 0.0);
+    double2 a = yin[k];
+    if (k == 0 || k == nyq) a.y = 0.0;
+    return cmul(a, __ldg(pre + (size_t)h * nfo + k));
+  }
+};
+
+__global__ void __launch_bounds__(512)
+k_filter_spectrum_h(const double2* __restrict__ bfilt, double2* __restrict__ Bhat, int M, int logM,
+                    const double2* __restrict__ tw, const double2* __restrict__ htw) {
+  extern __shared__ double2 sbuf[];
+  double2* s = sbuf;
+  double2* stw = sbuf + sp_elems(M);
+  const int H = M >> 1, logH = logM - 1;
+  halves_stage_twiddles(stw, htw, M);
+  __syncthreads();
+  FilterHalvesInput in{bfilt, tw + M, H};
+  bool first = true;
+  halves_forward(s, stw, M, logH, in, first);
+  for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
+    const int base = i * 16;                   // half h = base / H, contiguous block of 16
+    double2 x[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int idx = base + a * 4 + b;
+        x[a][b] = first ? in(idx >= H, idx & (H - 1)) : s[sp(idx)];
+      }
+    r16_fwd_unit(x);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Bhat[base + a * 4 + b] = x[a][b];
+  }
+}
+
+__global__ void __launch_bounds__(512)
+k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, int M, int logM,
+              double scale, const double2* __restrict__ pre, const double2* __restrict__ post,
+              const double2* __restrict__ htw, const double2* __restrict__ Bhat,
+              double* __restrict__ out) {
+  extern __shared__ double2 sbuf[];
+  double2* s = sbuf;
+  double2* stw = sbuf + sp_elems(M);
+  const int H = M >> 1, logH = logM - 1;
+  halves_stage_twiddles(stw, htw, M);
+  __syncthreads();
+  const int nyq = (n & 1) ? -1 : nfo - 1;
+  for (long long px = blockIdx.x; px < npix; px += gridDim.x) {
+    CztHalvesInput in{yhat + (size_t)px * nfo, pre, nfo, nyq};
+    bool first = true;
+    int toff = halves_forward(s, stw, M, logH, in, first);
+    // last forward pass (blocks of 16), filter, first inverse pass: all on the same 16 elements
+    for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
+      const int base = i * 16;
+      double2 x[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int idx = base + a * 4 + b;
+          x[a][b] = first ? in(idx >= H, idx & (H - 1)) : s[sp(idx)];
+        }
+      r16_fwd_unit(x);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[a][b] = cmul(x[a][b], __ldg(Bhat + base + a * 4 + b));
+      r16_inv_unit(x);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s[sp(base + a * 4 + b)] = x[a][b];
+    }
+    __syncthreads();
+    // inverse passes: blocks of D -> 16 D, D = 16 ... H/16
+    for (int D = 16; 16 * D <= H; D <<= 4) {
+      const int qq = D, q = 4 * D;
+      toff -= qq;
+      for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
+        const int h = i >> (logH - 4), li = i & ((H >> 4) - 1);
+        const int j = li & (qq - 1);
+        const int base = h * H + (li - j) * 16 + j;
+        double2 x[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) x[a][b] = s[sp(base + a * q + b * qq)];
+        r16_inv(x, stw[toff + j]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) s[sp(base + a * q + b * qq)] = x[a][b];
+      }
+      __syncthreads();
+    }
+    // output sweep: z[m] = z0[i] +- conj(W_M^i) z1[i] (i = m mod H), y[m] = Re(chi[m] z[m]) * scale
+    //             = Re(post0[m] z0[i] + post1[m] z1[i]) * scale
+    double* yo = out + (size_t)px * n;
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+      const int i = m & (H - 1);
+      const double2 z0 = s[sp(i)], z1 = s[sp(H + i)];
+      const double2 p0 = __ldg(post + m), p1 = __ldg(post + n + m);
+      yo[m] = (fma(p0.x, z0.x, -p0.y * z0.y) + fma(p1.x, z1.x, -p1.y * z1.y)) * scale;
+    }
+    __syncthreads();   // the next pixel's first pass overwrites s
+  }
+}
+
+// ----------------------------------------------------------------------------
 // four-step variant for M = R * C > shared memory (C = 4096 in smem, R <= 16 rows in a CTA-private,
 // L2-resident global scratch g[R][C]):
 //   forward: column DFTs of length R (direct, R^2 complex MACs per column) with the twiddle
@@ -521,8 +787,21 @@ void czt_prepare_filter(pkm_plan* pl) {
     }
   }
   PKM_CUDA(cudaGetLastError());
+  if (pl->d_Bhat_h) {
+    const size_t smem = sizeof(double2) * (sp_elems(c.M) + halves_twiddle_elems(c.M));
+    PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_filter_spectrum_h<<<1, std::max(32, std::min(512, c.M / 16)), smem>>>(d_b, pl->d_Bhat_h, c.M, c.logM, pl->d_twiddle, pl->d_htw);
+    PKM_CUDA(cudaGetLastError());
+  }
   PKM_CUDA(cudaDeviceSynchronize());
   cudaFree(d_b);
+}
+
+// M = 2 * 16^p, one-piece transform: the halves kernel applies (PKM_IRFFT_HALVES=0 turns it off)
+bool czt_halves_ok(const CztTables& c) {
+  if (c.R != 1 || c.M < 32 || (c.logM - 1) % 4 != 0) return false;
+  const char* e = getenv("PKM_IRFFT_HALVES");
+  return !(e && atoi(e) == 0);
 }
 
 template <int R>
@@ -542,7 +821,14 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
   const CztTables& c = pl->czt;
   const double s = scale / ((double)c.M * (double)c.n);
   KernelTimer tm(pl, PKM_K_IRFFT, st);
-  if (c.R == 1) {
+  if (pl->d_Bhat_h && czt_halves_ok(c)) {
+    const size_t smem = sizeof(double2) * (sp_elems(c.M) + halves_twiddle_elems(c.M));
+    PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+    const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
+    k_irfft_czt_h<<<grid, std::max(32, std::min(512, c.M / 16)), smem, st>>>(
+        yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_pre, pl->d_post, pl->d_htw, pl->d_Bhat_h, out);
+  } else if (c.R == 1) {
     const size_t smem = sizeof(double2) * sp_elems(c.M);
     PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));

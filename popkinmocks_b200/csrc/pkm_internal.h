@@ -95,7 +95,12 @@ struct CztTables {
   std::vector<double> alpha;   // [nfo] weights 1,2,...,2,(1 if n even)
   std::vector<double> twiddle; // [M] complex: exp(-2*pi*i*j/M)
   std::vector<double> bfilt;   // [M] complex: conj chirp laid out circularly (time domain)
+  // halves kernel (M = 2 * 16^p): input weights pre[h][k] = alpha_k chi_k (W_M^k)^h, h < 2, k < nfo;
+  // output weights post[0][m] = chi_m, post[1][m] = +-chi_m conj(W_M^(m mod M/2)), m < n
+  std::vector<double> pre, post;
+  std::vector<double> htw;     // radix-16 block twiddles exp(-2 pi i j/Nb), j < Nb/16, for Nb = M/2, M/32, ..., 256
 };
+bool czt_halves_ok(const CztTables& c);
 void build_czt_tables(int n, CztTables& out);
 
 // ----------------------------------------------------------------------------
@@ -148,6 +153,10 @@ struct pkm_plan {
   double* d_alpha = nullptr;
   double2* d_twiddle = nullptr;
   double2* d_Bhat = nullptr;    // [M] forward transform of bfilt, in the kernel's permuted order
+  double2* d_Bhat_h = nullptr;  // [M] the same in the order of the halves kernel (M = 2 * 16^p only)
+  double2* d_pre = nullptr;     // [2][nfo] input weights of the halves kernel
+  double2* d_post = nullptr;    // [2][n] output weights of the halves kernel
+  double2* d_htw = nullptr;     // block twiddles of the halves kernel
   double2* d_wn = nullptr;      // [n] exp(+2 pi i r / n) for the naive cross-check transform
 
   double* d_exp_tab = nullptr;  // [256] 2^(j/256) for exp_tab()

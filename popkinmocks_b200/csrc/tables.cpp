@@ -255,6 +255,39 @@ void build_czt_tables(int n, CztTables& out) {
     out.twiddle[2 * (2 * size_t(C) + j)] = (double)cosl(ang);
     out.twiddle[2 * (2 * size_t(C) + j) + 1] = (double)sinl(ang);
   }
+  // halves kernel tables (one-piece transforms with M = 2 * 16^p), phases reduced exactly:
+  // chi_k (W_M^k)^h = exp(i pi (k^2 mod 2n)/n - 2 pi i h k/M)
+  out.pre.clear();
+  out.post.clear();
+  out.htw.clear();
+  if (R == 1 && M >= 32 && (logM - 1) % 4 == 0) {
+    const int nfo = out.nfo, H = M / 2;
+    for (int Nb = H; Nb > 16; Nb >>= 4)
+      for (int j = 0; j < Nb / 16; ++j) {
+        const long double ang = -2.0L * PI_L * (long double)j / (long double)Nb;
+        out.htw.push_back((double)cosl(ang));
+        out.htw.push_back((double)sinl(ang));
+      }
+    out.htw.resize(out.htw.size() + 2, 0.0);   // never empty (M = 32 has no such pass)
+    out.pre.assign(size_t(4) * nfo, 0.0);
+    for (int h = 0; h < 2; ++h)
+      for (long long k = 0; k < nfo; ++k) {
+        const long double ang = PI_L * (long double)((k * k) % (2LL * n)) / (long double)n -
+                                2.0L * PI_L * (long double)(h * k) / (long double)M;
+        out.pre[2 * (size_t(h) * nfo + k)] = out.alpha[k] * (double)cosl(ang);
+        out.pre[2 * (size_t(h) * nfo + k) + 1] = out.alpha[k] * (double)sinl(ang);
+      }
+    out.post.assign(size_t(4) * n, 0.0);
+    for (long long m = 0; m < n; ++m) {
+      const long double a0 = PI_L * (long double)((m * m) % (2LL * n)) / (long double)n;
+      out.post[2 * m] = (double)cosl(a0);
+      out.post[2 * m + 1] = (double)sinl(a0);
+      const long double a1 = a0 + 2.0L * PI_L * (long double)(m % H) / (long double)M;
+      const double sgn = m < H ? 1.0 : -1.0;
+      out.post[2 * (size_t(n) + m)] = sgn * (double)cosl(a1);
+      out.post[2 * (size_t(n) + m) + 1] = sgn * (double)sinl(a1);
+    }
+  }
   // z[m] = chi[m] * sum_k (a[k] chi[k]) conj(chi[m-k]),  m-k in [-(nfo-1), n-1]
   out.bfilt.assign(size_t(2) * M, 0.0);
   for (long long j = -(long long)(out.nfo - 1); j <= (long long)(n - 1); ++j) {

@@ -94,6 +94,37 @@ def test_irfft_matches_numpy(gpu_ok, name):
     assert rel_err(plan.irfft(Y, naive=True), ref) < 1e-12
 
 
+@pytest.mark.parametrize("lmd,n_fft,M", [
+    ((5000, 5027), 17, 32), ((5000, 5032), 20, 32),      # M = 2 * 16: the fused middle pass is the whole transform
+    ((5000, 5500), 300, 512), ((5000, 5480), 288, 512),  # M = 2 * 16^2
+])
+def test_irfft_halves_kernel_sizes(gpu_ok, lmd, n_fft, M):
+    """The M = 2 * 16^p inverse-FFT kernel (k_irfft_czt_h; M = 8192 is the headline n_fft = 4907,
+    covered by test_irfft_matches_numpy on g3) at its other sizes, odd and even n_fft."""
+    import popkinmocks_b200 as pkm
+    ssps = pkm.milesSSPs(lmd_min=lmd[0], lmd_max=lmd[1], age_rebin=8, z_rebin=4)
+    cube = pkm.ifu_cube.IFUCube(ssps=ssps, nx1=2, nx2=2, nv=21, vrng=(-1000.0, 1000.0))
+    plan = pkm.engine.get_plan(cube)
+    assert plan.n_fft == n_fft
+    rng = np.random.default_rng(n_fft)
+    Y = rng.standard_normal((300, plan.nfo)) + 1j * rng.standard_normal((300, plan.nfo))
+    ref = np.fft.irfft(Y, n_fft, axis=1)
+    assert rel_err(plan.irfft(Y), ref) < 1e-13
+    assert rel_err(plan.irfft(Y, scale=0.25), 0.25 * ref) < 1e-13
+
+
+def test_irfft_generic_kernel_still_matches(gpu_ok, monkeypatch):
+    """PKM_IRFFT_HALVES=0 keeps the general radix-16/4/2 kernel reachable at the headline size."""
+    plan = _plan("g3_full_nv101_odd")
+    rng = np.random.default_rng(11)
+    Y = rng.standard_normal((3, plan.nfo)) + 1j * rng.standard_normal((3, plan.nfo))
+    ref = np.fft.irfft(Y, plan.n_fft, axis=1)
+    fast = plan.irfft(Y)
+    monkeypatch.setenv("PKM_IRFFT_HALVES", "0")
+    slow = plan.irfft(Y)
+    assert rel_err(fast, ref) < 1e-13 and rel_err(slow, ref) < 1e-13
+
+
 def test_row_ranges_and_pixel_major_layout(gpu_ok):
     from popkinmocks_b200 import _lib
     g = load_golden("g2_rebin_nv21_prime")
