@@ -360,6 +360,11 @@ __device__ __forceinline__ double2 w16_mulc(double2 x, int k) {  // x * exp(+2 p
   }
 }
 
+// index padding of the halves kernels: one empty slot after every 16 elements - conflict-free for
+// all their access patterns (contiguous runs of >= 8 elements, or one 16-element block per lane)
+__device__ __forceinline__ int sq(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr size_t sq_elems(size_t n) { return n + (n >> 4); }
+
 // one forward radix-16 item with block twiddle u (level 1: u^m W16^(m b), level 2: (u^4)^n)
 __device__ __forceinline__ void r16_fwd(double2 (&x)[4][4], double2 u) {
   Tw16 tw;
@@ -408,17 +413,6 @@ __device__ __forceinline__ void r16_fwd_unit(double2 (&x)[4][4]) {
 #pragma unroll
   for (int a = 0; a < 4; ++a) bfly4_fwd(x[a][0], x[a][1], x[a][2], x[a][3]);
 }
-__device__ __forceinline__ void r16_inv_unit(double2 (&x)[4][4]) {
-#pragma unroll
-  for (int a = 0; a < 4; ++a) bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-#pragma unroll
-    for (int m = 1; m < 4; ++m) x[m][b] = w16_mulc(x[m][b], m * b);
-    bfly4_inv(x[0][b], x[1][b], x[2][b], x[3][b]);
-  }
-}
-
 // shared-memory twiddles of the halves transforms: htw = for Nb = H, H/16, ..., 256 the Nb/16 values
 // exp(-2 pi i j / Nb) (the u of a radix-16 pass with block Nb), concatenated (CztTables::htw)
 __device__ __forceinline__ void halves_stage_twiddles(double2* stw, const double2* __restrict__ htw, int M) {
@@ -432,10 +426,16 @@ __host__ __device__ constexpr size_t halves_twiddle_elems(size_t M) { return M /
 // returns the twiddle offset after the last pass.  The Nb = 16 pass is left to the caller.
 template <class In>
 __device__ __forceinline__ int halves_forward(double2* s, const double2* stw, int M, int logH, In in,
-                                              bool& first) {
+                                              bool& first, bool skip_first_pass = false) {
   const int H = M >> 1;
   int toff = 0;
-  for (int Nb = H; Nb > 16; Nb >>= 4) {
+  int Nb = H;
+  if (skip_first_pass && H > 16) {     // the caller has done the Nb = H pass itself
+    toff = H >> 4;
+    Nb = H >> 4;
+    first = false;
+  }
+  for (; Nb > 16; Nb >>= 4) {
     const int q = Nb >> 2, qq = Nb >> 4;
     for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
       const int h = i >> (logH - 4), li = i & ((H >> 4) - 1);
@@ -447,13 +447,13 @@ __device__ __forceinline__ int halves_forward(double2* s, const double2* stw, in
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int k = lbase + a * q + b * qq;
-          x[a][b] = first ? in(h, k) : s[sp(h * H + k)];
+          x[a][b] = first ? in(h, k) : s[sq(h * H + k)];
         }
       r16_fwd(x, stw[toff + j]);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s[sp(h * H + lbase + a * q + b * qq)] = x[a][b];
+        for (int b = 0; b < 4; ++b) s[sq(h * H + lbase + a * q + b * qq)] = x[a][b];
     }
     __syncthreads();
     toff += qq;
@@ -481,6 +481,18 @@ struct CztHalvesInput {        // pre[h][k] = alpha_k chi_k (W_M^k)^h; DC / Nyqu
     if (k == 0 || k == nyq) a.y = 0.0;
     return cmul(a, __ldg(pre + (size_t)h * nfo + k));
   }
+  // the same without control flow (clamped index, select), so that the loads of a whole item can
+  // be in flight together: the pass was bound by one L2 round trip per element
+  __device__ __forceinline__ void fetch(int h, int k, double2& a, double2& w) const {
+    const int kk = min(k, nfo - 1);
+    a = __ldg(yin + kk);
+    w = __ldg(pre + (size_t)h * nfo + kk);
+  }
+  __device__ __forceinline__ double2 finish(int k, double2 a, double2 w) const {
+    a.y = (k == 0 || k == nyq) ? 0.0 : a.y;
+    const double2 v = cmul(a, w);
+    return k < nfo ? v : make_double2(0.0, 0.0);
+  }
 };
 
 __global__ void __launch_bounds__(512)
@@ -488,7 +500,7 @@ k_filter_spectrum_h(const double2* __restrict__ bfilt, double2* __restrict__ Bha
                     const double2* __restrict__ tw, const double2* __restrict__ htw) {
   extern __shared__ double2 sbuf[];
   double2* s = sbuf;
-  double2* stw = sbuf + sp_elems(M);
+  double2* stw = sbuf + sq_elems(M);
   const int H = M >> 1, logH = logM - 1;
   halves_stage_twiddles(stw, htw, M);
   __syncthreads();
@@ -503,7 +515,7 @@ k_filter_spectrum_h(const double2* __restrict__ bfilt, double2* __restrict__ Bha
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int idx = base + a * 4 + b;
-        x[a][b] = first ? in(idx >= H, idx & (H - 1)) : s[sp(idx)];
+        x[a][b] = first ? in(idx >= H, idx & (H - 1)) : s[sq(idx)];
       }
     r16_fwd_unit(x);
 #pragma unroll
@@ -513,14 +525,15 @@ k_filter_spectrum_h(const double2* __restrict__ bfilt, double2* __restrict__ Bha
   }
 }
 
-__global__ void __launch_bounds__(512)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, int M, int logM,
               double scale, const double2* __restrict__ pre, const double2* __restrict__ post,
               const double2* __restrict__ htw, const double2* __restrict__ Bhat,
               double* __restrict__ out) {
   extern __shared__ double2 sbuf[];
   double2* s = sbuf;
-  double2* stw = sbuf + sp_elems(M);
+  double2* stw = sbuf + sq_elems(M);
   const int H = M >> 1, logH = logM - 1;
   halves_stage_twiddles(stw, htw, M);
   __syncthreads();
@@ -528,28 +541,81 @@ k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, 
   for (long long px = blockIdx.x; px < npix; px += gridDim.x) {
     CztHalvesInput in{yhat + (size_t)px * nfo, pre, nfo, nyq};
     bool first = true;
-    int toff = halves_forward(s, stw, M, logH, in, first);
-    // last forward pass (blocks of 16), filter, first inverse pass: all on the same 16 elements
+    if (H > 16) {
+      // first forward pass (Nb = H) straight from global memory: rows of the item that lie
+      // entirely above nfo are zero (a CTA-uniform test), the others are fetched as one batch
+      const int q = H >> 2, qq = H >> 4;
+      for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
+        const int h = i >> (logH - 4), j = i & (qq - 1);
+        double2 x[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (a * q < nfo) {
+            double2 raw[4], w[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) in.fetch(h, j + a * q + b * qq, raw[b], w[b]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[a][b] = in.finish(j + a * q + b * qq, raw[b], w[b]);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[a][b] = make_double2(0.0, 0.0);
+          }
+        }
+        r16_fwd(x, stw[j]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) s[sq(h * H + j + a * q + b * qq)] = x[a][b];
+      }
+      __syncthreads();
+    }
+    int toff = halves_forward(s, stw, M, logH, in, first, true);
+    // last forward pass (blocks of 16), filter, first inverse pass: all on the same 16 elements.
+    // The filter values of rows 0, 1 are requested before the shared-memory loads, those of rows
+    // 2, 3 once the first level of butterflies has freed registers.
     for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
       const int base = i * 16;
-      double2 x[4][4];
+      const double2* fp = Bhat + base;
+      double2 x[4][4], f[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) f[a][b] = __ldg(fp + a * 4 + b);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int idx = base + a * 4 + b;
-          x[a][b] = first ? in(idx >= H, idx & (H - 1)) : s[sp(idx)];
+          x[a][b] = first ? in(idx >= H, idx & (H - 1)) : s[sq(idx)];
         }
-      r16_fwd_unit(x);
+      // forward level 1 (over a), then per row: forward level 2, filter, inverse level 1
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        bfly4_fwd(x[0][b], x[1][b], x[2][b], x[3][b]);
+#pragma unroll
+        for (int m = 1; m < 4; ++m) x[m][b] = w16_mul(x[m][b], m * b);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        bfly4_fwd(x[a][0], x[a][1], x[a][2], x[a][3]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[a][b] = cmul(x[a][b], f[a & 1][b]);
+        if (a < 2) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) f[a][b] = __ldg(fp + (a + 2) * 4 + b);
+        }
+        bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int m = 1; m < 4; ++m) x[m][b] = w16_mulc(x[m][b], m * b);
+        bfly4_inv(x[0][b], x[1][b], x[2][b], x[3][b]);
+      }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) x[a][b] = cmul(x[a][b], __ldg(Bhat + base + a * 4 + b));
-      r16_inv_unit(x);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) s[sp(base + a * 4 + b)] = x[a][b];
+        for (int b = 0; b < 4; ++b) s[sq(base + a * 4 + b)] = x[a][b];
     }
     __syncthreads();
     // inverse passes: blocks of D -> 16 D, D = 16 ... H/16
@@ -564,23 +630,36 @@ k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, 
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) x[a][b] = s[sp(base + a * q + b * qq)];
+          for (int b = 0; b < 4; ++b) x[a][b] = s[sq(base + a * q + b * qq)];
         r16_inv(x, stw[toff + j]);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) s[sp(base + a * q + b * qq)] = x[a][b];
+          for (int b = 0; b < 4; ++b) s[sq(base + a * q + b * qq)] = x[a][b];
       }
       __syncthreads();
     }
     // output sweep: z[m] = z0[i] +- conj(W_M^i) z1[i] (i = m mod H), y[m] = Re(chi[m] z[m]) * scale
-    //             = Re(post0[m] z0[i] + post1[m] z1[i]) * scale
+    //             = Re(post0[m] z0[i] + post1[m] z1[i]) * scale;  the weights of OB outputs are
+    // requested together
     double* yo = out + (size_t)px * n;
-    for (int m = threadIdx.x; m < n; m += blockDim.x) {
-      const int i = m & (H - 1);
-      const double2 z0 = s[sp(i)], z1 = s[sp(H + i)];
-      const double2 p0 = __ldg(post + m), p1 = __ldg(post + n + m);
-      yo[m] = (fma(p0.x, z0.x, -p0.y * z0.y) + fma(p1.x, z1.x, -p1.y * z1.y)) * scale;
+    constexpr int OB = 5;
+    for (int m0 = threadIdx.x; m0 < n; m0 += OB * blockDim.x) {
+      double2 p0[OB], p1[OB];
+#pragma unroll
+      for (int r = 0; r < OB; ++r) {
+        const int m = min(m0 + r * (int)blockDim.x, n - 1);
+        p0[r] = __ldg(post + m);
+        p1[r] = __ldg(post + n + m);
+      }
+#pragma unroll
+      for (int r = 0; r < OB; ++r) {
+        const int m = m0 + r * (int)blockDim.x;
+        const int i = min(m, n - 1) & (H - 1);
+        const double2 z0 = s[sq(i)], z1 = s[sq(H + i)];
+        const double y = (fma(p0[r].x, z0.x, -p0[r].y * z0.y) + fma(p1[r].x, z1.x, -p1[r].y * z1.y)) * scale;
+        if (m < n) yo[m] = y;
+      }
     }
     __syncthreads();   // the next pixel's first pass overwrites s
   }
@@ -788,7 +867,7 @@ void czt_prepare_filter(pkm_plan* pl) {
   }
   PKM_CUDA(cudaGetLastError());
   if (pl->d_Bhat_h) {
-    const size_t smem = sizeof(double2) * (sp_elems(c.M) + halves_twiddle_elems(c.M));
+    const size_t smem = sizeof(double2) * (sq_elems(c.M) + halves_twiddle_elems(c.M));
     PKM_CUDA(cudaFuncSetAttribute(k_filter_spectrum_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_filter_spectrum_h<<<1, std::max(32, std::min(512, c.M / 16)), smem>>>(d_b, pl->d_Bhat_h, c.M, c.logM, pl->d_twiddle, pl->d_htw);
     PKM_CUDA(cudaGetLastError());
@@ -822,12 +901,16 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
   const double s = scale / ((double)c.M * (double)c.n);
   KernelTimer tm(pl, PKM_K_IRFFT, st);
   if (pl->d_Bhat_h && czt_halves_ok(c)) {
-    const size_t smem = sizeof(double2) * (sp_elems(c.M) + halves_twiddle_elems(c.M));
-    PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(double2) * (sq_elems(c.M) + halves_twiddle_elems(c.M));
+    const char* e = getenv("PKM_IRFFT_THREADS");            // 256 = two items per thread and pass
+    const int want = e ? atoi(e) : 512;
+    const int nthr = std::max(32, std::min(want == 256 ? 256 : 512, c.M / 16));
+    auto kern = want == 256 ? k_irfft_czt_h<256> : k_irfft_czt_h<512>;
+    PKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
     const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
-    k_irfft_czt_h<<<grid, std::max(32, std::min(512, c.M / 16)), smem, st>>>(
-        yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_pre, pl->d_post, pl->d_htw, pl->d_Bhat_h, out);
+    kern<<<grid, nthr, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_pre, pl->d_post, pl->d_htw,
+                                   pl->d_Bhat_h, out);
   } else if (c.R == 1) {
     const size_t smem = sizeof(double2) * sp_elems(c.M);
     PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
