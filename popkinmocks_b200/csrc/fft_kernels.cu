@@ -481,18 +481,6 @@ struct CztHalvesInput {        // pre[h][k] = alpha_k chi_k (W_M^k)^h; DC / Nyqu
     if (k == 0 || k == nyq) a.y = 0.0;
     return cmul(a, __ldg(pre + (size_t)h * nfo + k));
   }
-  // the same without control flow (clamped index, select), so that the loads of a whole item can
-  // be in flight together: the pass was bound by one L2 round trip per element
-  __device__ __forceinline__ void fetch(int h, int k, double2& a, double2& w) const {
-    const int kk = min(k, nfo - 1);
-    a = __ldg(yin + kk);
-    w = __ldg(pre + (size_t)h * nfo + kk);
-  }
-  __device__ __forceinline__ double2 finish(int k, double2 a, double2 w) const {
-    a.y = (k == 0 || k == nyq) ? 0.0 : a.y;
-    const double2 v = cmul(a, w);
-    return k < nfo ? v : make_double2(0.0, 0.0);
-  }
 };
 
 __global__ void __launch_bounds__(512)
@@ -525,62 +513,112 @@ k_filter_spectrum_h(const double2* __restrict__ bfilt, double2* __restrict__ Bha
   }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT)
-k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, int M, int logM,
+// a load the compiler may not sink past a barrier (operands requested ahead of their use)
+__device__ __forceinline__ double2 ldg_pinned(const double2* p) {
+#ifdef PKM_HOST_EMULATION            // tests/host_emulation compiles this file's device code for the CPU
+  return *p;
+#endif
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");  // not .nc: ptxas moves non-coherent loads across BAR.SYNC
+  return v;
+}
+
+// One thread owns one radix-16 item per pass (blockDim = M/16 <= 512).  Global operands never
+// stall a pass (the kernel was bound by L2 round trips, ncu long-scoreboard): the NEXT pixel's
+// spectrum is fetched into registers under the output sweep, the filter rows 0-1 and the first
+// output weights are requested before the barrier that precedes their use.  (Staging the input
+// weights `pre` in shared memory as well measured slower, 1.74 vs 1.67 ms on 14k pixels: the 78 KB
+// come out of the L1 that serves the filter and the output weights.)
+template <int LOGH>
+__global__ void __launch_bounds__(512)
+k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, int /*M*/, int /*logM*/,
               double scale, const double2* __restrict__ pre, const double2* __restrict__ post,
               const double2* __restrict__ htw, const double2* __restrict__ Bhat,
               double* __restrict__ out) {
   extern __shared__ double2 sbuf[];
   double2* s = sbuf;
-  double2* stw = sbuf + sq_elems(M);
-  const int H = M >> 1, logH = logM - 1;
+  double2* stw = sbuf + sq_elems(2 << LOGH);
+  constexpr int logH = LOGH, H = 1 << LOGH, M = 2 * H;    // compile-time: M = 32, 512 or 8192
   halves_stage_twiddles(stw, htw, M);
   __syncthreads();
   const int nyq = (n & 1) ? -1 : nfo - 1;
+  constexpr int q = H >> 2, qq = H >> 4;                  // first pass (Nb = H)
+  const int item = threadIdx.x;                           // this thread's item in every pass
+  const bool has_item = item < (M >> 4);
+  const int h0 = item >> (logH - 4), j0 = item & (qq - 1);
+  // raw spectrum values of the first pass: rows 0..2 (row 3 starts at 3H/4 >= nfo: always zero)
+  double2 raw[3][4];
+  auto fetch_raw = [&](long long px) {
+    const double2* yin = yhat + (size_t)px * nfo;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) raw[a][b] = ldg_pinned(yin + min(j0 + a * q + b * qq, nfo - 1));
+  };
+  fetch_raw(min((long long)blockIdx.x, npix - 1));
   for (long long px = blockIdx.x; px < npix; px += gridDim.x) {
     CztHalvesInput in{yhat + (size_t)px * nfo, pre, nfo, nyq};
     bool first = true;
-    if (H > 16) {
-      // first forward pass (Nb = H) straight from global memory: rows of the item that lie
-      // entirely above nfo are zero (a CTA-uniform test), the others are fetched as one batch
-      const int q = H >> 2, qq = H >> 4;
-      for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
-        const int h = i >> (logH - 4), j = i & (qq - 1);
-        double2 x[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          if (a * q < nfo) {
-            double2 raw[4], w[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) in.fetch(h, j + a * q + b * qq, raw[b], w[b]);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) x[a][b] = in.finish(j + a * q + b * qq, raw[b], w[b]);
-          } else {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) x[a][b] = make_double2(0.0, 0.0);
-          }
-        }
-        r16_fwd(x, stw[j]);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) s[sq(h * H + j + a * q + b * qq)] = x[a][b];
-      }
-      __syncthreads();
-    }
-    int toff = halves_forward(s, stw, M, logH, in, first, true);
-    // last forward pass (blocks of 16), filter, first inverse pass: all on the same 16 elements.
-    // The filter values of rows 0, 1 are requested before the shared-memory loads, those of rows
-    // 2, 3 once the first level of butterflies has freed registers.
-    for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
-      const int base = i * 16;
-      const double2* fp = Bhat + base;
-      double2 x[4][4], f[2][4];
+    double2 f[2][4];                                       // filter rows, two at a time
+    auto request_filter = [&](int r0) {                    // rows r0, r0 + 1 of this thread's block
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) f[a][b] = __ldg(fp + a * 4 + b);
+        for (int b = 0; b < 4; ++b) f[a][b] = ldg_pinned(Bhat + item * 16 + (r0 + a) * 4 + b);
+    };
+    if (H > 16) {
+      if (has_item) {
+        double2 x[4][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int k = j0 + a * q + b * qq, kk = min(k, nfo - 1);
+            double2 v = raw[a][b];
+            v.y = (k == 0 || k == nyq) ? 0.0 : v.y;
+            v = cmul(v, __ldg(pre + (size_t)h0 * nfo + kk));
+            x[a][b] = k < nfo ? v : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[3][b] = make_double2(0.0, 0.0);
+        r16_fwd(x, stw[j0]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) s[sq(h0 * H + j0 + a * q + b * qq)] = x[a][b];
+        if (H == 256) request_filter(0);                   // the next pass is the fused middle pass
+      }
+      __syncthreads();
+      first = false;
+    }
+    // remaining forward passes Nb = H/16 ... 256
+    int toff = H > 16 ? qq : 0;
+#pragma unroll
+    for (int Nb = H >> 4; Nb > 16; Nb >>= 4) {
+      const int q2 = Nb >> 2, qq2 = Nb >> 4;
+      if (has_item) {
+        const int li = item & ((H >> 4) - 1), j = li & (qq2 - 1);
+        const int base = h0 * H + (li - j) * 16 + j;
+        double2 x[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) x[a][b] = s[sq(base + a * q2 + b * qq2)];
+        r16_fwd(x, stw[toff + j]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) s[sq(base + a * q2 + b * qq2)] = x[a][b];
+        if (Nb == 256) request_filter(0);
+      }
+      __syncthreads();
+      toff += qq2;
+    }
+    // last forward pass (blocks of 16), filter, first inverse pass: all on the same 16 elements.
+    if (has_item) {
+      const int base = item * 16;
+      double2 x[4][4];
+      if (first) request_filter(0);                        // M = 32: nothing precedes this pass
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -602,7 +640,7 @@ k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, 
         for (int b = 0; b < 4; ++b) x[a][b] = cmul(x[a][b], f[a & 1][b]);
         if (a < 2) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) f[a][b] = __ldg(fp + (a + 2) * 4 + b);
+          for (int b = 0; b < 4; ++b) f[a][b] = __ldg(Bhat + base + (a + 2) * 4 + b);
         }
         bfly4_inv(x[a][0], x[a][1], x[a][2], x[a][3]);
       }
@@ -617,41 +655,48 @@ k_irfft_czt_h(const double2* __restrict__ yhat, long long npix, int n, int nfo, 
 #pragma unroll
         for (int b = 0; b < 4; ++b) s[sq(base + a * 4 + b)] = x[a][b];
     }
+    // output weights of the first batch: requested before the barrier(s) that precede the sweep
+    constexpr int OB = 5;
+    double2 p0[OB], p1[OB];
+    auto request_weights = [&](int m0) {
+#pragma unroll
+      for (int r = 0; r < OB; ++r) {
+        const int m = min(m0 + r * (int)blockDim.x, n - 1);
+        p0[r] = ldg_pinned(post + m);
+        p1[r] = ldg_pinned(post + n + m);
+      }
+    };
+    if (H == 16) request_weights(threadIdx.x);
     __syncthreads();
     // inverse passes: blocks of D -> 16 D, D = 16 ... H/16
+#pragma unroll
     for (int D = 16; 16 * D <= H; D <<= 4) {
-      const int qq = D, q = 4 * D;
-      toff -= qq;
-      for (int i = threadIdx.x; i < (M >> 4); i += blockDim.x) {
-        const int h = i >> (logH - 4), li = i & ((H >> 4) - 1);
-        const int j = li & (qq - 1);
-        const int base = h * H + (li - j) * 16 + j;
+      const int qq2 = D, q2 = 4 * D;
+      toff -= qq2;
+      if (has_item) {
+        const int li = item & ((H >> 4) - 1), j = li & (qq2 - 1);
+        const int base = h0 * H + (li - j) * 16 + j;
         double2 x[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) x[a][b] = s[sq(base + a * q + b * qq)];
+          for (int b = 0; b < 4; ++b) x[a][b] = s[sq(base + a * q2 + b * qq2)];
         r16_inv(x, stw[toff + j]);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) s[sq(base + a * q + b * qq)] = x[a][b];
+          for (int b = 0; b < 4; ++b) s[sq(base + a * q2 + b * qq2)] = x[a][b];
       }
+      if (16 * D == H) request_weights(threadIdx.x);
       __syncthreads();
     }
+    // the next pixel's spectrum travels under the output sweep
+    fetch_raw(min(px + (long long)gridDim.x, npix - 1));   // unconditional: `raw` is dead between its use and here
     // output sweep: z[m] = z0[i] +- conj(W_M^i) z1[i] (i = m mod H), y[m] = Re(chi[m] z[m]) * scale
-    //             = Re(post0[m] z0[i] + post1[m] z1[i]) * scale;  the weights of OB outputs are
-    // requested together
+    //             = Re(post0[m] z0[i] + post1[m] z1[i]) * scale
     double* yo = out + (size_t)px * n;
-    constexpr int OB = 5;
     for (int m0 = threadIdx.x; m0 < n; m0 += OB * blockDim.x) {
-      double2 p0[OB], p1[OB];
-#pragma unroll
-      for (int r = 0; r < OB; ++r) {
-        const int m = min(m0 + r * (int)blockDim.x, n - 1);
-        p0[r] = __ldg(post + m);
-        p1[r] = __ldg(post + n + m);
-      }
+      if (m0 != (int)threadIdx.x) request_weights(m0);
 #pragma unroll
       for (int r = 0; r < OB; ++r) {
         const int m = m0 + r * (int)blockDim.x;
@@ -878,7 +923,7 @@ void czt_prepare_filter(pkm_plan* pl) {
 
 // M = 2 * 16^p, one-piece transform: the halves kernel applies (PKM_IRFFT_HALVES=0 turns it off)
 bool czt_halves_ok(const CztTables& c) {
-  if (c.R != 1 || c.M < 32 || (c.logM - 1) % 4 != 0) return false;
+  if (c.R != 1 || c.M < 32 || c.M > 8192 || (c.logM - 1) % 4 != 0) return false;
   const char* e = getenv("PKM_IRFFT_HALVES");
   return !(e && atoi(e) == 0);
 }
@@ -902,15 +947,14 @@ void launch_irfft_czt(pkm_plan* pl, const double2* yhat, int64_t npix, double sc
   KernelTimer tm(pl, PKM_K_IRFFT, st);
   if (pl->d_Bhat_h && czt_halves_ok(c)) {
     const size_t smem = sizeof(double2) * (sq_elems(c.M) + halves_twiddle_elems(c.M));
-    const char* e = getenv("PKM_IRFFT_THREADS");            // 256 = two items per thread and pass
-    const int want = e ? atoi(e) : 512;
-    const int nthr = std::max(32, std::min(want == 256 ? 256 : 512, c.M / 16));
-    auto kern = want == 256 ? k_irfft_czt_h<256> : k_irfft_czt_h<512>;
+    auto kern = k_irfft_czt_h<12>;
+    if (c.logM - 1 == 4) kern = k_irfft_czt_h<4>;
+    if (c.logM - 1 == 8) kern = k_irfft_czt_h<8>;
     PKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
     const int grid = (int)std::min<int64_t>(npix, (int64_t)pl->num_sms * per_sm);
-    kern<<<grid, nthr, smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_pre, pl->d_post, pl->d_htw,
-                                   pl->d_Bhat_h, out);
+    kern<<<grid, std::max(32, std::min(512, c.M / 16)), smem, st>>>(yhat, npix, c.n, c.nfo, c.M, c.logM, s, pl->d_pre,
+                                                                   pl->d_post, pl->d_htw, pl->d_Bhat_h, out);
   } else if (c.R == 1) {
     const size_t smem = sizeof(double2) * sp_elems(c.M);
     PKM_CUDA(cudaFuncSetAttribute(k_irfft_czt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -61,6 +61,7 @@ def test_density_path_matches_reference(gpu_ok, name, tags):
     {"PKM_COEFF_TMA_MODE": "1"},                                # staged kernel, 1-D bulk copies
     {"PKM_COEFF_TMA_MODE": "0"},                                # staged kernel, plain loads
     {"PKM_COEFF_KERNEL": "0", "PKM_COEFF_GROUPS": "1"},         # staged kernel, one warp group
+    {"PKM_COEFF_FLOW": "0"},                                    # octet kernel with CTA barriers + TMA tensor store
 ])
 def test_coefficient_kernel_fallbacks_match_reference(gpu_ok, monkeypatch, env):
     """The default path uses the octet coefficient kernel; the staged kernel and its load modes
@@ -72,6 +73,33 @@ def test_coefficient_kernel_fallbacks_match_reference(gpu_ok, monkeypatch, env):
         g = load_golden(name)
         y = _plan(name).ybar_density(g[tag + "log_p_tvxz"], is_log=True)
         assert rel_err(y, g[tag + "ybar"]) < TOL, (env, name, rel_err(y, g[tag + "ybar"]))
+
+
+@pytest.mark.parametrize("env", [{}, {"PKM_COEFF_FLOW": "0"}, {"PKM_COEFF_KERNEL": "0"}, {"PKM_COEFF_GENERIC": "1"}])
+def test_density_special_values(gpu_ok, monkeypatch, env):
+    """log p = -inf and log p < -708 are exact zeros of the density, NaN poisons its own pixel only
+    (np.exp semantics, base.py:841): the rare-value branch of the fused table exponential, through
+    every coefficient kernel."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = load_golden("g3_full_nv101_odd")
+    plan = _plan("g3_full_nv101_odd")
+    logp = np.array(g["wn_log_p_tvxz"], copy=True)
+    rng = np.random.default_rng(3)
+    logp[rng.random(logp.shape) < 0.05] = -np.inf
+    logp[rng.random(logp.shape) < 0.05] = -800.0
+    logp[0, 3] = -np.inf                                    # a whole velocity plane of one age
+    ref = plan.ybar_density(np.exp(logp), is_log=False)
+    y = plan.ybar_density(logp, is_log=True)
+    assert np.isfinite(y).all() and rel_err(y, ref) < TOL
+    nx1, nx2 = y.shape[1:]
+    bad = logp.copy()
+    bad[5, 7, nx1 - 1, nx2 - 1, 2] = np.nan
+    yb = plan.ybar_density(bad, is_log=True)
+    assert np.isnan(yb[:, nx1 - 1, nx2 - 1]).all()
+    keep = np.ones((nx1, nx2), bool)
+    keep[nx1 - 1, nx2 - 1] = False
+    assert np.array_equal(yb[:, keep], y[:, keep])
 
 
 def test_density_even_nv_raises_index_error(gpu_ok):
