@@ -1,20 +1,25 @@
 """Stall breakdown of one kernel of an .ncu-rep: per-reason warp-stall ratios from the raw page and the
 hottest instructions of the source page (ncu --set full --import-source on).
-usage: python tools/ncu_stalls.py <report.ncu-rep> [top_n]"""
+usage: python tools/ncu_stalls.py <report.ncu-rep> [top_n [kernel_regex]]   (first matching launch)"""
 import csv
 import io
 import subprocess
 import sys
 
 
+KERNEL = []
+
+
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"] + KERNEL, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
     rep = sys.argv[1]
     top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    if len(sys.argv) > 3:
+        KERNEL.extend(["-k", "regex:" + sys.argv[3], "-c", "1"])
     rows = page(rep, "raw")
     hdr, r = rows[0], rows[2]
     for h, v in zip(hdr, r):
