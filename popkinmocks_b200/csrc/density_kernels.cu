@@ -601,8 +601,8 @@ struct ExpPair {
 };
 
 constexpr int K1F_THREADS = K1_THREADS + 32;   // 12 consumer warps + the producer warp
-template <int TM, bool IS_LOG>
-__global__ void __launch_bounds__(K1F_THREADS, 1)
+template <int TM, bool IS_LOG, bool APF>
+__global__ void __launch_bounds__(APF ? K1_THREADS : K1F_THREADS, 1)
 k_coeff_flow(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* __restrict__ CRt,
              const double* __restrict__ CIt, const double* __restrict__ exp2_tab,
              double2* __restrict__ cT) {
@@ -621,17 +621,21 @@ k_coeff_flow(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* _
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(etab + PKM_EXP_TAB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nitem = nz * (pxb >> 3);
-  for (int i = tid; i < frag_elems; i += K1F_THREADS) {
+  constexpr int NTHR = APF ? K1_THREADS : K1F_THREADS;
+  for (int i = tid; i < frag_elems; i += NTHR) {
     As_r[i] = CRt[i];
     As_i[i] = CIt[i];
   }
-  for (int i = tid; i < PKM_EXP_TAB; i += K1F_THREADS) etab[i] = exp2_tab[i];
+  for (int i = tid; i < PKM_EXP_TAB; i += NTHR) etab[i] = exp2_tab[i];
   const unsigned full0 = smem_u32(bars), empty0 = full0 + 16u;
+  const unsigned cnt0 = full0 + 32u;             // APF: arrival counters (the last arriver refills)
   if (tid == 0) {
     mbar_init(full0, 1);
     mbar_init(full0 + 8, 1);
     mbar_init(empty0, (unsigned)nitem);
     mbar_init(empty0 + 8, (unsigned)nitem);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0), "r"(0u) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u), "r"(0u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -640,7 +644,22 @@ k_coeff_flow(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* _
   const long long ntile = (long long)nxb * g.nt;
   const long long tstep = gridDim.x;
 
-  if (warp == K1_WARPS) {                        // ---- producer ----
+  auto issue_tile = [&](long long tile, int b) {  // one thread
+    const int t = (int)(tile / nxb);
+    const int xb = (int)(tile - (long long)t * nxb);
+    mbar_expect_tx(full0 + 8u * b, (unsigned)slab_elems * 8u);
+    tensor2d_g2s(smem_u32(Bbuf + (size_t)b * buf_elems), &tmap,
+                 (int)((g.pix0 + (long long)xb * pxb) * nz), t * nv, full0 + 8u * b);
+  };
+  if (APF) {
+    // no producer warp (12 warps = 3 per scheduler leave 168 registers per thread for the second
+    // A-fragment set): thread 0 issues the first two slabs, later the LAST consumer warp to
+    // release a slab refills it
+    if (tid == 0) {
+      if ((long long)blockIdx.x < ntile) issue_tile(blockIdx.x, 0);
+      if ((long long)blockIdx.x + tstep < ntile) issue_tile(blockIdx.x + tstep, 1);
+    }
+  } else if (warp == K1_WARPS) {                 // ---- producer ----
     if (lane == 0) {
       long long tile = blockIdx.x;
       for (int it = 0; tile < ntile; tile += tstep, ++it) {
@@ -692,15 +711,34 @@ k_coeff_flow(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* _
     bo = pa - pb;
     fetch(nks > 1 ? 1 : 0, pa, pb);
     constexpr bool is_log = IS_LOG;
-    for (int ks = 0; ks < nks; ++ks) {
+    // APF: the A fragments of k-step ks+1 are loaded into a second register set while the DMMAs
+    // of k-step ks issue (no load -> DMMA -> reload chain on the same registers); the k-loop is
+    // unrolled by two by hand so that both sets stay in registers
+    double f0r[MB], f0i[MB], f1r[MB], f1i[MB];
+    if (APF) {
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        f0r[mb] = Ar[mb * 32];
+        f0i[mb] = Ai[mb * 32];
+      }
+    }
+    auto kstep = [&](int ks, double (&cr)[MB], double (&ci)[MB], double (&nr)[MB], double (&ni)[MB]) {
       ExpPair ep;
       ep.xa = pa;
       ep.xb = pb;
       double nbe = 0.0, nbo = 0.0;
+      const int kn = min(ks + 1, nks - 1);
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        dmma_m8n8k4(accr[mb][0], accr[mb][1], Ar[(ks * MB + mb) * 32], be);
-        dmma_m8n8k4(acci[mb][0], acci[mb][1], Ai[(ks * MB + mb) * 32], bo);
+        if (APF) {
+          dmma_m8n8k4(accr[mb][0], accr[mb][1], cr[mb], be);
+          dmma_m8n8k4(acci[mb][0], acci[mb][1], ci[mb], bo);
+          nr[mb] = Ar[(kn * MB + mb) * 32];
+          ni[mb] = Ai[(kn * MB + mb) * 32];
+        } else {
+          dmma_m8n8k4(accr[mb][0], accr[mb][1], Ar[(ks * MB + mb) * 32], be);
+          dmma_m8n8k4(acci[mb][0], acci[mb][1], Ai[(ks * MB + mb) * 32], bo);
+        }
         // stages [mb * 7 / MB, (mb + 1) * 7 / MB) of the next step's B fragment
 #pragma unroll
         for (int st = (mb * 7) / MB; st < ((mb + 1) * 7) / MB; ++st) {
@@ -715,10 +753,31 @@ k_coeff_flow(const __grid_constant__ CUtensorMap tmap, K1Geom g, const double* _
       }
       be = nbe;
       bo = nbo;
+    };
+    if (APF) {
+      int ks = 0;
+      for (; ks + 1 < nks; ks += 2) {
+        kstep(ks, f0r, f0i, f1r, f1i);
+        kstep(ks + 1, f1r, f1i, f0r, f0i);
+      }
+      if (ks < nks) kstep(ks, f0r, f0i, f1r, f1i);
+    } else {
+      for (int ks = 0; ks < nks; ++ks) kstep(ks, f0r, f0i, f1r, f1i);
     }
     // the slab is consumed: one arrival per warp lets the producer refill it
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");
+    if (APF) {
+      if (lane == 0) {
+        unsigned old;
+        asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt0 + 4u * b) : "memory");
+        if (old == (unsigned)nitem - 1u) {
+          asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * b), "r"(0u) : "memory");
+          if (tile + 2 * tstep < ntile) issue_tile(tile + 2 * tstep, b);
+        }
+      }
+    } else if (lane == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * b) : "memory");
+    }
     const int xg0 = xb * pxb + oct * 8;
     const size_t base = (((size_t)(xg0 >> 5) * ntz + (size_t)t * nz + iz) * nfi) * 32 + (xg0 & 31) + 2 * fk;
 #pragma unroll
@@ -886,7 +945,7 @@ static size_t coeff_oct_smem(const pkm_plan* pl, int NC) {
 
 static size_t coeff_flow_smem(const pkm_plan* pl, int NC) {
   const size_t buf_elems = ((size_t)pl->d.nv * (NC + PKM_K1_PITCH_PAD) + 15) & ~size_t(15);
-  return ((size_t)2 * pl->nfiP + 2 * buf_elems + PKM_EXP_TAB) * sizeof(double) + 32;
+  return ((size_t)2 * pl->nfiP + 2 * buf_elems + PKM_EXP_TAB) * sizeof(double) + 48;
 }
 
 // 4-D view of the coefficient array cT[x/32][t*nz+z][m][x%32] (complex) in scalar elements:
@@ -956,9 +1015,12 @@ static bool launch_coeff_oct_t(pkm_plan* pl, const double* dens, int is_log, int
   const char* flow = getenv("PKM_COEFF_FLOW");          // "0" = the staged-store (TMA tensor store) form
   if (!flow || atoi(flow) != 0) {
     const size_t fsmem = coeff_flow_smem(pl, NC);
-    auto kern = is_log ? k_coeff_flow<TM, true> : k_coeff_flow<TM, false>;
+    const char* apf_env = getenv("PKM_COEFF_APF");      // "0" = producer-warp form without the second A-fragment set
+    const bool apf = !(apf_env && atoi(apf_env) == 0 && apf_env[0] != '\0');
+    auto kern = is_log ? (apf ? k_coeff_flow<TM, true, true> : k_coeff_flow<TM, true, false>)
+                       : (apf ? k_coeff_flow<TM, false, true> : k_coeff_flow<TM, false, false>);
     PKM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    kern<<<grid, K1F_THREADS, fsmem, st>>>(tmap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab, cT);
+    kern<<<grid, apf ? K1_THREADS : K1F_THREADS, fsmem, st>>>(tmap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab, cT);
   } else {
     k_coeff_oct<TM><<<grid, K1_THREADS, smem, st>>>(tmap, omap, g, pl->d_CRt, pl->d_CIt_oct, pl->d_exp_tab);
   }
