@@ -7,9 +7,10 @@
 // kernel 1 (coeff):    c = (A^{-1} D) p   - a small dense real->complex transform per
 //                      (t,x,z) column, done as an FP64 tensor-core (DMMA) GEMM on TMA-staged
 //                      density slabs, with the even/odd fold of the real DFT (halves the
-//                      flops) and exp(log p) fused into the fold.  Two variants: k_coeff_oct
-//                      (default: TMA tensor load AND store, warp = z x 8 pixels) and the
-//                      staged k_coeff (any shape / alignment).
+//                      flops) and exp(log p) fused into the fold.  Variants: k_coeff_flow
+//                      (default: warp = z x 8 pixels, no CTA barrier in the tile loop, stores
+//                      straight from the accumulators), k_coeff_oct (the same items with a TMA
+//                      tensor store per tile) and the staged k_coeff (any shape / alignment).
 // kernel 2 (contract): streams S' (TMA-staged, L2 resident) and the coefficient rows, evaluates
 //                      the 4-tap spline on the fly and accumulates over (t,z) in registers.
 // P-hat (25 MB per pixel in the reference, base.py:846-853) is never materialised.

@@ -10,7 +10,9 @@
 // a chirp-z transform: k m = (k^2 + m^2 - (m-k)^2)/2, i.e. a length nfo+n-1 linear convolution
 // with the chirp chi[j] = e^{i pi j^2/n}, done with power-of-two FFTs of size M >= nfo+n-1.
 // One CTA per pixel; the M-point transforms run in place in shared memory (M <= 8192) or in a
-// CTA-private, L2-resident global scratch (larger n).  Forward = decimation in frequency,
+// CTA-private, L2-resident global scratch (larger n).  M = 2 * 16^p (8192 for the headline
+// n_fft = 4907) takes the specialised "halves" kernel further down: two independent radix-16
+// half-transforms, middle passes fused in registers, global operands requested ahead of use.  Forward = decimation in frequency,
 // inverse = its exact stage-by-stage inverse, so no bit-reversal pass is needed: the filter
 // spectrum is prepared once with the same forward routine (same permuted order).
 // Chirp phases are reduced exactly (j^2 mod 2n in integers) on the host.
