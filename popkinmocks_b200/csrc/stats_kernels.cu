@@ -74,6 +74,52 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict
   return x < -708.0 ? 0.0 : exp_core_tab(x, tab);
 }
 
+// The two per-element tests of the streaming loop, written as PTX so that they stay what they are.
+// Left to the compiler, "does any element of the batch exceed the running maximum" became a
+// NaN-aware running maximum (DSETP.MAX + FSEL + SEL + LOP3 + four moves per element) and the
+// conditional add a DADD with two selects: 56 instructions per element, issue bound at half the
+// HBM rate (ncu, profiles/r2c_reduce_summary.md).
+__device__ __forceinline__ bool any_greater8(const double (&a)[8], double m) {   // NaN compares false
+  unsigned r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f64 p, %1, %9;\n\t"
+      "setp.gt.or.f64 p, %2, %9, p;\n\t"
+      "setp.gt.or.f64 p, %3, %9, p;\n\t"
+      "setp.gt.or.f64 p, %4, %9, p;\n\t"
+      "setp.gt.or.f64 p, %5, %9, p;\n\t"
+      "setp.gt.or.f64 p, %6, %9, p;\n\t"
+      "setp.gt.or.f64 p, %7, %9, p;\n\t"
+      "setp.gt.or.f64 p, %8, %9, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(m));
+  return r != 0;
+}
+__device__ __forceinline__ bool any_less8(const double (&a)[8], double lim) {    // NaN compares false
+  unsigned r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.lt.f64 p, %1, %9;\n\t"
+      "setp.lt.or.f64 p, %2, %9, p;\n\t"
+      "setp.lt.or.f64 p, %3, %9, p;\n\t"
+      "setp.lt.or.f64 p, %4, %9, p;\n\t"
+      "setp.lt.or.f64 p, %5, %9, p;\n\t"
+      "setp.lt.or.f64 p, %6, %9, p;\n\t"
+      "setp.lt.or.f64 p, %7, %9, p;\n\t"
+      "setp.lt.or.f64 p, %8, %9, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(lim));
+  return r != 0;
+}
+// s += y unless x < -708 (y underflows); a NaN x is unordered, passes the test and poisons the sum
+__device__ __forceinline__ void add_unless_underflow(double& s, double x, double y) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.geu.f64 p, %1, 0dC086200000000000;\n\t"
+      "@p add.f64 %0, %0, %2;\n\t}"
+      : "+d"(s)
+      : "d"(x), "d"(y));
+}
+
 // ONE streaming pass over the 5-D array ("online" log-sum-exp).
 // Thread = one (pixel-in-chunk, z) element of a chunk of PB whole pixels, contiguous in memory for
 // fixed (t, v).  CTA = (chunk or chunk group, kept t, block of VPC kept v's); for every kept v of
@@ -87,12 +133,13 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict
 // TWO batches of loads in flight.  The kernel was bound by instruction issue (65 instructions per
 // element, ncu profiles/r2_*): full batches take an unpredicated path with pointer increments,
 // equal velocity bins are folded into the per-(t,z) constant, the exponential has one range test.
-constexpr int RED_U = 8;
+constexpr int RED_U = 8;      // any_greater8() is written for this batch size
 constexpr int RED_VPC = 16;    // kept velocity bins per CTA
-#ifndef PKM_RED_MINB
-#define PKM_RED_MINB 4
-#endif
-__global__ void __launch_bounds__(256, PKM_RED_MINB)
+// MINB = resident CTAs per SM the register budget is set for: 4 (64 registers) is best when the
+// velocity axis is kept (batches along t: 7.7 vs 8.2 ms per pass of the 201x201 array), 3 (80) when
+// it is summed (batches along v: 5.2 vs 5.5 ms)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
                 const double* __restrict__ log_dv, const double* __restrict__ log_dz,
                 const double* __restrict__ log_lw, const double* __restrict__ exp2_tab,
@@ -139,9 +186,7 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
     // batch that raises M takes the slow path once (rescale the sum).  NaN compares false, passes
     // the underflow test and poisons the sum - scipy's logsumexp gives NaN as well.
     auto flush = [&acc](const double (&a)[RED_U], const double* tab) {
-      bool grow = false;
-#pragma unroll
-      for (int k = 0; k < RED_U; ++k) grow = grow || a[k] > acc.m;
+      const bool grow = any_greater8(a, acc.m);
       if (grow) {
         double bm = a[0];
 #pragma unroll
@@ -151,11 +196,17 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
       }
       if (acc.m > -INFINITY) {
         double sum = acc.s;
+        if (!any_less8(a, acc.m - 708.0)) {
+          // common case: no term underflows (none is -inf either), so every exponential is added
+          // unconditionally; NaN compares false, lands here and poisons the sum
 #pragma unroll
-        for (int k = 0; k < RED_U; ++k) {
-          const double x = a[k] - acc.m;
-          const double y = exp_core_tab(x, tab);
-          if (!(x < -708.0)) sum += y;
+          for (int k = 0; k < RED_U; ++k) sum += exp_core_tab(a[k] - acc.m, tab);
+        } else {
+#pragma unroll
+          for (int k = 0; k < RED_U; ++k) {
+            const double x = a[k] - acc.m;
+            add_unless_underflow(sum, x, exp_core_tab(x, tab));
+          }
         }
         acc.s = sum;
       } else {                      // nothing finite seen so far: -inf elements add nothing, NaN poisons
@@ -631,16 +682,18 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
   PKM_REQUIRE(smem <= 40 * 1024, "age/velocity/metallicity grid too large for the reduction kernel");
   if (g.kx) {
     dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
-    k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
-                                            pl->d_exp_tab, d_mx, d_sum, d_gmax, PB, nchunk, uniform_dv);
+    auto kern = g.kv ? k_reduce_online<4> : k_reduce_online<3>;
+    kern<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, pl->d_exp_tab, d_mx, d_sum,
+                                 d_gmax, PB, nchunk, uniform_dv);
     return 1;
   }
   const int G = reduce_groups(pl, g, nchunk);
   double* pm = d_part;
   double* ps = d_part + nout * G;
   dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
-  k_reduce_online<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw,
-                                          pl->d_exp_tab, pm, ps, d_gmax, PB, nchunk, uniform_dv);
+  auto kern = g.kv ? k_reduce_online<4> : k_reduce_online<3>;
+  kern<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, pl->d_exp_tab, pm, ps, d_gmax,
+                               PB, nchunk, uniform_dv);
   k_reduce_combine<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(pm, ps, nout, G, d_mx, d_sum);
   return 2;
 }
