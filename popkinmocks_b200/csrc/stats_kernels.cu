@@ -139,7 +139,7 @@ constexpr int RED_VPC = 16;    // kept velocity bins per CTA
 // MINB = resident CTAs per SM the register budget is set for: 4 (64 registers) is best when the
 // velocity axis is kept (batches along t: 7.7 vs 8.2 ms per pass of the 201x201 array), 3 (80) when
 // it is summed (batches along v: 5.2 vs 5.5 ms)
-template <int MINB>
+template <int MINB, bool CONTIG>
 __global__ void __launch_bounds__(256, MINB)
 k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __restrict__ log_dt,
                 const double* __restrict__ log_dv, const double* __restrict__ log_dz,
@@ -218,7 +218,7 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
       }
     };
     if (active) {
-      if (per_contig > 0 && (nV > 1 || nT > 1)) {
+      if (CONTIG && (nV > 1 || nT > 1)) {
         // x summed, many chunks per CTA: the CTA owns a CONTIGUOUS range of per_contig chunks and
         // the batches run along it, so that for every (t,v) row it streams one contiguous piece of
         // memory (8 chunks = 16 KB per batch) instead of 2 KB pieces megabytes apart (4.4 vs 5.0 ms
@@ -754,7 +754,7 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
   PKM_REQUIRE(smem <= 40 * 1024, "age/velocity/metallicity grid too large for the reduction kernel");
   if (g.kx) {
     dim3 grid((unsigned)nchunk, g.kt ? g.nt : 1, g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
-    auto kern = reduce_minb(g) == 4 ? k_reduce_online<4> : k_reduce_online<3>;
+    auto kern = reduce_minb(g) == 4 ? k_reduce_online<4, false> : k_reduce_online<3, false>;
     kern<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, pl->d_exp_tab, d_mx, d_sum,
                                  d_gmax, PB, nchunk, uniform_dv, 0);
     return 1;
@@ -774,7 +774,9 @@ static int reduce_online(pkm_plan* pl, const double* logp, const ReduceGeom& g, 
   double* pm = d_part;
   double* ps = d_part + nout * G;
   dim3 grid((unsigned)G, g.kt ? g.nt : 1, g.kv ? (g.nv + RED_VPC - 1) / RED_VPC : 1);
-  auto kern = reduce_minb(g) == 4 ? k_reduce_online<4> : k_reduce_online<3>;
+  const bool m4 = reduce_minb(g) == 4;
+  auto kern = per_contig > 0 ? (m4 ? k_reduce_online<4, true> : k_reduce_online<3, true>)
+                             : (m4 ? k_reduce_online<4, false> : k_reduce_online<3, false>);
   kern<<<grid, 256, smem, st>>>(logp, g, pl->d_log_dt, d_log_dv, pl->d_log_dz, d_log_lw, pl->d_exp_tab, pm, ps, d_gmax,
                                PB, nchunk, uniform_dv, per_contig);
   k_reduce_combine<<<(unsigned)((nout + 7) / 8), 256, 0, st>>>(pm, ps, nout, G, d_mx, d_sum);
