@@ -257,7 +257,7 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
             load(b);
             flush(a, s_exp);
             load(a);
-            flush(b, s_exp);
+            if (ib + 1 < nbatch) flush(b, s_exp);   // a batch wholly past the end holds only -inf
           }
         };
         if (nV > 1) {                            // rows = velocity bins, once per age
@@ -297,7 +297,7 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
               load(b, vb + RED_U);
               flush(a, s_exp);
               load(a, vb + 2 * RED_U);
-              flush(b, s_exp);
+              if (vb + RED_U < nV) flush(b, s_exp);
             }
           }
         }
@@ -329,7 +329,7 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
             load(b, tb + RED_U);
             flush(a, s_exp);
             load(a, tb + 2 * RED_U);
-            flush(b, s_exp);
+            if (tb + RED_U < nT) flush(b, s_exp);
           }
         }
       } else {
@@ -370,7 +370,7 @@ k_reduce_online(const double* __restrict__ logp, ReduceGeom g, const double* __r
             load(b, cb + cst * RED_U);
             flush(a, s_exp);
             load(a, cb + 2 * cst * RED_U);
-            flush(b, s_exp);
+            if (cb + cst * RED_U < clast) flush(b, s_exp);
           }
         }
       }
