@@ -699,30 +699,43 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
   }
 }
 
+// One Philox call, one log / sqrt / sincospi per PAIR of voxels (both Box-Muller outputs are used):
+// voxel with global index gi = offset + i takes the cosine (gi even) or sine (gi odd) deviate of the
+// pair gi >> 1, so the noise of a voxel depends on (seed, global index) only - not on how a cube
+// is cut into calls.  Thread = one aligned pair.
 __global__ void k_noise(const double* __restrict__ ybar, long long n, double snr, int mode,
                         unsigned long long seed, unsigned long long offset,
                         const double* __restrict__ d_max, double* __restrict__ yobs,
                         double* __restrict__ sigma_out) {
   double K = 0.0;
   if (mode == 0) K = sqrt(*d_max) / snr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const double y = ybar[i];
-    const double sg = (mode == 0) ? K * sqrt(y) : y / snr;
-    if (sigma_out) sigma_out[i] = sg;
+  const unsigned long long odd = offset & 1ull;          // the first voxel is the second of its pair
+  const long long npair = (n + (long long)odd + 1) >> 1;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < npair;
+       j += (long long)gridDim.x * blockDim.x) {
+    const long long i0 = 2 * j - (long long)odd, i1 = i0 + 1;   // local indices of the pair
+    const bool h0 = i0 >= 0, h1 = i1 < n;
+    const double y0 = h0 ? ybar[i0] : 0.0, y1 = h1 ? ybar[i1] : 0.0;
+    const double s0 = (mode == 0) ? K * sqrt(y0) : y0 / snr;
+    const double s1 = (mode == 0) ? K * sqrt(y1) : y1 / snr;
+    if (sigma_out) {
+      if (h0) sigma_out[i0] = s0;
+      if (h1) sigma_out[i1] = s1;
+    }
     if (yobs) {
-      const unsigned long long ctr = offset + (unsigned long long)i;
+      const unsigned long long ctr = (offset + (unsigned long long)(i0 + (long long)odd)) >> 1;
       uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x706b6d62u, 0u};
       philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-      // two 53-bit uniforms in (0,1]
+      // two 53-bit uniforms: u1 in (0,1], u2 in [0,1)
       const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1];
       const unsigned long long b = ((unsigned long long)c[2] << 32) | c[3];
       const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);
       const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
       double sn, cs;
       sincospi(2.0 * u2, &sn, &cs);
-      const double zn = sqrt(-2.0 * log(u1)) * cs;
-      yobs[i] = y + sg * zn;
+      const double r = sqrt(-2.0 * log(u1));
+      if (h0) yobs[i0] = y0 + s0 * (r * cs);
+      if (h1) yobs[i1] = y1 + s1 * (r * sn);
     }
   }
 }
@@ -918,7 +931,7 @@ void launch_max(const double* x, int64_t n, double* d_result, cudaStream_t st) {
 void launch_noise(const double* ybar, int64_t n, double snr, int mode, uint64_t seed, uint64_t offset,
                   const double* d_max, double* yobs, double* sigma, cudaStream_t st) {
   if (n <= 0) return;
-  int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  int grid = (int)std::min<int64_t>((n / 2 + 256) / 256, 148 * 16);
   k_noise<<<grid, 256, 0, st>>>(ybar, n, snr, mode, seed, offset, d_max, yobs, sigma);
   PKM_CUDA(cudaGetLastError());
 }

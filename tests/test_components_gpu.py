@@ -215,6 +215,25 @@ def test_mixture_moments_against_discrete(galaxy, base_component):
                 assert np.nanmedian(np.abs((a - b) / a)) < 1e-10, (dist, lw)
 
 
+def test_noise_depends_on_the_global_index_only(gpu_ok):
+    """pkm_noise draws one Philox / Box-Muller pair per two voxels, keyed on the GLOBAL voxel index
+    (offset + i): a cube cut into calls at odd or even offsets gets the noise of the single call."""
+    from popkinmocks_b200 import engine
+    rng = np.random.default_rng(4)
+    y = rng.random(1001) + 0.5
+    full, sig = engine.noise(y, 30.0, 1, seed=123, offset=10)
+    assert np.allclose(sig, y / 30.0, rtol=1e-15)
+    for lo, hi in ((0, 1), (0, 500), (1, 2), (3, 778), (500, 1001), (777, 1000), (1000, 1001)):
+        part, _ = engine.noise(y[lo:hi].copy(), 30.0, 1, seed=123, offset=10 + lo)
+        assert np.array_equal(part, full[lo:hi]), (lo, hi)
+    other, _ = engine.noise(y, 30.0, 1, seed=124, offset=10)
+    assert not np.array_equal(other, full)
+    z = (full - y) / sig
+    assert abs(z.mean()) < 0.15 and abs(z.std() - 1.0) < 0.1
+    # the two deviates of a pair are uncorrelated
+    assert abs(np.corrcoef(z[0:1000:2], z[1:1001:2])[0, 1]) < 0.15
+
+
 def test_shot_noise_is_noisier_than_constant_snr(galaxy):
     eps_shot = pkm.noise.ShotNoise(galaxy).get_noisy_data(snr=100) - galaxy.ybar
     eps_const = pkm.noise.ConstantSNR(galaxy).get_noisy_data(snr=100) - galaxy.ybar
