@@ -62,6 +62,7 @@ def test_density_path_matches_reference(gpu_ok, name, tags):
     {"PKM_COEFF_TMA_MODE": "0"},                                # staged kernel, plain loads
     {"PKM_COEFF_KERNEL": "0", "PKM_COEFF_GROUPS": "1"},         # staged kernel, one warp group
     {"PKM_COEFF_FLOW": "0"},                                    # octet kernel with CTA barriers + TMA tensor store
+    {"PKM_COEFF_APF": "0"},                                     # barrier-free kernel with a producer warp, one A-fragment set
 ])
 def test_coefficient_kernel_fallbacks_match_reference(gpu_ok, monkeypatch, env):
     """The default path uses the octet coefficient kernel; the staged kernel and its load modes
@@ -75,7 +76,8 @@ def test_coefficient_kernel_fallbacks_match_reference(gpu_ok, monkeypatch, env):
         assert rel_err(y, g[tag + "ybar"]) < TOL, (env, name, rel_err(y, g[tag + "ybar"]))
 
 
-@pytest.mark.parametrize("env", [{}, {"PKM_COEFF_FLOW": "0"}, {"PKM_COEFF_KERNEL": "0"}, {"PKM_COEFF_GENERIC": "1"}])
+@pytest.mark.parametrize("env", [{}, {"PKM_COEFF_APF": "0"}, {"PKM_COEFF_FLOW": "0"}, {"PKM_COEFF_KERNEL": "0"},
+                                 {"PKM_COEFF_GENERIC": "1"}])
 def test_density_special_values(gpu_ok, monkeypatch, env):
     """log p = -inf and log p < -708 are exact zeros of the density, NaN poisons its own pixel only
     (np.exp semantics, base.py:841): the rare-value branch of the fused table exponential, through
